@@ -1,0 +1,159 @@
+/* tlsan_b200.h -- C ABI of the B200-native TLSAN train / scoring hot path.
+ *
+ * The reference (TsingZ0/TLSAN) has no FFI: its boundary is the in-process Python surface
+ * `class Model` (TLSAN/model.py:13-313) fed by the 9-tuple of TLSAN/input.py:54,107.  Every
+ * entry point below names the reference call it replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (params, batch, workspace, outputs); nothing is allocated or freed behind the ABI;
+ *   - every call is asynchronous on the `cudaStream_t` passed as `void* stream`;
+ *   - return 0 on success, a negative TLSAN_E_* code otherwise; `tlsan_last_error()` returns
+ *     a thread-local description; no C++ exception crosses the ABI;
+ *   - indices are int32, values fp32; embedding rows are 128 B and must be 16-B aligned.
+ * The small attention weights are mirrored into one __constant__ bank per process: calls
+ * that read them upload in-stream first, so concurrent use from two streams must be
+ * serialised by the caller.
+ */
+#ifndef TLSAN_B200_H
+#define TLSAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLSAN_ABI_VERSION 1
+
+/* fixed architecture of the path (TLSAN/train.py:26-35 defaults; hidden_units must equal
+ * item+cate embedding size, model.py:100-109) */
+#define TLSAN_EMB 32        /* itemid/cateid/userid_embedding_size */
+#define TLSAN_HID 64        /* hidden_units */
+#define TLSAN_HEADS 8       /* num_heads */
+#define TLSAN_DH 8          /* hidden_units / num_heads */
+#define TLSAN_MAX_L 96      /* Ls <= 90 in the reference (build_dataset.py:7) */
+
+/* packed small-parameter vector (`dense`), float offsets.  TF variable names in
+ * tlsan_b200/model.py:DENSE_LAYOUT.  [k][j] row-major like the TF kernels (in x out). */
+#define TLSAN_OFF_W1L 0      /* long  FWA map1 W [8][8]   model.py:380-381,447 */
+#define TLSAN_OFF_B1L 64     /* long  FWA map1 bias [8] */
+#define TLSAN_OFF_W2L 72     /* long  FWA map2 W [8][8]   model.py:382-383 */
+#define TLSAN_OFF_B2L 136
+#define TLSAN_OFF_W1S 144    /* short FWA map1 W */
+#define TLSAN_OFF_B1S 208
+#define TLSAN_OFF_W2S 216
+#define TLSAN_OFF_B2S 280
+#define TLSAN_OFF_WD 288     /* tf.layers.dense kernel [64][64]  model.py:347 */
+#define TLSAN_OFF_BD 4384    /* tf.layers.dense bias [64] */
+#define TLSAN_OFF_GAMMA 4448 /* gamma_parameter  model.py:58-60 */
+#define TLSAN_DENSE_COUNT 4449
+#define TLSAN_DENSE_PAD 4452
+
+enum {
+  TLSAN_OK = 0,
+  TLSAN_E_DIMS = -1,      /* bad dimension (B<=0, L>TLSAN_MAX_L, ...) */
+  TLSAN_E_ALIGN = -2,     /* pointer not 16-B aligned */
+  TLSAN_E_NULL = -3,      /* required pointer is NULL */
+  TLSAN_E_WORKSPACE = -4, /* workspace too small */
+  TLSAN_E_CUDA = -5,      /* launch / runtime failure (cudaGetLastError) */
+  TLSAN_E_UNSUPPORTED = -6
+};
+
+typedef struct {
+  int32_t B;        /* rows in this (local) batch */
+  int32_t L;        /* Ls: width of hist_i / hist_t and of usert_emb   (train.py:29) */
+  int32_t S;        /* width of hist_i_new = max short length in batch (input.py:33,37) */
+  int32_t NI, NU, NC;
+  int32_t B_global; /* denominator of reduce_mean (model.py:171); = B on one GPU */
+  int32_t reserved;
+} tlsan_dims_t;
+
+/* Trainable state, model.py:56-81.  `emb` is ONE table: rows [0,NI) = item_emb,
+ * [NI,NI+NC) = cate_emb, [NI+NC,NI+NC+NU) = user_emb (32 floats each). */
+typedef struct {
+  float* emb;
+  float* usert;              /* usert_emb [NU][L] */
+  float* item_b;             /* [NI] */
+  float* dense;              /* [TLSAN_DENSE_PAD] */
+  const int32_t* icl;        /* item_cate_list [NI]  (model.py:85) */
+  const int32_t* cate_off;   /* [NC+1] CSR of items grouped by category (stable order) */
+  const int32_t* cate_items; /* [NI] */
+} tlsan_params_t;
+
+/* The 9-tuple of TLSAN/input.py:54 / :107 after the int64->int32 feed cast
+ * (model.py:210-222).  `i2` is batch[2] of the test tuple (negative item) or NULL. */
+typedef struct {
+  const int32_t* u;          /* batch[0] */
+  const int32_t* i;          /* batch[1] */
+  const int32_t* i2;         /* batch[2] as item (eval_auc) */
+  const float* y;            /* batch[2] as label (train) */
+  const int32_t* hist_i;     /* batch[3]  [B][L] */
+  const int32_t* hist_i_new; /* batch[4]  [B][S] */
+  const float* hist_t;       /* batch[5]  [B][L] */
+  const int32_t* sl;         /* batch[6] */
+  const int32_t* sl_new;     /* batch[7] */
+  const int32_t* c;          /* batch[8]  u_cate */
+} tlsan_batch_t;
+
+/* scalars a train step leaves on the device (index into `stats`) */
+enum {
+  TLSAN_STAT_LOSS = 0,     /* self.loss, model.py:171-172 */
+  TLSAN_STAT_BCE = 1,      /* reduce_mean(sigmoid_cross_entropy) */
+  TLSAN_STAT_NORM = 2,     /* global norm used by clip_by_global_norm, model.py:201 */
+  TLSAN_STAT_SCALE = 3,    /* clip multiplier */
+  TLSAN_STAT_L2 = 4,       /* l2_norm, model.py:164-169 */
+  TLSAN_STAT_COUNT = 8
+};
+
+int tlsan_abi_version(void);
+const char* tlsan_last_error(void);
+
+/* K2: n = sum_j [d >= 2^j], j=1..12, out = float32(1/n); d = 0 -> 0 (pad).
+ * Replaces proc_time_emb, TLSAN/build_dataset.py:16-21 (+ cast at input.py:36,45).
+ * `lut13` = device float[13], lut[n] = float32(1/n) built by the host. */
+int tlsan_time_bucket(const int32_t* d, const float* lut13, float* out, int32_t* bucket_out,
+                      int64_t n, void* stream);
+
+/* K1: out[r] = [ item_emb[idx[r]] || cate_emb[icl[idx[r]]] ] * (tau ? tau[r] : 1).
+ * Replaces the embedding_lookup/gather/concat/multiply group, model.py:84-86,105-113. */
+int tlsan_gather_concat(const tlsan_dims_t* dims, const tlsan_params_t* p, const int32_t* idx,
+                        const float* tau, float* out, int64_t n, void* stream);
+
+/* Forward only: logits for 1 (i) or 2 (i, i2) candidates per row.
+ * Replaces sess.run(self.logits, ...) in Model.eval_auc, model.py:237-263.
+ * logits: [B][ncand]; ut (optional): [B][64] = u_t of model.py:135. */
+int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                int32_t ncand, float* logits, float* ut, void* stream);
+
+/* bytes of workspace tlsan_train_step / tlsan_step_grads need for `dims`. */
+int tlsan_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes);
+
+/* One Model.train call (model.py:208-234): forward, loss, tf.gradients,
+ * clip_by_global_norm, GradientDescentOptimizer.apply_gradients, all on `stream`.
+ * `stats` = device float[TLSAN_STAT_COUNT]. */
+int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                     float lr, float reg, float clip_norm, void* workspace, size_t workspace_bytes,
+                     float* stats, void* stream);
+
+/* Data-parallel split of the same step.
+ * tlsan_step_grads: forward + backward on the local rows and the local deterministic
+ *   segmented reduce into ONE flat fp32 buffer `flat` of tlsan_flat_count() floats
+ *   (sparse-part table gradients, dense gradients, sum-of-squares and loss partials),
+ *   which the caller all-reduces (sum) across ranks;
+ * tlsan_apply_flat: L2 term + clip + SGD from the reduced buffer (identical on every rank). */
+int tlsan_flat_count(const tlsan_dims_t* dims, int64_t* count);
+int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                     void* workspace, size_t workspace_bytes, float* flat, void* stream);
+int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat,
+                     float lr, float reg, float clip_norm, void* workspace, size_t workspace_bytes,
+                     float* stats, void* stream);
+
+/* Full-catalogue ranking for Model.eval_prec / eval_recall (model.py:140-156,265-299):
+ * rank[b] = #items scored above label[b] under u_t . all_emb^T + item_b with top_k tie order. */
+int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut,
+                     const int32_t* label, int32_t* rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLSAN_B200_H */

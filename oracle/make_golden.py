@@ -87,7 +87,8 @@ def from_csr(d, prefix, is_test):
     """Inverse of to_csr: rebuild the list-of-tuples layout of build_dataset.py:58-59,71."""
     from oracle.tlsan_oracle import bucket_lut
     lut = bucket_lut().astype(np.float64)
-    g = lambda k: d[prefix + k]
+    cache = {k[len(prefix):]: np.asarray(d[k]) for k in d.keys() if k.startswith(prefix)}   # NpzFile re-reads per access
+    g = lambda k: cache[k]
     out = []
     po, no = g("pre_off"), g("new_off")
     pi, pb, nw = g("pre_items"), g("pre_bucket"), g("new_items")

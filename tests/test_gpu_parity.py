@@ -1,0 +1,244 @@
+"""CUDA path (through the C ABI) against the oracle on the same seeded inputs and weights.
+Tolerances (north star): logits / loss within 1e-4 relative in fp32, AUC equal to 4 decimals,
+index / bucket / gather outputs bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tlsan_oracle as O
+from tests.util import model_from_params, rel_err, synth_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cfg(NU, NI, NC, L=10):
+    return O.default_config(NU, NI, NC, Ls=L)
+
+
+def _params(cfg, seed=7):
+    return O.randomize_params(O.init_params(cfg, seed=1234), seed=seed)
+
+
+@pytest.fixture(scope="module")
+def dm_model(dm):
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    return cfg, params, model_from_params(params, dm.icl, cfg)
+
+
+def test_score_matches_oracle_digital_music(dm, dm_model):
+    cfg, params, model = dm_model
+    total_hit, total = 0.0, 0
+    for lo in range(0, len(dm.test_set), 128):
+        batch = O.collate_test(dm.test_set[lo:lo + 128], 10)
+        auc_ref, r1, r2 = O.eval_auc(params, dm.icl, batch, config=cfg)
+        pos = model.logits(batch, 1); neg = model.logits(batch, 2)
+        assert rel_err(pos, r1) < TOL and rel_err(neg, r2) < TOL
+        auc = model.eval_auc(None, batch)
+        assert round(float(auc), 4) == round(auc_ref, 4)
+        total_hit += auc * len(batch[0]); total += len(batch[0])
+    assert total == len(dm.test_set)
+
+
+def test_score_matches_committed_golden(dm, dm_model):
+    import os
+    from tests.util import GOLD
+    g = np.load(os.path.join(GOLD, "model_golden.npz"))
+    cfg, params, model = dm_model
+    batch = O.collate_test(dm.test_set[:128], 10)
+    assert rel_err(model.logits(batch, 1), g["test_f64_pos"]) < TOL
+    assert rel_err(model.logits(batch, 2), g["test_f64_neg"]) < TOL
+    assert round(float(model.eval_auc(None, batch)), 4) == round(float(g["test_f64_auc"]), 4)
+
+
+def _check_step(params, icl, cfg, batch, lr=1.0, **kw):
+    ref = O.train_step(params, icl, batch, lr, cfg, dtype=torch.float64)
+    model = model_from_params(params, icl, cfg, **kw)
+    loss = model.train(None, batch, lr)
+    stats = model._stats.cpu().numpy()
+    assert abs(loss - ref["loss"]) / abs(ref["loss"]) < TOL
+    assert abs(stats[2] - ref["norm_tf"]) / ref["norm_tf"] < TOL
+    assert stats[3] == 1.0 and ref["scale"] == 1.0          # clip never active: both norm defs agree
+    assert ref["norm_agg"] <= 5.0
+    sd = model.state_dict()
+    for k, v in ref["new_params"].items():
+        got = sd[k].numpy()
+        step = np.asarray(params[k], np.float64) - v         # lr * grad
+        err = np.max(np.abs(got - v))
+        bound = TOL * (np.max(np.abs(step)) + 1e-7) + 2e-7 * np.max(np.abs(v))
+        assert err <= bound, (k, err, bound)
+    return model, ref
+
+
+def test_train_step_matches_oracle_digital_music(dm):
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    for lo, bs in ((0, 32), (32, 32), (1000, 77), (5000, 1)):
+        _check_step(params, dm.icl, cfg, O.collate_train(dm.train_set[lo:lo + bs], 10))
+
+
+def test_train_step_matches_committed_golden(dm):
+    import os
+    from tests.util import GOLD
+    g = np.load(os.path.join(GOLD, "model_golden.npz"))
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    model = model_from_params(params, dm.icl, cfg)
+    loss = model.train(None, O.collate_train(dm.train_set[:32], 10), 1.0)
+    assert abs(loss - float(g["train_f64_loss"])) / float(g["train_f64_loss"]) < TOL
+    sd = model.state_dict()
+    for k in g.files:
+        if k.startswith("train_f64_grad/"):
+            name = k[len("train_f64_grad/"):]
+            grad = (np.asarray(params[name], np.float64) - sd[name].numpy().astype(np.float64)) / 1.0
+            assert np.max(np.abs(grad - g[k])) <= TOL * np.max(np.abs(g[k])) + 3e-7, name
+
+
+@pytest.mark.parametrize("B,L,S,full,dup", [
+    (1, 10, 1, False, False), (33, 10, 3, False, False), (64, 10, 18, True, False),
+    (50, 1, 1, True, False), (40, 90, 5, False, False), (32, 90, 2, True, False),
+    (257, 10, 4, False, True), (100, 37, 7, False, True)])
+def test_train_step_edge_shapes(B, L, S, full, dup):
+    rng = np.random.default_rng(B * 1000 + L)
+    NU, NI, NC = 50, 301, 7
+    cfg = _cfg(NU, NI, NC, L)
+    params = _params(cfg, seed=B)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    batch = synth_batch(rng, B, L, S, NI, NU, NC, full=full, dup_items=dup)
+    batch[3][0, 0] = 0                                         # id 0 as a real item
+    _check_step(params, icl, cfg, batch, lr=0.5)
+
+
+def test_sl_extremes_and_scoring_shapes():
+    rng = np.random.default_rng(5)
+    NU, NI, NC, L, S = 20, 100, 5, 10, 6
+    cfg = _cfg(NU, NI, NC, L)
+    params = _params(cfg)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    model = model_from_params(params, icl, cfg)
+    for B in (1, 31, 32, 33, 130):
+        batch = list(synth_batch(rng, B, L, S, NI, NU, NC, is_test=True))
+        batch[6][:] = 1; batch[3][:, 1:] = 0; batch[5][:, 1:] = 0      # sl = 1
+        if B > 2:
+            batch[6][1] = L; batch[3][1] = rng.integers(0, NI, L); batch[5][1] = 0.25
+        batch = tuple(batch)
+        ref1, _ = O.forward_logits(params, icl, batch, 1, config=cfg)
+        ref2, _ = O.forward_logits(params, icl, batch, 2, config=cfg)
+        assert rel_err(model.logits(batch, 1), ref1) < TOL
+        assert rel_err(model.logits(batch, 2), ref2) < TOL
+
+
+def test_multi_step_trajectory(dm):
+    """20 SGD steps from the same weights: loss curve and final AUC follow the oracle."""
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    model = model_from_params(params, dm.icl, cfg)
+    p = params
+    for step in range(20):
+        batch = O.collate_train(dm.train_set[step * 32:(step + 1) * 32], 10)
+        ref = O.train_step(p, dm.icl, batch, 1.0, cfg)
+        p = ref["new_params"]
+        loss = model.train(None, batch, 1.0)
+        assert abs(loss - ref["loss"]) / abs(ref["loss"]) < 5 * TOL, step
+    assert model.global_step.eval() == 20
+    tb = O.collate_test(dm.test_set[:512], 10)
+    auc_ref, _, _ = O.eval_auc(p, dm.icl, tb, config=cfg)
+    assert abs(float(model.eval_auc(None, tb)) - auc_ref) < 2.0 / 512
+
+
+def test_train_step_is_deterministic(dm):
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    batch = O.collate_train(dm.train_set[:512], 10)
+    outs = []
+    for _ in range(2):
+        model = model_from_params(params, dm.icl, cfg)
+        for _ in range(3):
+            model.train(None, batch, 1.0)
+        outs.append({k: v.numpy().copy() for k, v in model.state_dict().items()})
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_gather_concat_bit_exact():
+    from tlsan_b200 import _lib
+    rng = np.random.default_rng(3)
+    NU, NI, NC = 10, 500, 11
+    cfg = _cfg(NU, NI, NC)
+    params = _params(cfg)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    model = model_from_params(params, icl, cfg)
+    n = 1000
+    idx = rng.integers(0, NI, n).astype(np.int32)
+    tau = rng.standard_normal(n).astype(np.float32)
+    d_idx = torch.from_numpy(idx).cuda(); d_tau = torch.from_numpy(tau).cuda()
+    out = torch.empty(n, 64, device="cuda")
+    dims = model._dims(1, 1)
+    for t in (None, d_tau):
+        _lib.check(model._lib.tlsan_gather_concat(C.byref(dims), C.byref(model._params), d_idx.data_ptr(),
+                                                  t.data_ptr() if t is not None else None, out.data_ptr(), n,
+                                                  model._stream()))
+        ref = np.concatenate([params["item_emb"][idx], params["cate_emb"][icl[idx]]], -1)
+        if t is not None:
+            ref = ref * tau[:, None]
+        assert np.array_equal(out.cpu().numpy(), ref.astype(np.float32))
+
+
+def test_time_bucket_bit_exact():
+    from tlsan_b200 import _lib
+    lib = _lib.lib()
+    d = np.concatenate([np.arange(0, 5000), [8191, 8192, 10 ** 6, 2 ** 30]]).astype(np.int32)
+    dd = torch.from_numpy(d).cuda()
+    lut = torch.from_numpy(O.bucket_lut()).cuda()
+    out = torch.empty(len(d), device="cuda"); bk = torch.empty(len(d), dtype=torch.int32, device="cuda")
+    _lib.check(lib.tlsan_time_bucket(dd.data_ptr(), lut.data_ptr(), out.data_ptr(), bk.data_ptr(), len(d), None))
+    torch.cuda.synchronize()
+    ref_n = np.array([O.time_bucket(x) if x >= 2 else 0 for x in d])
+    assert np.array_equal(bk.cpu().numpy(), ref_n)
+    ref_v = np.array([O.time_weight(x) if x >= 2 else 0 for x in d], np.float32)
+    assert np.array_equal(out.cpu().numpy(), ref_v)
+
+
+def test_prec_recall_match_oracle(dm, dm_model):
+    cfg, params, model = dm_model
+    model.reset_metrics()
+    st_p, st_r = O.StreamingTopK(), O.StreamingTopK()
+    for lo in range(0, 512, 128):
+        batch = O.collate_test(dm.test_set[lo:lo + 128], 10)
+        scores = O.eval_logits_all(params, dm.icl, batch, dtype=torch.float64, config=cfg)
+        p_ref, _ = st_p.update(scores, batch[1])
+        _, r_ref = st_r.update(scores, batch[1])
+        p = model.eval_prec(None, batch); r = model.eval_recall(None, batch)
+        assert np.allclose(p, p_ref, atol=2e-3) and np.allclose(r, r_ref, atol=1e-2)
+    assert np.isclose(model.prec_10.eval(), p[1]) and np.isclose(model.recall_50.eval(), r[5])
+
+
+def test_errors_are_loud(dm, dm_model):
+    cfg, params, model = dm_model
+    batch = list(O.collate_test(dm.test_set[:8], 10))
+    bad = list(batch); bad[1] = np.array(batch[1]); bad[1][0] = 10 ** 6
+    with pytest.raises(IndexError):
+        model.eval_auc(None, tuple(bad))
+    with pytest.raises(ValueError):
+        model.eval_auc(None, O.collate_test(dm.test_set[:8], 7))
+    from tlsan_b200 import _lib
+    dims = model._dims(0, 1)
+    n = C.c_size_t()
+    assert model._lib.tlsan_workspace_bytes(C.byref(dims), C.byref(n)) == -1
+    assert b"B must be" in model._lib.tlsan_last_error()
+
+
+def test_save_restore_roundtrip(dm, dm_model, tmp_path):
+    cfg, params, model = dm_model
+    cfg2 = dict(cfg); cfg2["model_dir"] = str(tmp_path)
+    m = model_from_params(params, dm.icl, cfg2)
+    m.train(None, O.collate_train(dm.train_set[:32], 10), 1.0)
+    path = m.save(None)
+    m2 = model_from_params(O.init_params(cfg), dm.icl, cfg2)
+    m2.restore(None, path)
+    assert m2.global_step.eval() == 1
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k])

@@ -1,0 +1,72 @@
+"""ctypes binding of include/tlsan_b200.h.  No CPU fallback: if the CUDA library is missing
+or fails to load, importing the compute entry points raises."""
+import ctypes as C
+import os
+
+from .build import LIB
+
+DENSE_COUNT, DENSE_PAD, STAT_COUNT, MAX_L = 4449, 4452, 8, 96
+OFF = dict(W1L=0, B1L=64, W2L=72, B2L=136, W1S=144, B1S=208, W2S=216, B2S=280, WD=288, BD=4384, GAMMA=4448)
+STAT = dict(loss=0, bce=1, norm=2, scale=3, l2=4)
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "L", "S", "NI", "NU", "NC", "B_global", "reserved")]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("emb", "usert", "item_b", "dense", "icl", "cate_off", "cate_items")]
+
+
+class Batch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "i", "i2", "y", "hist_i", "hist_i_new", "hist_t", "sl", "sl_new", "c")]
+
+
+class TlsanError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    "tlsan_abi_version": (C.c_int, []),
+    "tlsan_last_error": (C.c_char_p, []),
+    "tlsan_time_bucket": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tlsan_gather_concat": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_void_p]),
+    "tlsan_score": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_int32, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
+    "tlsan_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),
+    "tlsan_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_float, C.c_float,
+                                   C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "tlsan_flat_count": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_int64)]),
+    "tlsan_step_grads": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_void_p, C.c_size_t,
+                                   C.c_void_p, C.c_void_p]),
+    "tlsan_apply_flat": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load tlsan_b200/libtlsan_b200.so (built by tlsan_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise TlsanError("CUDA library %s is missing: run `python -m tlsan_b200.build` "
+                             "(there is no CPU fallback)" % LIB)
+        h = C.CDLL(LIB)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        if h.tlsan_abi_version() != 1:
+            raise TlsanError("ABI version mismatch")
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TlsanError("tlsan_b200 error %d: %s" % (rc, lib().tlsan_last_error().decode()))

@@ -1,0 +1,163 @@
+// extern "C" entry points of include/tlsan_b200.h: argument validation + launch sequencing.
+#include <stdarg.h>
+#include <string.h>
+#include "tlsan_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tlsan_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define REQUIRE(cond, code, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      tlsan_set_error(__VA_ARGS__);   \
+      return code;                    \
+    }                                 \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int check_dims(const tlsan_dims_t* d) {
+  REQUIRE(d != nullptr, TLSAN_E_NULL, "dims is NULL");
+  REQUIRE(d->B > 0, TLSAN_E_DIMS, "B must be > 0 (got %d)", d->B);
+  REQUIRE(d->L >= 1 && d->L <= TLSAN_MAX_L, TLSAN_E_DIMS, "L must be in [1,%d] (got %d)", TLSAN_MAX_L, d->L);
+  REQUIRE(d->S >= 1, TLSAN_E_DIMS, "S must be >= 1 (got %d)", d->S);
+  REQUIRE(d->NI > 0 && d->NU > 0 && d->NC > 0, TLSAN_E_DIMS, "table sizes must be > 0");
+  REQUIRE((long long)d->NI + d->NC + d->NU < (1ll << 30), TLSAN_E_DIMS, "row space too large");
+  REQUIRE((long long)d->B * (d->L + d->S + 3) < (1ll << 31) - 1, TLSAN_E_DIMS, "B*(L+S+3) overflows int32");
+  return TLSAN_OK;
+}
+
+static int check_params(const tlsan_params_t* p, bool train) {
+  REQUIRE(p != nullptr, TLSAN_E_NULL, "params is NULL");
+  REQUIRE(p->emb && p->usert && p->item_b && p->dense && p->icl, TLSAN_E_NULL, "params has a NULL table");
+  REQUIRE(aligned16(p->emb) && aligned16(p->dense), TLSAN_E_ALIGN, "emb/dense must be 16-B aligned");
+  if (train) REQUIRE(p->cate_off && p->cate_items, TLSAN_E_NULL, "cate_off/cate_items required for training");
+  return TLSAN_OK;
+}
+
+static int check_batch(const tlsan_batch_t* b, bool train, int ncand) {
+  REQUIRE(b != nullptr, TLSAN_E_NULL, "batch is NULL");
+  REQUIRE(b->u && b->i && b->c && b->sl && b->sl_new && b->hist_i && b->hist_i_new && b->hist_t, TLSAN_E_NULL,
+          "batch has a NULL field");
+  if (train) REQUIRE(b->y != nullptr, TLSAN_E_NULL, "batch.y (labels) is NULL");
+  if (ncand > 1) REQUIRE(b->i2 != nullptr, TLSAN_E_NULL, "batch.i2 is NULL but ncand == 2");
+  return TLSAN_OK;
+}
+
+extern "C" {
+
+int tlsan_abi_version(void) { return TLSAN_ABI_VERSION; }
+const char* tlsan_last_error(void) { return g_err; }
+
+int tlsan_time_bucket(const int32_t* d, const float* lut13, float* out, int32_t* bucket_out, int64_t n,
+                      void* stream) {
+  REQUIRE(n >= 0, TLSAN_E_DIMS, "n < 0");
+  REQUIRE(d && lut13 && (out || bucket_out), TLSAN_E_NULL, "NULL argument");
+  return tlsan_launch_bucket(d, lut13, out, bucket_out, n, (cudaStream_t)stream);
+}
+
+int tlsan_gather_concat(const tlsan_dims_t* dims, const tlsan_params_t* p, const int32_t* idx, const float* tau,
+                        float* out, int64_t n, void* stream) {
+  REQUIRE(dims && p && p->emb && p->icl, TLSAN_E_NULL, "NULL argument");
+  REQUIRE(n >= 0, TLSAN_E_DIMS, "n < 0");
+  if (n == 0) return TLSAN_OK;
+  REQUIRE(idx && out, TLSAN_E_NULL, "idx/out is NULL");
+  REQUIRE(aligned16(p->emb) && aligned16(out), TLSAN_E_ALIGN, "emb/out must be 16-B aligned");
+  return tlsan_launch_gather(*dims, *p, idx, tau, out, n, (cudaStream_t)stream);
+}
+
+int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, int32_t ncand,
+                float* logits, float* ut, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, false))) return rc;
+  REQUIRE(ncand == 1 || ncand == 2, TLSAN_E_DIMS, "ncand must be 1 or 2 (got %d)", ncand);
+  if ((rc = check_batch(b, false, ncand))) return rc;
+  REQUIRE(logits != nullptr, TLSAN_E_NULL, "logits is NULL");
+  REQUIRE(ut == nullptr || aligned16(ut), TLSAN_E_ALIGN, "ut must be 16-B aligned");
+  return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
+}
+
+int tlsan_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(bytes != nullptr, TLSAN_E_NULL, "bytes is NULL");
+  *bytes = tlsan_ws_layout(*dims).total + 256;
+  return TLSAN_OK;
+}
+
+int tlsan_flat_count(const tlsan_dims_t* dims, int64_t* count) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(count != nullptr, TLSAN_E_NULL, "count is NULL");
+  *count = (int64_t)tlsan_ws_layout(*dims).flat_count;
+  return TLSAN_OK;
+}
+
+static char* ws_base(void* workspace) {
+  return reinterpret_cast<char*>(tlsan_align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+}
+
+int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
+                     size_t workspace_bytes, float* flat, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, true))) return rc;
+  if ((rc = check_batch(b, true, 1))) return rc;
+  REQUIRE(workspace && flat, TLSAN_E_NULL, "workspace/flat is NULL");
+  REQUIRE(aligned16(flat), TLSAN_E_ALIGN, "flat must be 16-B aligned");
+  const TlsanWs w = tlsan_ws_layout(*dims);
+  REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
+          w.total + 256);
+  char* ws = ws_base(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t* sorted_vals = nullptr;
+  if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
+  int grid_a = 0, grid_b = 0;
+  if ((rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st))) return rc;
+  if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, flat + w.f_dgrad, st))) return rc;
+  return tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+}
+
+int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
+                     float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, true))) return rc;
+  REQUIRE(workspace && flat && stats, TLSAN_E_NULL, "workspace/flat/stats is NULL");
+  REQUIRE(clip_norm > 0.f, TLSAN_E_DIMS, "clip_norm must be > 0");
+  const TlsanWs w = tlsan_ws_layout(*dims);
+  REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
+          w.total + 256);
+  char* ws = ws_base(workspace);
+  return tlsan_launch_apply(*dims, *p, w, ws, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, flat + w.f_dgrad, lr,
+                            reg, clip_norm, stats, (cudaStream_t)stream);
+}
+
+int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, float lr, float reg,
+                     float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(workspace != nullptr, TLSAN_E_NULL, "workspace is NULL");
+  const TlsanWs w = tlsan_ws_layout(*dims);
+  float* flat = reinterpret_cast<float*>(ws_base(workspace) + w.flat);
+  if ((rc = tlsan_step_grads(dims, p, b, workspace, workspace_bytes, flat, stream))) return rc;
+  return tlsan_apply_flat(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, stream);
+}
+
+int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut, const int32_t* label,
+                     int32_t* rank, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, false))) return rc;
+  REQUIRE(ut && label && rank, TLSAN_E_NULL, "NULL argument");
+  return tlsan_launch_label_rank(*dims, *p, ut, label, rank, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared declarations for the TLSAN sm_100a kernels (internal; the public surface is
+// include/tlsan_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/tlsan_b200.h"
+
+#define TLSAN_INVALID_KEY 0x7fffffff
+#define TLSAN_TILE 32          // samples per CTA tile in the fused kernels (8 warps x 4)
+#define TLSAN_THREADS 256
+#define TLSAN_MAX_GRID 592     // upper bound on persistent grid (148 SMs x 4)
+// per-CTA partial row: dense layout + [loss, sumsq, pad...]
+#define TLSAN_PART_LOSS TLSAN_DENSE_PAD
+#define TLSAN_PART_SUMSQ (TLSAN_DENSE_PAD + 1)
+#define TLSAN_PART 4456
+#define TLSAN_SORT_CHUNK 2048  // keys per warp in one radix pass
+
+void tlsan_set_error(const char* fmt, ...);
+
+#define TLSAN_CHECK_CUDA(expr)                                                      \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      tlsan_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return TLSAN_E_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define TLSAN_CHECK_LAUNCH(name)                                                    \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      tlsan_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
+      return TLSAN_E_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+static inline size_t tlsan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Workspace carve-up (byte offsets from a 256-B aligned base).
+struct TlsanWs {
+  int SLOTS;  // occurrence slots per sample: L long, S short, candidate, u_cate, user
+  int SI;     // slots with a 64-float payload (all but the user slot)
+  int PU;     // floats per user payload: 32 (user_emb grad) + L (usert_emb grad), padded to 4
+  int NR;     // unified row space NI + NC + NU
+  int64_t nocc;
+  int nchunks;
+  size_t keys_a, keys_b, vals_a, vals_b, hist, nvalid, seg_off;
+  size_t rows_i, rows_u, gscal, scratch, cpart;
+  size_t part_a, part_b, tsq, flat;
+  // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
+  size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
+  size_t total;
+};
+
+static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
+  TlsanWs w;
+  w.SLOTS = d.L + d.S + 3;
+  w.SI = d.L + d.S + 2;
+  w.PU = (int)tlsan_align_up(32 + d.L, 4);
+  w.NR = d.NI + d.NC + d.NU;
+  w.nocc = (int64_t)d.B * w.SLOTS;
+  w.nchunks = (int)((w.nocc + TLSAN_SORT_CHUNK - 1) / TLSAN_SORT_CHUNK);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = tlsan_align_up(o + bytes, 256); return r; };
+  w.keys_a = take(w.nocc * 4);
+  w.keys_b = take(w.nocc * 4);
+  w.vals_a = take(w.nocc * 4);
+  w.vals_b = take(w.nocc * 4);
+  w.hist = take((size_t)256 * w.nchunks * 4 + 1024);
+  w.nvalid = take(64);
+  w.seg_off = take((size_t)(w.NR + 2) * 4);
+  w.rows_i = take((size_t)d.B * w.SI * 64 * 4);
+  w.rows_u = take((size_t)d.B * w.PU * 4);
+  w.gscal = take((size_t)d.B * 4);
+  w.scratch = take((size_t)d.B * 256 * 4);
+  w.cpart = take((size_t)(d.NI + d.NC) * 32 * 4);
+  w.part_a = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
+  w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
+  w.tsq = take((size_t)TLSAN_MAX_GRID * 4 * 4);
+  w.f_gi = 0;
+  w.f_gb = (size_t)(d.NI + d.NC) * 64;
+  w.f_gu = w.f_gb + tlsan_align_up(d.NI, 4);
+  w.f_dgrad = w.f_gu + (size_t)d.NU * w.PU;
+  w.flat_count = w.f_dgrad + TLSAN_PART;
+  w.flat = take(w.flat_count * 4);
+  w.total = o;
+  return w;
+}
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`) ----
+int tlsan_launch_upload_consts(const float* dense, cudaStream_t st);
+int tlsan_launch_score(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
+                       float* logits, float* ut, cudaStream_t st);
+int tlsan_launch_fwd_bwd(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
+                         const TlsanWs& w, char* ws, int* grid_a, int* grid_b, cudaStream_t st);
+int tlsan_launch_gather(const tlsan_dims_t& d, const tlsan_params_t& p, const int32_t* idx, const float* tau,
+                        float* out, int64_t n, cudaStream_t st);
+int tlsan_launch_bucket(const int32_t* dd, const float* lut, float* out, int32_t* bucket, int64_t n,
+                        cudaStream_t st);
+int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
+                      char* ws, const int32_t** sorted_vals, cudaStream_t st);
+int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
+                            float* g_i, float* g_b, float* g_u, cudaStream_t st);
+int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, float* dgrad, cudaStream_t st);
+int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
+                       const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
+                       float reg, float clip, float* stats, cudaStream_t st);
+int tlsan_launch_label_rank(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
+                            int32_t* rank, cudaStream_t st);
+int tlsan_num_sms();

@@ -1,0 +1,294 @@
+// Gradient aggregation and the optimiser step (reference model.py:164-172,185-205):
+//   k_row_reduce   deterministic segmented reduce of the per-occurrence gradient rows
+//   k_finalize1    fixed-order sum of the per-CTA dense partials
+//   k_table_sumsq  sum of squares of the four L2-regularised tables (l2_loss, model.py:164-169)
+//   k_finalize2    global norm, clip scale, loss, SGD on the 4449 small parameters
+//   k_apply_rows / k_apply_cate   W <- W - lr * scale * (g_sparse + reg * W) for every table row
+//   k_label_rank   full-catalogue rank of the label item (model.py:140-156)
+#include "tlsan_common.cuh"
+
+// ------------------------------------------------------------------ segmented reduce
+// one warp per row of the unified row space; occurrences are visited in sorted (stable) order
+__global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int L, int S, int PU,
+                                                    const int* __restrict__ seg_off, const int* __restrict__ vals,
+                                                    const float* __restrict__ rows_i,
+                                                    const float* __restrict__ rows_u,
+                                                    const float* __restrict__ gscal, float* __restrict__ g_i,
+                                                    float* __restrict__ g_b, float* __restrict__ g_u) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int NR = NI + NC + NU;
+  if (r >= NR) return;
+  const int SLOTS = L + S + 3, SI = L + S + 2;
+  const int lo = seg_off[r], hi = seg_off[r + 1];
+  if (r < NI + NC) {
+    float2 acc = make_float2(0.f, 0.f);
+    float accb = 0.f;
+    for (int base = lo; base < hi; base += 32) {
+      const int mine = base + lane < hi ? vals[base + lane] : 0;
+      const int cnt = min(32, hi - base);
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const int occ = __shfl_sync(0xffffffffu, mine, k);
+        const int b = occ / SLOTS, j = occ - b * SLOTS;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(rows_i + ((size_t)b * SI + j) * 64) + lane);
+        acc.x += v.x; acc.y += v.y;
+        if (j == L + S) accb += __ldg(gscal + b);
+      }
+    }
+    reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
+    if (r < NI && lane == 0) g_b[r] = accb;
+  } else {
+    const int u = r - NI - NC;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = lo; base < hi; base += 32) {
+      const int mine = base + lane < hi ? vals[base + lane] : 0;
+      const int cnt = min(32, hi - base);
+      for (int k = 0; k < cnt; ++k) {
+        const int occ = __shfl_sync(0xffffffffu, mine, k);
+        const int b = occ / SLOTS;
+        const float* src = rows_u + (size_t)b * PU;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (lane + 32 * q < PU) acc[q] += __ldg(src + lane + 32 * q);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (lane + 32 * q < PU) g_u[(size_t)u * PU + lane + 32 * q] = acc[q];
+  }
+}
+
+// ------------------------------------------------------------------ dense partials
+__global__ void k_finalize1(const float* __restrict__ part_a, int grid_a, const float* __restrict__ part_b,
+                            int grid_b, float* __restrict__ dgrad) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= TLSAN_PART) return;
+  const bool from_a = (e >= TLSAN_OFF_W1S && e < TLSAN_OFF_WD) || (e >= TLSAN_OFF_WD && e < TLSAN_OFF_BD + 64) ||
+                      e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ;
+  const bool from_b = e < TLSAN_OFF_W1S || e == TLSAN_OFF_GAMMA || e == TLSAN_PART_SUMSQ;
+  float s = 0.f;
+  if (from_a)
+    for (int c = 0; c < grid_a; ++c) s += part_a[(size_t)c * TLSAN_PART + e];
+  if (from_b)
+    for (int c = 0; c < grid_b; ++c) s += part_b[(size_t)c * TLSAN_PART + e];
+  dgrad[e] = s;
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) r += sh[w];
+  return r;
+}
+
+// tsq[cta][4] = partial sum of squares of (item_emb, cate_emb, user_emb, usert_emb)
+__global__ void __launch_bounds__(256) k_table_sumsq(const float* __restrict__ emb, const float* __restrict__ usert,
+                                                     long long n_item, long long n_cate, long long n_user,
+                                                     long long n_usert, float* __restrict__ tsq) {
+  __shared__ float sh[8];
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_emb = n_item + n_cate + n_user;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_emb; e += stride) {
+    const float v = emb[e];
+    const int w = e < n_item ? 0 : (e < n_item + n_cate ? 1 : 2);
+    s[w] = fmaf(v, v, s[w]);
+  }
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_usert; e += stride) {
+    const float v = usert[e];
+    s[3] = fmaf(v, v, s[3]);
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float r = block_sum_256(s[w], sh);
+    if (threadIdx.x == 0) tsq[blockIdx.x * 4 + w] = r;
+  }
+}
+
+// global norm (TF style: un-aggregated slices, see oracle header), clip scale, loss, dense SGD
+__global__ void __launch_bounds__(256) k_finalize2(const float* __restrict__ dgrad, const float* __restrict__ tsq,
+                                                   int ntsq, float invB, float lr, float reg, float clip,
+                                                   float* __restrict__ dense, float* __restrict__ stats) {
+  __shared__ float sh[8];
+  __shared__ float s_scale;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < TLSAN_DENSE_COUNT; e += 256) s = fmaf(dgrad[e], dgrad[e], s);
+  const float dense_sq = block_sum_256(s, sh);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int c = 0; c < ntsq; ++c)
+      t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
+    const double sq = (double)dgrad[TLSAN_PART_SUMSQ] + (double)dense_sq + (double)reg * (double)reg * t;
+    const float norm = (float)sqrt(sq);
+    const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
+    const float l2 = (float)(0.5 * t);
+    const float bce = dgrad[TLSAN_PART_LOSS] * invB;
+    stats[TLSAN_STAT_LOSS] = bce + reg * l2;
+    stats[TLSAN_STAT_BCE] = bce;
+    stats[TLSAN_STAT_NORM] = norm;
+    stats[TLSAN_STAT_SCALE] = scale;
+    stats[TLSAN_STAT_L2] = l2;
+    s_scale = scale;
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  for (int e = threadIdx.x; e < TLSAN_DENSE_COUNT; e += 256) dense[e] -= lr * (dgrad[e] * scale);
+}
+
+// element-wise update of item_emb, user_emb, usert_emb and item_b from the reduced buffers
+__global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int L, int PU, float* __restrict__ emb,
+                                                    float* __restrict__ usert, float* __restrict__ item_b,
+                                                    const float* __restrict__ g_i, const float* __restrict__ g_b,
+                                                    const float* __restrict__ g_u, float lr, float reg,
+                                                    const float* __restrict__ stats) {
+  const float scale = stats[TLSAN_STAT_SCALE];
+  const long long n1 = (long long)NI * 32, n2 = n1 + (long long)NU * 32, n3 = n2 + (long long)NU * L, n4 = n3 + NI;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
+    if (e < n1) {
+      const long long r = e >> 5; const int q = (int)(e & 31);
+      const float w = emb[e];
+      emb[e] = w - lr * ((g_i[r * 64 + q] + reg * w) * scale);
+    } else if (e < n2) {
+      const long long x = e - n1; const long long u = x >> 5; const int q = (int)(x & 31);
+      float* wp = emb + (size_t)(NI + NC) * 32 + x;
+      const float w = *wp;
+      *wp = w - lr * ((g_u[u * PU + q] + reg * w) * scale);
+    } else if (e < n3) {
+      const long long x = e - n2; const long long u = x / L; const int t = (int)(x - u * L);
+      const float w = usert[x];
+      usert[x] = w - lr * ((g_u[u * PU + 32 + t] + reg * w) * scale);
+    } else {
+      const long long x = e - n3;
+      item_b[x] = item_b[x] - lr * (g_b[x] * scale);
+    }
+  }
+}
+
+// one CTA per category: sum the cate halves of its items' reduced rows in CSR order
+__global__ void __launch_bounds__(256) k_apply_cate(int NI, float* __restrict__ emb, const float* __restrict__ g_i,
+                                                    const int* __restrict__ cate_off,
+                                                    const int* __restrict__ cate_items, float lr, float reg,
+                                                    const float* __restrict__ stats) {
+  __shared__ float sh[8][32];
+  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lo = cate_off[k], hi = cate_off[k + 1];
+  float acc = 0.f;
+#pragma unroll 4
+  for (int n = lo + warp; n < hi; n += 8) acc += __ldg(g_i + (size_t)__ldg(cate_items + n) * 64 + 32 + lane);
+  sh[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float g = g_i[(size_t)(NI + k) * 64 + 32 + lane];   // direct u_cate occurrences
+#pragma unroll
+    for (int w = 0; w < 8; ++w) g += sh[w][lane];
+    const float scale = stats[TLSAN_STAT_SCALE];
+    float* wp = emb + (size_t)(NI + k) * 32 + lane;
+    const float w = *wp;
+    *wp = w - lr * ((g + reg * w) * scale);
+  }
+}
+
+// rank[b] = #{ j : s_j > s_label  or  (s_j == s_label and j < label) },  s = u_t . all_emb^T + item_b
+__global__ void __launch_bounds__(256) k_label_rank(int NI, const float* __restrict__ emb,
+                                                    const float* __restrict__ item_b, const int* __restrict__ icl,
+                                                    const float* __restrict__ ut, const int* __restrict__ label,
+                                                    int* __restrict__ rank) {
+  __shared__ float su[64];
+  __shared__ int scnt[8];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 64) su[threadIdx.x] = ut[(size_t)b * 64 + threadIdx.x];
+  __syncthreads();
+  auto score = [&](int j) {
+    const float4* pi = reinterpret_cast<const float4*>(emb + (size_t)j * 32);
+    const float4* pc = reinterpret_cast<const float4*>(emb + (size_t)(NI + __ldg(icl + j)) * 32);
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(pi + q);
+      s = fmaf(su[4 * q], v.x, s); s = fmaf(su[4 * q + 1], v.y, s);
+      s = fmaf(su[4 * q + 2], v.z, s); s = fmaf(su[4 * q + 3], v.w, s);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(pc + q);
+      s = fmaf(su[32 + 4 * q], v.x, s); s = fmaf(su[32 + 4 * q + 1], v.y, s);
+      s = fmaf(su[32 + 4 * q + 2], v.z, s); s = fmaf(su[32 + 4 * q + 3], v.w, s);
+    }
+    return s + __ldg(item_b + j);
+  };
+  const int lab = label[b];
+  const float sl = score(lab);
+  int cnt = 0;
+  for (int j = threadIdx.x; j < NI; j += 256) {
+    const float s = score(j);
+    cnt += (s > sl) || (s == sl && j < lab);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) scnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += scnt[w];
+    rank[b] = t;
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
+                            float* g_i, float* g_b, float* g_u, cudaStream_t st) {
+  k_row_reduce<<<(w.NR + 7) / 8, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, d.S, w.PU,
+                                               reinterpret_cast<const int*>(ws + w.seg_off), sorted_vals,
+                                               reinterpret_cast<const float*>(ws + w.rows_i),
+                                               reinterpret_cast<const float*>(ws + w.rows_u),
+                                               reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b, g_u);
+  TLSAN_CHECK_LAUNCH("k_row_reduce");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, float* dgrad, cudaStream_t st) {
+  k_finalize1<<<(TLSAN_PART + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.part_a), grid_a,
+                                                        reinterpret_cast<const float*>(ws + w.part_b), grid_b,
+                                                        dgrad);
+  TLSAN_CHECK_LAUNCH("k_finalize1");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
+                       const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
+                       float reg, float clip, float* stats, cudaStream_t st) {
+  float* tsq = reinterpret_cast<float*>(ws + w.tsq);
+  int ntsq = tlsan_num_sms() * 2;
+  if (ntsq > TLSAN_MAX_GRID) ntsq = TLSAN_MAX_GRID;
+  k_table_sumsq<<<ntsq, 256, 0, st>>>(p.emb, p.usert, (long long)d.NI * 32, (long long)d.NC * 32,
+                                      (long long)d.NU * 32, (long long)d.NU * d.L, tsq);
+  TLSAN_CHECK_LAUNCH("k_table_sumsq");
+  const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
+  k_finalize2<<<1, 256, 0, st>>>(dgrad, tsq, ntsq, invB, lr, reg, clip, p.dense, stats);
+  TLSAN_CHECK_LAUNCH("k_finalize2");
+  const long long n4 = (long long)d.NI * 32 + (long long)d.NU * 32 + (long long)d.NU * d.L + d.NI;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)tlsan_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  k_apply_rows<<<(unsigned)blocks, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert, p.item_b, g_i, g_b,
+                                                 g_u, lr, reg, stats);
+  TLSAN_CHECK_LAUNCH("k_apply_rows");
+  k_apply_cate<<<d.NC, 256, 0, st>>>(d.NI, p.emb, g_i, p.cate_off, p.cate_items, lr, reg, stats);
+  TLSAN_CHECK_LAUNCH("k_apply_cate");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_label_rank(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
+                            int32_t* rank, cudaStream_t st) {
+  k_label_rank<<<d.B, 256, 0, st>>>(d.NI, p.emb, p.item_b, p.icl, ut, label, rank);
+  TLSAN_CHECK_LAUNCH("k_label_rank");
+  return TLSAN_OK;
+}

@@ -1,0 +1,393 @@
+"""`Model`: the reference TLSAN/model.py surface on top of the sm_100a C-ABI library.
+
+Same constructor and methods as the reference class (TLSAN/model.py:13-313):
+
+    Model(config, item_cate_list)
+    train(sess, batch, lr, add_summary=False) -> loss      model.py:208-234
+    eval_auc(sess, batch) -> float                         model.py:237-263
+    eval_prec(sess, batch) / eval_recall(sess, batch)      model.py:265-299
+    save(sess) / restore(sess, path)                       model.py:302-313
+    global_step / global_epoch_step / global_epoch_step_op (``.eval()``)
+
+``sess`` is accepted and ignored (there is no TF session).  ``batch`` is the 9-tuple of
+TLSAN/input.py:54,107 (lists / numpy, any integer dtype): it is packed into ONE pinned host
+buffer, copied host->device once and handed to the CUDA kernels through the C ABI of
+include/tlsan_b200.h.  There is no CPU path: without the CUDA library every compute method
+raises.  PyTorch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes as C
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OFF, STAT, Batch, Dims, Params, check
+
+_L = "all/long_term/num_blocks0_0/long_term_layer/feature_wise_attention1/"
+_S = "all/short_term/num_blocks1_0/short_term_layer/feature_wise_attention2/"
+_D = "all/long_term/num_blocks0_0/dense/"
+# TF variable name -> (offset, shape) inside the packed `dense` vector (include/tlsan_b200.h)
+DENSE_LAYOUT = OrderedDict([
+    ("gamma_parameter", (OFF["GAMMA"], ())),
+    (_L + "bn_dense_map1/linear_map/W", (OFF["W1L"], (8, 8))),
+    (_L + "bn_dense_map1/linear_map/bias", (OFF["B1L"], (8,))),
+    (_L + "bn_dense_map2/linear_map/W", (OFF["W2L"], (8, 8))),
+    (_L + "bn_dense_map2/linear_map/bias", (OFF["B2L"], (8,))),
+    (_D + "kernel", (OFF["WD"], (64, 64))),
+    (_D + "bias", (OFF["BD"], (64,))),
+    (_S + "bn_dense_map1/linear_map/W", (OFF["W1S"], (8, 8))),
+    (_S + "bn_dense_map1/linear_map/bias", (OFF["B1S"], (8,))),
+    (_S + "bn_dense_map2/linear_map/W", (OFF["W2S"], (8, 8))),
+    (_S + "bn_dense_map2/linear_map/bias", (OFF["B2S"], (8,))),
+])
+TABLES = ("item_emb", "item_b", "user_emb", "usert_emb", "cate_emb")
+KS = (1, 10, 20, 30, 40, 50)                                  # model.py:144-156
+
+
+class _Var:
+    """Stands in for a non-trainable tf.Variable read with ``.eval()`` (train.py:94,194,...)."""
+
+    def __init__(self, value=0):
+        self.value = value
+
+    def eval(self, session=None):
+        return self.value
+
+
+class _Metric:
+    def __init__(self, fn):
+        self._fn = fn
+
+    def eval(self, session=None):
+        return self._fn()
+
+
+class _IncrOp:
+    def __init__(self, var):
+        self._var = var
+
+    def eval(self, session=None):
+        self._var.value += 1
+        return self._var.value
+
+
+class DeviceBatch:
+    """A batch resident in HBM: one packed int32 buffer + the C struct pointing into it."""
+
+    def __init__(self, buf, B, L, S, offs, is_test):
+        self.buf, self.B, self.L, self.S, self.is_test = buf, B, L, S, is_test
+        base = buf.data_ptr()
+        p = lambda k: base + 4 * offs[k]
+        self.offs = offs
+        self.c = Batch(u=p("u"), i=p("i"), i2=p("second") if is_test else None,
+                       y=None if is_test else p("second"), hist_i=p("hist_i"), hist_i_new=p("hist_i_new"),
+                       hist_t=p("hist_t"), sl=p("sl"), sl_new=p("sl_new"), c=p("c"))
+        self.nbytes = buf.numel() * 4
+
+
+def _pack_offsets(B, L, S):
+    offs, o = {}, 0
+    for name, n in (("u", B), ("i", B), ("second", B), ("c", B), ("sl", B), ("sl_new", B),
+                    ("hist_i", B * L), ("hist_i_new", B * S), ("hist_t", B * L)):
+        offs[name] = o
+        o += (n + 3) // 4 * 4
+    return offs, o
+
+
+class Model(object):
+    def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True):
+        self.config = config
+        if config.get("num_blocks", 1) != 1:
+            raise ValueError("num_blocks != 1 is ill-formed in the reference (model.py:331-364); unsupported")
+        if (config.get("hidden_units", 64), config.get("num_heads", 8)) != (64, 8) or any(
+                config.get(k, 32) != 32 for k in ("itemid_embedding_size", "userid_embedding_size",
+                                                  "cateid_embedding_size")):
+            raise ValueError("kernels are built for hidden_units=64, num_heads=8, embedding sizes 32")
+        if config.get("dropout", 0.0) != 0.0:
+            raise ValueError("dropout > 0 is not supported (reference default 0.0, train.py:30)")
+        if config.get("optimizer", "sgd") != "sgd":
+            raise ValueError("only the reference default optimizer 'sgd' is implemented (train.py:40)")
+        self._lib = _lib.lib()                                  # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _lib.TlsanError("tlsan_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.NI, self.NU, self.NC = int(config["item_count"]), int(config["user_count"]), int(config["cate_count"])
+        self.L = int(config["Ls"])
+        if not 1 <= self.L <= _lib.MAX_L:
+            raise ValueError("Ls must be in [1, %d]" % _lib.MAX_L)
+        self.reg = float(config.get("regulation_rate", 0.00005))
+        self.clip = float(config.get("max_gradient_norm", 5.0))
+        self.validate = validate
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+
+        icl = np.ascontiguousarray(np.asarray(item_cate_list, dtype=np.int32))
+        if icl.shape != (self.NI,) or icl.min() < 0 or icl.max() >= self.NC:
+            raise ValueError("item_cate_list must be int[item_count] with values in [0, cate_count)")
+        order = np.argsort(icl, kind="stable").astype(np.int32)
+        cate_off = np.zeros(self.NC + 1, np.int32)
+        np.cumsum(np.bincount(icl, minlength=self.NC), out=cate_off[1:])
+        dev = self.device
+        self.icl = torch.from_numpy(icl).to(dev)
+        self.cate_off = torch.from_numpy(cate_off).to(dev)
+        self.cate_items = torch.from_numpy(order).to(dev)
+
+        # ---- variables (model.py:56-81, 347, 443-454); glorot_uniform = tf.get_variable default
+        g = torch.Generator().manual_seed(seed)
+
+        def glorot(rows, cols):
+            lim = (6.0 / (rows + cols)) ** 0.5
+            return (torch.rand(rows, cols, generator=g) * 2 - 1) * lim
+
+        NR = self.NI + self.NC + self.NU
+        emb = torch.empty(NR, 32)
+        emb[:self.NI] = glorot(self.NI, 32)
+        emb[self.NI + self.NC:] = glorot(self.NU, 32)
+        emb[self.NI:self.NI + self.NC] = glorot(self.NC, 32)
+        self.emb = emb.to(dev)
+        self.item_emb = self.emb[:self.NI]
+        self.cate_emb = self.emb[self.NI:self.NI + self.NC]
+        self.user_emb = self.emb[self.NI + self.NC:]
+        self.item_b = torch.zeros(self.NI, device=dev)
+        self.usert_emb = torch.full((self.NU, self.L), -1.0, device=dev)
+        dense = torch.zeros(_lib.DENSE_PAD)
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            if name == "gamma_parameter":
+                dense[off] = 1.0
+            elif len(shape) == 2:
+                dense[off:off + shape[0] * shape[1]] = glorot(*shape).reshape(-1)
+        self.dense = dense.to(dev)
+        self._params = Params(emb=self.emb.data_ptr(), usert=self.usert_emb.data_ptr(),
+                              item_b=self.item_b.data_ptr(), dense=self.dense.data_ptr(),
+                              icl=self.icl.data_ptr(), cate_off=self.cate_off.data_ptr(),
+                              cate_items=self.cate_items.data_ptr())
+
+        self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
+        self._ws = None
+        self._flat = None
+        self._stage_cache = {}
+        self.last_h2d_bytes = 0
+        self.last_d2h_bytes = 0
+
+        # ---- step variables and streaming metrics (model.py:142-161)
+        self.global_step = _Var(0)
+        self.global_epoch_step = _Var(0)
+        self.global_epoch_step_op = _IncrOp(self.global_epoch_step)
+        self.reset_metrics()
+        for n, k in enumerate(KS):
+            setattr(self, "prec_%d" % k, _Metric(lambda n=n: self._metric(n, "p")))
+            setattr(self, "recall_%d" % k, _Metric(lambda n=n: self._metric(n, "r")))
+        self.train_writer = None
+        self.eval_writer = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _dims(self, B, S, B_global=None):
+        return Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC,
+                    B_global=int(B_global if B_global is not None else B), reserved=0)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, dims):
+        need = C.c_size_t()
+        check(self._lib.tlsan_workspace_bytes(C.byref(dims), C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def stage_batch(self, batch, is_test=False):
+        """Pack the input.py 9-tuple into pinned memory and copy it to the device (one H2D)."""
+        hist_i = np.asarray(batch[3])
+        hist_i_new = np.asarray(batch[4])
+        B, L = hist_i.shape
+        S = max(int(hist_i_new.shape[1]), 1)
+        if L != self.L:
+            raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (L, self.L))
+        offs, total = _pack_offsets(B, L, S)
+        key = (B, S)
+        if key not in self._stage_cache:
+            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(),)
+        host = self._stage_cache[key][0]
+        h = host.numpy()
+        hf = h.view(np.float32)
+
+        def put(name, arr, n):
+            h[offs[name]:offs[name] + n] = np.asarray(arr).reshape(-1)
+
+        put("u", batch[0], B); put("i", batch[1], B); put("c", batch[8], B)
+        put("sl", batch[6], B); put("sl_new", batch[7], B)
+        if is_test:
+            put("second", batch[2], B)
+        else:
+            hf[offs["second"]:offs["second"] + B] = np.asarray(batch[2], dtype=np.float32)
+        put("hist_i", hist_i, B * L)
+        if hist_i_new.shape[1] == 0:
+            h[offs["hist_i_new"]:offs["hist_i_new"] + B] = 0
+        else:
+            put("hist_i_new", hist_i_new, B * S)
+        hf[offs["hist_t"]:offs["hist_t"] + B * L] = np.asarray(batch[5], dtype=np.float32).reshape(-1)
+        if self.validate:
+            self._validate(h, offs, B, L, S, is_test)
+        dev = torch.empty(total, dtype=torch.int32, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        self.last_h2d_bytes = total * 4
+        return DeviceBatch(dev, B, L, S, offs, is_test)
+
+    def _validate(self, h, offs, B, L, S, is_test):
+        """Out-of-range ids raise, like tf.gather on CPU (InvalidArgumentError)."""
+        def rng(name, n, hi, lo=0):
+            a = h[offs[name]:offs[name] + n]
+            if a.min() < lo or a.max() >= hi:
+                raise IndexError("batch field %s out of range [%d, %d)" % (name, lo, hi))
+        rng("u", B, self.NU); rng("i", B, self.NI); rng("c", B, self.NC)
+        rng("hist_i", B * L, self.NI); rng("hist_i_new", B * S, self.NI)
+        rng("sl", B, L + 1, 1); rng("sl_new", B, S + 1, 0)
+        if is_test:
+            rng("second", B, self.NI)
+
+    # ------------------------------------------------------------------ training
+    def train_staged(self, db, lr, global_batch=None):
+        """One optimiser step on a device-resident batch; returns the device stats tensor
+        (index with ``tlsan_b200._lib.STAT``) without synchronising."""
+        Bg = global_batch if global_batch is not None else db.B * self.world
+        dims = self._dims(db.B, db.S, Bg)
+        ws = self._workspace(dims)
+        st = self._stream()
+        if self.world == 1:
+            check(self._lib.tlsan_train_step(C.byref(dims), C.byref(self._params), C.byref(db.c), lr, self.reg,
+                                             self.clip, ws.data_ptr(), ws.numel(), self._stats.data_ptr(), st))
+        else:
+            n = C.c_int64()
+            check(self._lib.tlsan_flat_count(C.byref(dims), C.byref(n)))
+            if self._flat is None or self._flat.numel() != n.value:
+                self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
+            check(self._lib.tlsan_step_grads(C.byref(dims), C.byref(self._params), C.byref(db.c), ws.data_ptr(),
+                                             ws.numel(), self._flat.data_ptr(), st))
+            torch.distributed.all_reduce(self._flat, group=self.pg)
+            check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
+                                             self.reg, self.clip, ws.data_ptr(), ws.numel(),
+                                             self._stats.data_ptr(), st))
+        self.global_step.value += 1
+        return self._stats
+
+    def train(self, sess, batch, lr, add_summary=False):
+        """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op]."""
+        db = self.stage_batch(batch, is_test=False)
+        stats = self.train_staged(db, float(lr))
+        loss = float(stats[STAT["loss"]].item())
+        self.last_d2h_bytes = 4
+        if add_summary and self.train_writer is not None:
+            self.train_writer.add_scalar("Training Loss", loss, self.global_step.eval())
+        return loss
+
+    # ------------------------------------------------------------------ scoring
+    def score_staged(self, db, ncand=1, want_ut=False):
+        dims = self._dims(db.B, db.S)
+        logits = torch.empty(db.B, ncand, dtype=torch.float32, device=self.device)
+        ut = torch.empty(db.B, 64, dtype=torch.float32, device=self.device) if want_ut else None
+        check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(db.c), ncand,
+                                    logits.data_ptr(), ut.data_ptr() if want_ut else None, self._stream()))
+        return logits, ut
+
+    def logits(self, batch, cand_index=1):
+        """sess.run(self.logits, ...) with ``self.i = batch[cand_index]`` (model.py:239-261)."""
+        b = list(batch)
+        b[1] = batch[cand_index]
+        b[2] = batch[cand_index]
+        db = self.stage_batch(tuple(b), is_test=True)
+        lg, _ = self.score_staged(db, 1)
+        return lg[:, 0].cpu().numpy()
+
+    def eval_auc(self, sess, batch):
+        """Reference Model.eval_auc (model.py:237-263): mean(logit(pos) - logit(neg) > 0)."""
+        db = self.stage_batch(batch, is_test=True)
+        lg, _ = self.score_staged(db, 2)
+        res = lg.cpu().numpy()
+        self.last_d2h_bytes = res.nbytes
+        return np.mean(res[:, 0] - res[:, 1] > 0)
+
+    def _update_topk(self, batch):
+        db = self.stage_batch(batch, is_test=True)
+        _, ut = self.score_staged(db, 1, want_ut=True)
+        dims = self._dims(db.B, db.S)
+        rank = torch.empty(db.B, dtype=torch.int32, device=self.device)
+        label = db.buf[db.offs["i"]:db.offs["i"] + db.B]
+        check(self._lib.tlsan_label_rank(C.byref(dims), C.byref(self._params), ut.data_ptr(), label.data_ptr(),
+                                         rank.data_ptr(), self._stream()))
+        return rank.cpu().numpy()
+
+    def _metric(self, n, which):
+        tp, other = (self._ptp[n], self._pfp[n]) if which == "p" else (self._rtp[n], self._rfn[n])
+        return float(tp / (tp + other)) if tp + other > 0 else float("nan")
+
+    def eval_prec(self, sess, batch):
+        """Reference Model.eval_prec (model.py:265-281): run the six precision_at_k update ops and
+        return their values.  The accumulators are never reset by the reference driver
+        (train.py:75-76,82), so values are cumulative; ``reset_metrics`` re-initialises them."""
+        rank = self._update_topk(batch)
+        for n, k in enumerate(KS):
+            hit = float(np.sum(rank < k))
+            self._ptp[n] += hit
+            self._pfp[n] += len(rank) * k - hit
+        return [self._metric(n, "p") for n in range(len(KS))]
+
+    def eval_recall(self, sess, batch):
+        """Reference Model.eval_recall (model.py:283-299)."""
+        rank = self._update_topk(batch)
+        for n, k in enumerate(KS):
+            hit = float(np.sum(rank < k))
+            self._rtp[n] += hit
+            self._rfn[n] += len(rank) - hit
+        return [self._metric(n, "r") for n in range(len(KS))]
+
+    def reset_metrics(self):
+        """sess.run(tf.initialize_variables(metric_ops)) of train.py:75-76."""
+        self._ptp = np.zeros(len(KS)); self._pfp = np.zeros(len(KS))
+        self._rtp = np.zeros(len(KS)); self._rfn = np.zeros(len(KS))
+
+    # ------------------------------------------------------------------ state
+    def state_dict(self):
+        """All trainable variables keyed by their TF names (model.py:56-81, scopes :328-364)."""
+        sd = OrderedDict()
+        sd["item_emb"] = self.item_emb.detach().cpu().clone()
+        sd["item_b"] = self.item_b.detach().cpu().clone()
+        sd["user_emb"] = self.user_emb.detach().cpu().clone()
+        sd["usert_emb"] = self.usert_emb.detach().cpu().clone()
+        sd["cate_emb"] = self.cate_emb.detach().cpu().clone()
+        dense = self.dense.detach().cpu()
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            n = int(np.prod(shape)) if shape else 1
+            sd[name] = dense[off:off + n].reshape(shape).clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        for name in TABLES:
+            getattr(self, name).copy_(torch.as_tensor(np.asarray(sd[name]), dtype=torch.float32))
+        dense = self.dense.detach().cpu().clone()
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            n = int(np.prod(shape)) if shape else 1
+            dense[off:off + n] = torch.as_tensor(np.asarray(sd[name]), dtype=torch.float32).reshape(-1)
+        self.dense.copy_(dense)
+
+    def save(self, sess=None):
+        """Reference Model.save (model.py:302-308): <model_dir>/TLSAN-<step> + config JSON."""
+        os.makedirs(self.config["model_dir"], exist_ok=True)
+        checkpoint_path = os.path.join(self.config["model_dir"], "TLSAN")
+        step = self.global_step.eval()
+        save_path = "%s-%d" % (checkpoint_path, step)
+        torch.save({"variables": self.state_dict(), "global_step": step,
+                    "global_epoch_step": self.global_epoch_step.eval()}, save_path)
+        json.dump(dict(self.config), open("%s-%d.json" % (checkpoint_path, step), "w"), indent=2)
+        print("model saved at %s" % save_path, flush=True)
+        return save_path
+
+    def restore(self, sess, path):
+        """Reference Model.restore (model.py:310-313)."""
+        ck = torch.load(path, weights_only=False)
+        self.load_state_dict(ck["variables"])
+        self.global_step.value = int(ck["global_step"])
+        self.global_epoch_step.value = int(ck["global_epoch_step"])
+        print("model restored from %s" % path, flush=True)
