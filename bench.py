@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- TLSAN train-step throughput on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--batch B] [--Ls L] [--no-cpu-baseline]
+
+Workload (BASELINE.json configs[1]): "TLSAN Electronics-shape synthetic (40k users, 22k items,
+673 cates) fp32": NU 39 991, NI 22 048, NC 673, generators of SURVEY.md section 8d config 2
+(numpy default_rng(1234 + rank)), per-GPU batch 65 536, Ls 10.  A step = one Model.train step
+(forward, loss, backward, segmented reduce, L2 + clip + SGD over every table row).
+
+  value : train samples/s, all ranks, device-resident batches (several distinct batches cycled)
+  e2e   : the same step through Model.train(sess, batch, lr) with HOST numpy batches
+          (pack -> pinned -> H2D -> step -> loss D2H inside the timed region)
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NU, NI, NC = 39991, 22048, 673
+N_SAMPLES = 561100
+# Digital-Music empirical laws: P(min(len,10) = k), k = 1..10 ; short length pmf
+P_LONG = np.array([7.0, 6.9, 6.7, 6.5, 6.3, 5.9, 5.2, 4.5, 3.9, 47.1]) / 100.0
+P_SHORT_HEAD = np.array([.8724, .0886, .0223, .0085, .0040])
+S_MAX = 18
+
+
+def synth_batches(rng, n_batches, B, L):
+    """Electronics-shape synthetic batches in the TLSAN/input.py layout."""
+    p_long = P_LONG / P_LONG.sum()
+    tail = np.full(S_MAX - 5, (1.0 - P_SHORT_HEAD.sum()) / (S_MAX - 5))
+    p_short = np.concatenate([P_SHORT_HEAD, tail])
+    p_short /= p_short.sum()
+    out = []
+    for _ in range(n_batches):
+        frac = rng.choice(10, B, p=p_long) + 1                           # law of min(len, 10)
+        sl = np.maximum(1, np.round(frac * (L / 10.0))).astype(np.int64) if L != 10 else frac.astype(np.int64)
+        new_sl = (rng.choice(S_MAX, B, p=p_short) + 1).astype(np.int64)
+        S = int(new_sl.max())
+        hist_i = rng.integers(0, NI, (B, L)).astype(np.int64)
+        hist_i_new = rng.integers(0, NI, (B, S)).astype(np.int64)
+        n = np.sort(rng.integers(1, 13, (B, L)), axis=1)[:, ::-1]        # bucket non-increasing in t
+        hist_t = (1.0 / n).astype(np.float32)
+        col = np.arange(L)[None, :]
+        hist_i[col >= sl[:, None]] = 0
+        hist_t[col >= sl[:, None]] = 0
+        hist_i_new[np.arange(S)[None, :] >= new_sl[:, None]] = 0
+        out.append((rng.integers(0, NU, B).astype(np.int64), rng.integers(0, NI, B).astype(np.int64),
+                    rng.integers(0, 2, B).astype(np.int64), hist_i, hist_i_new, hist_t, sl, new_sl,
+                    rng.integers(0, NC, B).astype(np.int64)))
+    return out
+
+
+def algorithmic_bytes(batch, L):
+    """SURVEY.md 8d byte model, evaluated on the actual lengths of `batch`.  Returns per-batch
+    totals: (scoring1, train_per_sample_total, fused_a, bwd_long)."""
+    sl = np.asarray(batch[6], np.int64); s = np.asarray(batch[7], np.int64)
+    B = len(sl); S = batch[4].shape[1]
+    R = 2 * (sl + s) + 4
+    scoring1 = 4 * (2 * L + S + 6) + 4 * (sl + s + 1) + 128 * R + (4 * L + 4) + 4
+    train = scoring1 + 2 * (128 * R + 4 * sl + 4) + 4
+    fused_a = scoring1 + 128 * (2 * s + 4) + 4            # reads of the forward + short/cand/user grad rows
+    bwd_long = 4 * 2 * L + 4 * sl + 128 * 2 * sl + 4 * L + 128 * 2 * sl + 4 * sl
+    return int(scoring1.sum()), int(train.sum()), int(fused_a.sum()), int(bwd_long.sum()), B
+
+
+def table_bytes(L):
+    return 4 * (33 * NI + 32 * NU + L * NU + 32 * NC)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(L, budget_s, B=1024, seed=99):
+    """Oracle (torch-CPU restatement of model.py) train steps on a bounded sample of the workload."""
+    import torch
+    from oracle import tlsan_oracle as O
+    rng = np.random.default_rng(seed)
+    cfg = O.default_config(NU, NI, NC, Ls=L)
+    params = O.init_params(cfg, seed=1234)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    batches = synth_batches(rng, 4, B, L)
+    O.train_step(params, icl, batches[0], 1.0, cfg)                     # warm-up
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        r = O.train_step(params, icl, batches[n % 4], 1.0, cfg)
+        params = r["new_params"]
+        n += 1
+    dt = time.perf_counter() - t0
+    return n * B / dt, torch.get_num_threads(), "%d steps of B=%d, L=%d, Electronics-shape synthetic (%.1f s)" % (
+        n, B, L, dt)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (TF 1.8 cannot be installed), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import tlsan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = 2048
+    rng = np.random.default_rng(1234)
+    cfg = O.default_config(NU, NI, NC, Ls=args.Ls)
+    params = O.init_params(cfg, seed=1234)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    batches = synth_batches(rng, 4, B, args.Ls)
+    for w in range(args.warmup):
+        params = O.train_step(params, icl, batches[w % 4], 1.0, cfg)["new_params"]
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        params = O.train_step(params, icl, batches[k % 4], 1.0, cfg)["new_params"]
+    dt = time.perf_counter() - t0
+    v = args.steps * B / dt
+    sample = "each step = B=%d rows of the Electronics-shape workload (bounded sample of the 65536-row step)" % B
+    print(json.dumps({
+        "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, B):
+    return {"workload": "TLSAN Electronics-shape synthetic (NU 39991, NI 22048, NC 673), train step "
+                        "(fwd+bwd+L2+clip+SGD)", "per_gpu_batch": B, "global_batch": B * args.gpus,
+            "Ls": args.Ls, "short_max": S_MAX, "lr": 1.0, "optimizer": "sgd", "parallelism": "dp%d" % args.gpus,
+            "l2_policy": "several distinct device-resident batches cycled; per-step working set "
+                         "(gradient rows + tables + batch) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--Ls", type=int, default=10)
+    ap.add_argument("--resident", type=int, default=6, help="distinct device-resident batches")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tlsan_b200 import _lib
+    from tlsan_b200.model import Model
+    from oracle import tlsan_oracle as O            # config defaults + cpu_baseline leg only
+
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pg = dist.group.WORLD
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    B, L = args.batch, args.Ls
+    cfg = O.default_config(NU, NI, NC, Ls=L)
+    icl = np.random.default_rng(1234).integers(0, NC, NI).astype(np.int32)     # same on every rank
+    model = Model(cfg, icl, seed=1234, process_group=pg)
+    rng = np.random.default_rng(1234 + 1000 * rank)
+    host_batches = synth_batches(rng, args.resident, B, L)
+    dev_batches = [model.stage_batch(b) for b in host_batches]
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timed region
+    for w in range(args.warmup):
+        model.train_staged(dev_batches[w % len(dev_batches)], 1.0)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.tlsan_launch_count()
+    _lib.check(lib.tlsan_profile_begin(args.steps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        model.train_staged(dev_batches[k % len(dev_batches)], 1.0)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    phase = np.zeros((args.steps, len(_lib.PHASES)), np.float32)
+    nrec = C.c_int32()
+    _lib.check(lib.tlsan_profile_end(phase.ctypes.data, C.byref(nrec)))
+    launches = lib.tlsan_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss = float(model._stats[0].item())
+
+    # ---------------- end to end through Model.train with host batches
+    for w in range(2):
+        model.train(None, host_batches[w % len(host_batches)], 1.0)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        model.train(None, host_batches[k % len(host_batches)], 1.0)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e2e.item())
+    h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
+
+    # ---------------- scoring (eval_auc-style, 2 candidates) device-resident
+    test_b = list(host_batches[0]); test_b[2] = host_batches[1][1]
+    db = model.stage_batch(tuple(test_b), is_test=True)
+    for _ in range(3):
+        model.score_staged(db, 2)
+    barrier()
+    e0.record()
+    for _ in range(10):
+        model.score_staged(db, 2)
+    e1.record()
+    barrier()
+    ms_score = e0.elapsed_time(e1) / 10
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (CUDA events recorded around it on its stream)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ph = phase[:nrec.value].mean(axis=0)
+    per_batch = [algorithmic_bytes(b, L) for b in host_batches]
+    used = [per_batch[k % len(per_batch)] for k in range(args.steps)]
+    a_bytes = float(np.mean([u[2] for u in used])); b_bytes = float(np.mean([u[3] for u in used]))
+    train_bytes = float(np.mean([u[1] for u in used])) + 2 * table_bytes(L) + 2 * 4 * 4449
+    ia, ib = _lib.PHASES.index("fused_a"), _lib.PHASES.index("bwd_long")
+    if ph[ia] >= ph[ib]:
+        kname, kbytes, kms = "k_fused<true>", a_bytes, float(ph[ia])
+    else:
+        kname, kbytes, kms = "k_bwd_long", b_bytes, float(ph[ib])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname)
+    except Exception:
+        pass
+    achieved = kbytes / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": kms, "algorithmic_bytes_per_launch": kbytes,
+                "phases_ms": {n: float(v) for n, v in zip(_lib.PHASES, ph)},
+                "step": {"algorithmic_bytes": train_bytes,
+                         "achieved": train_bytes / (ms / args.steps * 1e-3) / 1e9,
+                         "frac": train_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample = cpu_port_throughput(L, args.cpu_budget)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": "train_samples_per_s", "value": args.steps * B * world / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B),
+        "e2e": {"value": e2e_steps * B * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        "eval": {"metric": "eval_seqs_per_s", "value": B * world / (ms_score * 1e-3), "unit": "seqs/s",
+                 "candidates": 2},
+        "final_loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

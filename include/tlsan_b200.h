@@ -153,6 +153,23 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
 int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut,
                      const int32_t* label, int32_t* rank, void* stream);
 
+/* Instrumentation for bench.py (not on the product path).
+ * tlsan_launch_count: kernels launched by this library since load (all threads).
+ * tlsan_profile_begin(max_steps): from now on every tlsan_step_grads / tlsan_apply_flat records
+ *   CUDA events on its stream at phase boundaries; tlsan_profile_end waits for them and fills
+ *   ms[step][TLSAN_PHASE_COUNT] (elapsed per phase), returning the number of steps recorded. */
+enum {
+  TLSAN_PHASE_SORT = 0,    /* keys + radix sort + segment bounds */
+  TLSAN_PHASE_FUSED_A = 1, /* k_fused<train>: forward, loss, backward of logit/short/dense */
+  TLSAN_PHASE_BWD_LONG = 2,/* k_bwd_long */
+  TLSAN_PHASE_REDUCE = 3,  /* k_finalize1 + k_row_reduce */
+  TLSAN_PHASE_APPLY = 4,   /* table sumsq, finalize2, row / cate updates */
+  TLSAN_PHASE_COUNT = 5
+};
+long long tlsan_launch_count(void);
+int tlsan_profile_begin(int32_t max_steps);
+int tlsan_profile_end(float* ms, int32_t* steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,85 @@
+"""The C-ABI library: builds, loads, exports every symbol include/tlsan_b200.h declares, and
+rejects bad arguments before touching the GPU (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tlsan_b200 import _lib
+from tlsan_b200.build import LIB, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "tlsan_b200.h")).read()
+    declared = set(re.findall(r"\b(tlsan_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    raw = C.CDLL(LIB)
+    for name in sorted(declared):
+        assert hasattr(raw, name), "missing export %s" % name
+    assert declared == set(_lib.EXPORTS)
+    assert lib.tlsan_abi_version() == 1
+
+
+def test_constants_match_header():
+    hdr = open(os.path.join(ROOT, "include", "tlsan_b200.h")).read()
+    d = dict(re.findall(r"#define TLSAN_(\w+) (\d+)", hdr))
+    assert int(d["DENSE_COUNT"]) == _lib.DENSE_COUNT and int(d["DENSE_PAD"]) == _lib.DENSE_PAD
+    for k, v in _lib.OFF.items():
+        assert int(d["OFF_" + k]) == v
+    assert int(d["MAX_L"]) == _lib.MAX_L
+    assert C.sizeof(_lib.Dims) == 32 and C.sizeof(_lib.Params) == 56 and C.sizeof(_lib.Batch) == 80
+
+
+def test_argument_validation_without_gpu(lib):
+    n = C.c_size_t()
+    good = _lib.Dims(B=64, L=10, S=3, NI=100, NU=50, NC=5, B_global=64, reserved=0)
+    assert lib.tlsan_workspace_bytes(C.byref(good), C.byref(n)) == 0 and n.value > 64 * 15 * 256
+    cnt = C.c_int64()
+    assert lib.tlsan_flat_count(C.byref(good), C.byref(cnt)) == 0
+    assert cnt.value == 105 * 64 + 100 + 50 * 44 + 4456
+    for field, val, msg in (("B", 0, b"B must"), ("L", 97, b"L must"), ("S", 0, b"S must"), ("NI", 0, b"table")):
+        bad = _lib.Dims(B=64, L=10, S=3, NI=100, NU=50, NC=5, B_global=64, reserved=0)
+        setattr(bad, field, val)
+        assert lib.tlsan_workspace_bytes(C.byref(bad), C.byref(n)) == -1
+        assert msg in lib.tlsan_last_error()
+    p, b = _lib.Params(), _lib.Batch()
+    assert lib.tlsan_score(C.byref(good), C.byref(p), C.byref(b), 1, None, None, None) == -3      # NULL tables
+    assert lib.tlsan_score(C.byref(good), None, C.byref(b), 1, None, None, None) == -3
+    assert lib.tlsan_train_step(C.byref(good), C.byref(p), C.byref(b), 1.0, 0.0, 5.0, None, 0, None, None) == -3
+    p.emb = 8; p.usert = 16; p.item_b = 16; p.dense = 16; p.icl = 16                             # misaligned emb
+    assert lib.tlsan_score(C.byref(good), C.byref(p), C.byref(b), 1, None, None, None) == -2
+    with pytest.raises(_lib.TlsanError):
+        _lib.check(-2)
+
+
+def test_model_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tlsan_b200.model import Model
+    with pytest.raises(_lib.TlsanError):
+        Model({"item_count": 10, "user_count": 10, "cate_count": 3, "Ls": 10}, [0] * 10)
+
+
+def test_product_package_never_imports_the_oracle():
+    import ast
+    for root, _, files in os.walk(os.path.join(ROOT, "tlsan_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(root, f)).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or ""]
+                    assert not any(n.split(".")[0] == "oracle" for n in names), f

@@ -46,8 +46,12 @@ _SIGS = {
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
+    "tlsan_launch_count": (C.c_longlong, []),
+    "tlsan_profile_begin": (C.c_int, [C.c_int32]),
+    "tlsan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
 }
 EXPORTS = tuple(_SIGS)
+PHASES = ("sort", "fused_a", "bwd_long", "reduce", "apply")
 
 
 def lib():

@@ -12,6 +12,23 @@ void tlsan_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+long long g_tlsan_launches = 0;
+
+// ---- optional phase timing (bench.py): events recorded on the caller's stream
+static cudaEvent_t* g_ev = nullptr;      // [max_steps][TLSAN_PHASE_COUNT + 1]
+static int g_ev_steps_cap = 0, g_ev_step = -1;
+static bool g_prof_on = false;
+
+void tlsan_profile_mark(int phase_done, cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (phase_done < 0) {
+    if (g_ev_step + 1 >= g_ev_steps_cap) { g_prof_on = false; return; }
+    ++g_ev_step;
+  }
+  if (g_ev_step < 0) return;
+  cudaEventRecord(g_ev[(size_t)g_ev_step * (TLSAN_PHASE_COUNT + 1) + (phase_done + 1)], st);
+}
+
 #define REQUIRE(cond, code, ...)      \
   do {                                \
     if (!(cond)) {                    \
@@ -118,11 +135,15 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   char* ws = ws_base(workspace);
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t* sorted_vals = nullptr;
+  tlsan_profile_mark(-1, st);
   if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
+  tlsan_profile_mark(TLSAN_PHASE_SORT, st);
   int grid_a = 0, grid_b = 0;
   if ((rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st))) return rc;
   if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, flat + w.f_dgrad, st))) return rc;
-  return tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+  rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+  tlsan_profile_mark(TLSAN_PHASE_REDUCE, st);
+  return rc;
 }
 
 int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
@@ -136,8 +157,10 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
   REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
           w.total + 256);
   char* ws = ws_base(workspace);
-  return tlsan_launch_apply(*dims, *p, w, ws, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, flat + w.f_dgrad, lr,
-                            reg, clip_norm, stats, (cudaStream_t)stream);
+  rc = tlsan_launch_apply(*dims, *p, w, ws, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, flat + w.f_dgrad, lr,
+                          reg, clip_norm, stats, (cudaStream_t)stream);
+  tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
+  return rc;
 }
 
 int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, float lr, float reg,
@@ -158,6 +181,40 @@ int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
   if ((rc = check_params(p, false))) return rc;
   REQUIRE(ut && label && rank, TLSAN_E_NULL, "NULL argument");
   return tlsan_launch_label_rank(*dims, *p, ut, label, rank, (cudaStream_t)stream);
+}
+
+long long tlsan_launch_count(void) { return g_tlsan_launches; }
+
+int tlsan_profile_begin(int32_t max_steps) {
+  REQUIRE(max_steps > 0 && max_steps <= 4096, TLSAN_E_DIMS, "max_steps must be in [1,4096]");
+  if (g_ev_steps_cap < max_steps) {
+    const int per = TLSAN_PHASE_COUNT + 1;
+    cudaEvent_t* ev = new cudaEvent_t[(size_t)max_steps * per];
+    for (int i = 0; i < max_steps * per; ++i) TLSAN_CHECK_CUDA(cudaEventCreate(&ev[i]));
+    g_ev = ev;  // earlier (smaller) pool is intentionally kept alive: events may still be pending
+    g_ev_steps_cap = max_steps;
+  }
+  g_ev_step = -1;
+  g_prof_on = true;
+  return TLSAN_OK;
+}
+
+int tlsan_profile_end(float* ms, int32_t* steps) {
+  REQUIRE(ms && steps, TLSAN_E_NULL, "NULL argument");
+  g_prof_on = false;
+  const int per = TLSAN_PHASE_COUNT + 1;
+  const int n = g_ev_step + 1;
+  for (int s = 0; s < n; ++s) {
+    TLSAN_CHECK_CUDA(cudaEventSynchronize(g_ev[(size_t)s * per + TLSAN_PHASE_COUNT]));
+    for (int ph = 0; ph < TLSAN_PHASE_COUNT; ++ph) {
+      // FUSED_A / BWD_LONG share one mark pair per kernel, see tlsan_launch_fwd_bwd
+      TLSAN_CHECK_CUDA(cudaEventElapsedTime(&ms[s * TLSAN_PHASE_COUNT + ph], g_ev[(size_t)s * per + ph],
+                                            g_ev[(size_t)s * per + ph + 1]));
+    }
+  }
+  *steps = n;
+  g_ev_step = -1;
+  return TLSAN_OK;
 }
 
 }  // extern "C"

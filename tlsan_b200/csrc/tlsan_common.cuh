@@ -27,8 +27,12 @@ void tlsan_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+extern long long g_tlsan_launches;
+void tlsan_profile_mark(int phase_done, cudaStream_t st);   // phase_done = -1: step start
+
 #define TLSAN_CHECK_LAUNCH(name)                                                    \
   do {                                                                              \
+    ++g_tlsan_launches;                                                             \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       tlsan_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \

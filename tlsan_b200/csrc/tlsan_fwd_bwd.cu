@@ -56,10 +56,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float oct_sum(float v) {  // over the 8 lanes (heads) of one sample
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
+// sum over the 8 lanes (heads) of one sample.  Only those 8 lanes are named in the mask: the
+// call sites sit inside per-sample loops whose trip count differs between the 4 samples of a warp.
+__device__ __forceinline__ float oct_sum(float v) {
+  const unsigned m = 0xffu << (threadIdx.x & 24);
+  v += __shfl_xor_sync(m, v, 1);
+  v += __shfl_xor_sync(m, v, 2);
+  v += __shfl_xor_sync(m, v, 4);
   return v;
 }
 
@@ -647,9 +650,11 @@ int tlsan_launch_fwd_bwd(const tlsan_dims_t& d, const tlsan_params_t& p, const t
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   k_fused<true><<<g, TLSAN_THREADS, sizeof(SmemDense), st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fused<train>");
+  tlsan_profile_mark(TLSAN_PHASE_FUSED_A, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
   k_bwd_long<<<g, TLSAN_THREADS, 0, st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long");
+  tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
   return TLSAN_OK;
 }
 
