@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--resident", type=int, default=6, help="distinct device-resident batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no e2e / scoring / cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +265,10 @@ def main():
     loss = float(model._stats[0].item())
 
     # ---------------- end to end through Model.train with host batches
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps({"ms_per_step": ms / args.steps, "phases_ms": dict(zip(_lib.PHASES, map(float, phase[:nrec.value].mean(axis=0))))}))
+        return
     for w in range(2):
         model.train(None, host_batches[w % len(host_batches)], 1.0)
     barrier()

@@ -1,5 +1,6 @@
 // extern "C" entry points of include/tlsan_b200.h: argument validation + launch sequencing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "tlsan_common.cuh"
 
@@ -27,6 +28,17 @@ void tlsan_profile_mark(int phase_done, cudaStream_t st) {
   }
   if (g_ev_step < 0) return;
   cudaEventRecord(g_ev[(size_t)g_ev_step * (TLSAN_PHASE_COUNT + 1) + (phase_done + 1)], st);
+}
+
+// Both fused variants are sm_100a CUDA in this library; TLSAN_FUSED_IMPL=ffma selects the
+// CUDA-core formulation (kept for the mma-vs-FFMA comparison the design calls for).
+static bool use_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TLSAN_FUSED_IMPL");
+    v = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 #define REQUIRE(cond, code, ...)      \
@@ -98,6 +110,7 @@ int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_b
   if ((rc = check_batch(b, false, ncand))) return rc;
   REQUIRE(logits != nullptr, TLSAN_E_NULL, "logits is NULL");
   REQUIRE(ut == nullptr || aligned16(ut), TLSAN_E_ALIGN, "ut must be 16-B aligned");
+  if (use_mma()) return tlsan_launch_score_mma(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
   return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
 }
 
@@ -138,9 +151,11 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   tlsan_profile_mark(-1, st);
   if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SORT, st);
-  int grid_a = 0, grid_b = 0;
-  if ((rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st))) return rc;
-  if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, flat + w.f_dgrad, st))) return rc;
+  int grid_a = 0, grid_b = 0, grid_c = 0;
+  if (use_mma()) rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, st);
+  else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
+  if (rc) return rc;
+  if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;
   rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
   tlsan_profile_mark(TLSAN_PHASE_REDUCE, st);
   return rc;

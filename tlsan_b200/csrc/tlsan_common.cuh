@@ -14,6 +14,7 @@
 #define TLSAN_PART_LOSS TLSAN_DENSE_PAD
 #define TLSAN_PART_SUMSQ (TLSAN_DENSE_PAD + 1)
 #define TLSAN_PART 4456
+#define TLSAN_SCR 5            // 64-float slots per sample in scratch: do_long | o_long | max | 1/den | dz
 #define TLSAN_SORT_CHUNK 2048  // keys per warp in one radix pass
 
 void tlsan_set_error(const char* fmt, ...);
@@ -51,8 +52,8 @@ struct TlsanWs {
   int64_t nocc;
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, hist, nvalid, seg_off;
-  size_t rows_i, rows_u, gscal, scratch, cpart;
-  size_t part_a, part_b, tsq, flat;
+  size_t rows_i, rows_u, gscal, scratch;
+  size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
   size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
   size_t total;
@@ -78,10 +79,10 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.rows_i = take((size_t)d.B * w.SI * 64 * 4);
   w.rows_u = take((size_t)d.B * w.PU * 4);
   w.gscal = take((size_t)d.B * 4);
-  w.scratch = take((size_t)d.B * 256 * 4);
-  w.cpart = take((size_t)(d.NI + d.NC) * 32 * 4);
+  w.scratch = take((size_t)d.B * TLSAN_SCR * 64 * 4);
   w.part_a = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
+  w.part_c = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.tsq = take((size_t)TLSAN_MAX_GRID * 4 * 4);
   w.f_gi = 0;
   w.f_gb = (size_t)(d.NI + d.NC) * 64;
@@ -107,7 +108,12 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
                       char* ws, const int32_t** sorted_vals, cudaStream_t st);
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st);
-int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, float* dgrad, cudaStream_t st);
+int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
+                           float* logits, float* ut, cudaStream_t st);
+int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
+                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st);
+int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,
+                           cudaStream_t st);
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                        const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
                        float reg, float clip, float* stats, cudaStream_t st);

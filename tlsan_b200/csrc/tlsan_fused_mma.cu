@@ -1,0 +1,659 @@
+// Fused TLSAN forward / backward kernels, tensor-core formulation (default path).
+//
+// One WARP works on one sample at a time.  A work tile is 16 (token, head) rows = 2 tokens x 8
+// heads of that sample; the four 8x8 maps of the feature-wise attention (x W1, m1 W2 and the two
+// transposed products of the backward) are `mma.sync.m16n8k8` TF32 tiles with the 3xTF32 hi/lo
+// split (fp32-level accuracy: the 1e-4 logit tolerance does not survive plain TF32).
+//
+// Register layout of every per-row 8-vector (x, m1, m2, dm2, dpre, dx): lane (g = lane/4,
+// t = lane%4) holds features {2t, 2t+1} of head g for token A (v[0], v[1]) and token B
+// (v[2], v[3]) -- exactly the accumulator (D) fragment of the mma.  Permuting the K index of
+// the next product (slot t <-> feature 2t, slot t+4 <-> feature 2t+1, applied to the rows of
+// the weight fragment) makes the same registers a valid A fragment, so the chain
+// x -> m1 -> m2 and dm2 -> dm1 -> dx never leaves registers and needs no shuffles.
+// The per-feature softmax over the sequence (model.py:386) is an online softmax per lane.
+// A warp touches one token as one 256-B coalesced float2 access (item row | cate row).
+//
+//   k_score_mma   forward, 1 or 2 candidates (Model.eval_auc, model.py:237-263)
+//   k_fwd_a_mma   forward + loss + backward of logit / short FWA / dense input (model.py:84-137,164-172)
+//   k_bwd_long_mma  backward of the long FWA and of the time-aware position term (model.py:98-109)
+//   k_dense_grad  dWd = O^T dZ, dbd = sum dZ over the batch (tf.layers.dense, model.py:347)
+#include "tlsan_fused.cuh"
+
+#define MMA_THREADS 256
+#define MMA_WARPS 8
+
+struct BMat { uint32_t h0, h1, l0, l1; };          // B fragment (b0, b1) split into tf32 hi / lo
+struct FwaW { BMat W1, W2; float b1[2], b2[2]; };  // forward weights of one FWA
+struct FwaWT { BMat W2T, W1T; };                   // transposed fragments for the backward
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ BMat make_b(float b0, float b1) {
+  BMat m;
+  m.h0 = to_tf32(b0); m.h1 = to_tf32(b1);
+  m.l0 = to_tf32(b0 - __uint_as_float(m.h0)); m.l1 = to_tf32(b1 - __uint_as_float(m.h1));
+  return m;
+}
+// out[n] = sum_f in[f] W[f][n]  : B[slot t] = W[2t][g], B[slot t+4] = W[2t+1][g]
+__device__ __forceinline__ BMat load_b(const float* __restrict__ W, int g, int t) {
+  return make_b(W[(2 * t) * 8 + g], W[(2 * t + 1) * 8 + g]);
+}
+// out[n] = sum_f in[f] W[n][f]  (transposed product of the backward)
+__device__ __forceinline__ BMat load_bt(const float* __restrict__ W, int g, int t) {
+  return make_b(W[g * 8 + 2 * t], W[g * 8 + 2 * t + 1]);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// d += x B with 3xTF32.  x in D order {A:2t, A:2t+1, B:2t, B:2t+1}; as an A fragment:
+// a0 = (row g, slot t) = x[0], a1 = (row g+8, slot t) = x[2], a2 = (row g, slot t+4) = x[1], a3 = x[3].
+__device__ __forceinline__ void mma3(float (&d)[4], const float (&x)[4], const BMat& B) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = to_tf32(x[i]);
+    l[i] = to_tf32(x[i] - __uint_as_float(h[i]));
+  }
+  mma_tf32(d, l[0], l[2], l[1], l[3], B.h0, B.h1);
+  mma_tf32(d, h[0], h[2], h[1], h[3], B.l0, B.l1);
+  mma_tf32(d, h[0], h[2], h[1], h[3], B.h0, B.h1);
+}
+
+__device__ __forceinline__ FwaW load_fwa(const float* __restrict__ dense, int base, int g, int t) {
+  FwaW w;
+  w.W1 = load_b(dense + base, g, t);
+  w.W2 = load_b(dense + base + 72, g, t);
+  w.b1[0] = dense[base + 64 + 2 * t]; w.b1[1] = dense[base + 64 + 2 * t + 1];
+  w.b2[0] = dense[base + 136 + 2 * t]; w.b2[1] = dense[base + 136 + 2 * t + 1];
+  return w;
+}
+__device__ __forceinline__ FwaWT load_fwa_t(const float* __restrict__ dense, int base, int g, int t) {
+  FwaWT w;
+  w.W2T = load_bt(dense + base + 72, g, t);
+  w.W1T = load_bt(dense + base, g, t);
+  return w;
+}
+
+// m1 = relu(x W1 + b1), m2 = m1 W2 + b2   (model.py:380-383)
+__device__ __forceinline__ void tile_maps(const float (&x)[4], const FwaW& w, float (&m1)[4], float (&m2)[4]) {
+  m1[0] = w.b1[0]; m1[1] = w.b1[1]; m1[2] = w.b1[0]; m1[3] = w.b1[1];
+  mma3(m1, x, w.W1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m1[i] = fmaxf(m1[i], 0.f);
+  m2[0] = w.b2[0]; m2[1] = w.b2[1]; m2[2] = w.b2[0]; m2[3] = w.b2[1];
+  mma3(m2, m1, w.W2);
+}
+
+// online softmax over the sequence axis for the lane's two features
+struct Soft2 {
+  float mx[2], den[2], acc[2];
+  __device__ __forceinline__ void init() {
+    mx[0] = mx[1] = -INFINITY; den[0] = den[1] = 0.f; acc[0] = acc[1] = 0.f;
+  }
+  __device__ __forceinline__ void push(float m0, float m1, float x0, float x1) {
+    const float mm[2] = {m0, m1}, xx[2] = {x0, x1};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float d = mm[j] - mx[j];
+      const float e = __expf(-fabsf(d));
+      const bool up = d > 0.f;
+      const float c = up ? e : 1.f, n = up ? 1.f : e;
+      den[j] = fmaf(den[j], c, n);
+      acc[j] = fmaf(acc[j], c, n * xx[j]);
+      mx[j] = up ? mm[j] : mx[j];
+    }
+  }
+};
+
+// per-lane gradient accumulators of one FWA weight set: rows k = 0..7, the lane's 2 columns
+struct FwaGrad {
+  float W1[8][2], W2[8][2], b1[2], b2[2];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { W1[k][0] = W1[k][1] = 0.f; W2[k][0] = W2[k][1] = 0.f; }
+    b1[0] = b1[1] = b2[0] = b2[1] = 0.f;
+  }
+};
+
+// backward of one tile.  okB = second token of the tile is real.
+__device__ __forceinline__ void tile_bwd(const float (&x)[4], bool okB, const float (&o)[2], const float (&dout)[2],
+                                         const float (&mx)[2], const float (&inv)[2], const FwaW& w,
+                                         const FwaWT& wt, int lane, float (&dx)[4], FwaGrad& G) {
+  float m1[4], m2[4];
+  tile_maps(x, w, m1, m2);
+  float ado[4], dm2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = i & 1;
+    const float aw = __expf(m2[i] - mx[j]) * inv[j];
+    const float on = (i < 2 || okB) ? 1.f : 0.f;
+    ado[i] = on * aw * dout[j];
+    dm2[i] = ado[i] * (x[i] - o[j]);
+  }
+  G.b2[0] += dm2[0] + dm2[2]; G.b2[1] += dm2[1] + dm2[3];
+  float dpre[4] = {0.f, 0.f, 0.f, 0.f};
+  mma3(dpre, dm2, wt.W2T);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dpre[i] = m1[i] > 0.f ? dpre[i] : 0.f;
+  G.b1[0] += dpre[0] + dpre[2]; G.b1[1] += dpre[1] + dpre[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dx[i] = ado[i];
+  mma3(dx, dpre, wt.W1T);
+  // dW2[k][j] += m1[k] dm2[j], dW1[k][j] += x[k] dpre[j]: the 8 k-values of a row live in the
+  // 4 lanes of the row's quad (2 each) -> quad shuffles, then FFMA on the lane's 2 columns.
+  const int qbase = lane & ~3;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int tq = 0; tq < 4; ++tq) {
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int k = 2 * tq + jj;
+        const float mk = __shfl_sync(0xffffffffu, m1[2 * r + jj], qbase + tq);
+        const float xk = __shfl_sync(0xffffffffu, x[2 * r + jj], qbase + tq);
+        G.W2[k][0] = fmaf(mk, dm2[2 * r], G.W2[k][0]);
+        G.W2[k][1] = fmaf(mk, dm2[2 * r + 1], G.W2[k][1]);
+        G.W1[k][0] = fmaf(xk, dpre[2 * r], G.W1[k][0]);
+        G.W1[k][1] = fmaf(xk, dpre[2 * r + 1], G.W1[k][1]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+// lane geometry: features f0, f0+1 of the 64-float token; which table half; offset inside the row
+struct LaneGeo {
+  int lane, g, t, f0, half, col;
+  __device__ __forceinline__ void init() {
+    lane = threadIdx.x & 31; g = lane >> 2; t = lane & 3;
+    f0 = 8 * g + 2 * t; half = g >> 2; col = (g & 3) * 8 + 2 * t;
+  }
+};
+
+// ---- token meta of up to 32 tokens, one per lane (coalesced), broadcast by shuffle
+struct LongMeta { int id, crow; float tau, pt, ht; };
+__device__ __forceinline__ LongMeta load_long_meta(const FArgs& a, int b, int u, int tt, int ell, float gamma) {
+  LongMeta m;
+  const bool ok = tt < ell;
+  m.id = ok ? __ldg(a.hist_i + (size_t)b * a.L + tt) : 0;
+  m.ht = ok ? __ldg(a.hist_t + (size_t)b * a.L + tt) : 0.f;
+  const float pu = ok ? __ldg(a.usert + (size_t)u * a.L + tt) : 0.f;
+  m.pt = pu * m.ht;                  // P[u,t] * hist_t    (model.py:99)
+  m.tau = gamma * m.pt;              // gamma * (...)      (model.py:109)
+  m.crow = a.NI + __ldg(a.icl + m.id);
+  return m;
+}
+__device__ __forceinline__ const float* row_ptr(const FArgs& a, const LaneGeo& L, int id, int crow) {
+  return a.emb + (size_t)(L.half ? crow : id) * 32 + L.col;
+}
+
+// long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state
+__device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, int b, int u, int ell, float gamma,
+                                             const FwaW& w, Soft2& st) {
+  st.init();
+  for (int r0 = 0; r0 < ell; r0 += 32) {
+    const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
+    const int cnt = min(32, ell - r0);
+    for (int j = 0; j < cnt; j += 2) {
+      const bool okB = j + 1 < cnt;
+      const int idA = __shfl_sync(0xffffffffu, me.id, j), crA = __shfl_sync(0xffffffffu, me.crow, j);
+      const int idB = __shfl_sync(0xffffffffu, me.id, (j + 1) & 31), crB = __shfl_sync(0xffffffffu, me.crow, (j + 1) & 31);
+      const float tA = __shfl_sync(0xffffffffu, me.tau, j), tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
+      const float2 eA = ldg2(row_ptr(a, L, idA, crA));
+      const float2 eB = okB ? ldg2(row_ptr(a, L, idB, crB)) : make_float2(0.f, 0.f);
+      const float x[4] = {eA.x * tA, eA.y * tA, okB ? eB.x * tB : 0.f, okB ? eB.y * tB : 0.f};
+      float m1[4], m2[4];
+      tile_maps(x, w, m1, m2);
+      st.push(m2[0], m2[1], x[0], x[1]);
+      if (okB) st.push(m2[2], m2[3], x[2], x[3]);
+    }
+  }
+}
+
+// shared-memory image of the dense layer (natural layouts: lane reads float2 at [k][f0])
+struct SmemMma {
+  float wd[64 * 64];    // Wd[k][f]
+  float wdt[64 * 64];   // Wd^T: wdt[j][f] = Wd[f][j]
+  float bd[64];
+  float vec[MMA_WARPS][64];  // per-warp staging of o_long / dz
+  float red[MMA_WARPS][160];
+};
+
+// out[jj] += sum_k vec[k] * W[k][f0 + jj]
+__device__ __forceinline__ void dense2(const float* __restrict__ vec, const float* __restrict__ W, int f0,
+                                       float (&out)[2]) {
+#pragma unroll 4
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const float4 v = *reinterpret_cast<const float4*>(vec + 4 * k4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float2 wv = *reinterpret_cast<const float2*>(W + (4 * k4 + kk) * 64 + f0);
+      out[0] = fmaf(vv[kk], wv.x, out[0]);
+      out[1] = fmaf(vv[kk], wv.y, out[1]);
+    }
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, const int ncand) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemMma& sm = *reinterpret_cast<SmemMma*>(smem_raw);
+  for (int e = threadIdx.x; e < 64 * 64; e += MMA_THREADS) {
+    const float wv = a.dense[TLSAN_OFF_WD + e];
+    sm.wd[e] = wv;
+    if (TRAIN) sm.wdt[(e & 63) * 64 + (e >> 6)] = wv;
+  }
+  if (threadIdx.x < 64) sm.bd[threadIdx.x] = a.dense[TLSAN_OFF_BD + threadIdx.x];
+  __syncthreads();
+
+  LaneGeo L; L.init();
+  const int warp = threadIdx.x >> 5;
+  const float gamma = a.dense[TLSAN_OFF_GAMMA];
+  const FwaW wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+  const FwaW ws = load_fwa(a.dense, TLSAN_OFF_W1S, L.g, L.t);
+  FwaWT wst;
+  FwaGrad G;
+  float loss_acc = 0.f, sq_acc = 0.f;
+  if (TRAIN) { wst = load_fwa_t(a.dense, TLSAN_OFF_W1S, L.g, L.t); G.init(); }
+  float* vec = sm.vec[warp];
+  const int nwarps = gridDim.x * MMA_WARPS;
+
+  for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
+    const int u = __ldg(a.u + b), ell = __ldg(a.sl + b), s = __ldg(a.sl_new + b);
+    const int cand = __ldg(a.i + b), uc = __ldg(a.c + b);
+    // ---- long-term FWA forward
+    Soft2 st;
+    long_forward(a, L, b, u, ell, gamma, wl, st);
+    float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
+    if (TRAIN) {
+      float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
+      st2(sc + 64, o[0], o[1]);
+      st2(sc + 128, st.mx[0], st.mx[1]);
+      st2(sc + 192, 1.f / st.den[0], 1.f / st.den[1]);
+    }
+    __syncwarp();
+    st2(vec + L.f0, o[0], o[1]);
+    __syncwarp();
+    // ---- z = o_long Wd + bd   (model.py:347)
+    float z[2] = {0.f, 0.f};
+    dense2(vec, sm.wd, L.f0, z);
+    z[0] += sm.bd[L.f0]; z[1] += sm.bd[L.f0 + 1];
+    // ---- short-term FWA forward over s+1 tokens (model.py:350-364)
+    const int ntok = s + 1;
+    Soft2 ss; ss.init();
+    for (int r0 = 0; r0 < ntok; r0 += 32) {       // round covers tokens r0 .. r0+31 (token n >= 1 is item n-1)
+      // lane l holds the meta of item r0 + l, i.e. of token r0 + l + 1
+      const int item = r0 + L.lane;
+      const bool ok = item < s;
+      const int id_l = ok ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
+      const int crow_l = a.NI + __ldg(a.icl + id_l);
+      const int cnt = min(32, ntok - r0);          // tokens in this round
+      for (int j = 0; j < cnt; j += 2) {
+        float x[4]; bool okB;
+        // token index n = r0 + j (A) and n+1 (B); item index = n - 1 -> lane (n - 1 - r0) = j - 1 (A), j (B)
+        const int nA = r0 + j, nB = nA + 1;
+        okB = nB < ntok;
+        const int laneA = (j - 1) & 31, laneB = j & 31;
+        int idA = __shfl_sync(0xffffffffu, id_l, laneA), crA = __shfl_sync(0xffffffffu, crow_l, laneA);
+        const int idB = __shfl_sync(0xffffffffu, id_l, laneB), crB = __shfl_sync(0xffffffffu, crow_l, laneB);
+        if (nA == 0) { x[0] = z[0]; x[1] = z[1]; }
+        else {
+          if (j == 0) {   // first token of a later round: item r0-1 was not loaded in this round
+            idA = __ldg(a.hist_i_new + (size_t)b * a.S + (nA - 1));
+            crA = a.NI + __ldg(a.icl + idA);
+          }
+          const float2 e = ldg2(row_ptr(a, L, idA, crA)); x[0] = e.x; x[1] = e.y;
+        }
+        if (okB) { const float2 e = ldg2(row_ptr(a, L, idB, crB)); x[2] = e.x; x[3] = e.y; }
+        else { x[2] = 0.f; x[3] = 0.f; }
+        float m1[4], m2[4];
+        tile_maps(x, ws, m1, m2);
+        ss.push(m2[0], m2[1], x[0], x[1]);
+        if (okB) ss.push(m2[2], m2[3], x[2], x[3]);
+      }
+    }
+    const float inv_s[2] = {1.f / ss.den[0], 1.f / ss.den[1]};
+    const float v[2] = {ss.acc[0] * inv_s[0], ss.acc[1] * inv_s[1]};
+    // ---- user vector, candidate, logit (model.py:84-95,135-137)
+    const float2 p = ldg2(a.emb + (size_t)(L.half ? a.NI + uc : a.NI + a.NC + u) * 32 + L.col);
+    const float ut[2] = {v[0] + p.x, v[1] + p.y};
+    const int ccrow = a.NI + __ldg(a.icl + cand);
+    const float2 q = ldg2(row_ptr(a, L, cand, ccrow));
+    const float logit = warp_sum_f(fmaf(ut[0], q.x, ut[1] * q.y)) + __ldg(a.item_b + cand);
+
+    if (!TRAIN) {
+      if (L.lane == 0) a.logits[(size_t)b * ncand] = logit;
+      if (a.ut) st2(a.ut + (size_t)b * 64 + L.f0, ut[0], ut[1]);
+      if (ncand > 1) {   // Model.eval_auc second run (model.py:251-261): same u_t, other item
+        const int c2 = __ldg(a.i2 + b);
+        const int c2row = a.NI + __ldg(a.icl + c2);
+        const float2 q2 = ldg2(row_ptr(a, L, c2, c2row));
+        const float l2 = warp_sum_f(fmaf(ut[0], q2.x, ut[1] * q2.y)) + __ldg(a.item_b + c2);
+        if (L.lane == 0) a.logits[(size_t)b * ncand + 1] = l2;
+      }
+      continue;
+    }
+
+    // =========================== backward ===========================
+    const float yb = __ldg(a.y + b);
+    const float ex = expf(-fabsf(logit));
+    const float bce = fmaxf(logit, 0.f) - logit * yb + log1pf(ex);     // model.py:171
+    const float sig = logit >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
+    const float gl = (sig - yb) * a.invB;                               // d loss / d logit
+    if (L.lane == 0) { loss_acc += bce; sq_acc = fmaf(gl, gl, sq_acc); a.gscal[b] = gl; }
+    float* rcand = a.rows_i + ((size_t)b * a.SI + a.L + a.S) * 64 + L.f0;
+    const float dq[2] = {gl * ut[0], gl * ut[1]};
+    const float du[2] = {gl * q.x, gl * q.y};
+    sq_acc = fmaf(dq[0], dq[0], sq_acc); sq_acc = fmaf(dq[1], dq[1], sq_acc);
+    sq_acc = fmaf(du[0], du[0], sq_acc); sq_acc = fmaf(du[1], du[1], sq_acc);
+    st2(rcand, dq[0], dq[1]);                                           // -> item_emb[i] | cate_emb[icl[i]]
+    if (L.half) st2(rcand + 64, du[0], du[1]);                          // -> cate_emb[u_cate]
+    else { st2(rcand + 64, 0.f, 0.f); st2(a.rows_u + (size_t)b * a.PU + L.f0, du[0], du[1]); }  // -> user_emb[u]
+    // short-term FWA backward, d v = du
+    float dz[2] = {0.f, 0.f};
+    for (int r0 = 0; r0 < ntok; r0 += 32) {
+      const int item = r0 + L.lane;
+      const bool ok = item < s;
+      const int id_l = ok ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
+      const int crow_l = a.NI + __ldg(a.icl + id_l);
+      const int cnt = min(32, ntok - r0);
+      for (int j = 0; j < cnt; j += 2) {
+        float x[4], dx[4];
+        const int nA = r0 + j, nB = nA + 1;
+        const bool okB = nB < ntok;
+        const int laneA = (j - 1) & 31, laneB = j & 31;
+        int idA = __shfl_sync(0xffffffffu, id_l, laneA), crA = __shfl_sync(0xffffffffu, crow_l, laneA);
+        const int idB = __shfl_sync(0xffffffffu, id_l, laneB), crB = __shfl_sync(0xffffffffu, crow_l, laneB);
+        if (nA == 0) { x[0] = z[0]; x[1] = z[1]; }
+        else {
+          if (j == 0) {
+            idA = __ldg(a.hist_i_new + (size_t)b * a.S + (nA - 1));
+            crA = a.NI + __ldg(a.icl + idA);
+          }
+          const float2 e = ldg2(row_ptr(a, L, idA, crA)); x[0] = e.x; x[1] = e.y;
+        }
+        if (okB) { const float2 e = ldg2(row_ptr(a, L, idB, crB)); x[2] = e.x; x[3] = e.y; }
+        else { x[2] = 0.f; x[3] = 0.f; }
+        tile_bwd(x, okB, v, du, ss.mx, inv_s, ws, wst, L.lane, dx, G);
+        if (nA == 0) { dz[0] = dx[0]; dz[1] = dx[1]; }
+        else {
+          sq_acc = fmaf(dx[0], dx[0], sq_acc); sq_acc = fmaf(dx[1], dx[1], sq_acc);
+          st2(a.rows_i + ((size_t)b * a.SI + a.L + (nA - 1)) * 64 + L.f0, dx[0], dx[1]);
+        }
+        if (okB) {
+          sq_acc = fmaf(dx[2], dx[2], sq_acc); sq_acc = fmaf(dx[3], dx[3], sq_acc);
+          st2(a.rows_i + ((size_t)b * a.SI + a.L + (nB - 1)) * 64 + L.f0, dx[2], dx[3]);
+        }
+      }
+    }
+    // ---- d o_long = dz Wd^T ; dz and o_long go to scratch for k_dense_grad / k_bwd_long_mma
+    __syncwarp();
+    st2(vec + L.f0, dz[0], dz[1]);
+    __syncwarp();
+    float dol[2] = {0.f, 0.f};
+    dense2(vec, sm.wdt, L.f0, dol);
+    {
+      float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
+      st2(sc, dol[0], dol[1]);
+      st2(sc + 256, dz[0], dz[1]);
+    }
+  }
+
+  if (TRAIN) {
+    // lanes with equal t hold the same (k, column) slots: butterfly over g, then warps in order
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        float r1 = G.W1[k][jj], r2 = G.W2[k][jj];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+          r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        }
+        if (L.g == 0) { sm.red[warp][k * 8 + 2 * L.t + jj] = r1; sm.red[warp][72 + k * 8 + 2 * L.t + jj] = r2; }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float r1 = G.b1[jj], r2 = G.b2[jj];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (L.g == 0) { sm.red[warp][64 + 2 * L.t + jj] = r1; sm.red[warp][136 + 2 * L.t + jj] = r2; }
+    }
+    {
+      const float r1 = warp_sum_f(loss_acc), r2 = warp_sum_f(sq_acc);
+      if (L.lane == 0) { sm.red[warp][144] = r1; sm.red[warp][145] = r2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 146) {
+      float r = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < MMA_WARPS; ++wv) r += sm.red[wv][threadIdx.x];
+      const int dst = threadIdx.x < 144 ? TLSAN_OFF_W1S + threadIdx.x
+                                        : (threadIdx.x == 144 ? TLSAN_PART_LOSS : TLSAN_PART_SUMSQ);
+      a.part[(size_t)blockIdx.x * TLSAN_PART + dst] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward of the long-term FWA
+__global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) {
+  __shared__ float red[MMA_WARPS][160];
+  LaneGeo L; L.init();
+  const int warp = threadIdx.x >> 5;
+  const float gamma = a.dense[TLSAN_OFF_GAMMA];
+  const FwaW wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+  const FwaWT wlt = load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+  FwaGrad G; G.init();
+  float ggamma = 0.f, sq_acc = 0.f;
+  const int nwarps = gridDim.x * MMA_WARPS;
+
+  for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
+    const int u = __ldg(a.u + b), ell = __ldg(a.sl + b);
+    const float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
+    const float2 dol2 = *reinterpret_cast<const float2*>(sc);
+    const float2 o2 = *reinterpret_cast<const float2*>(sc + 64);
+    const float2 mx2 = *reinterpret_cast<const float2*>(sc + 128);
+    const float2 inv2 = *reinterpret_cast<const float2*>(sc + 192);
+    const float dol[2] = {dol2.x, dol2.y}, o[2] = {o2.x, o2.y}, mx[2] = {mx2.x, mx2.y}, inv[2] = {inv2.x, inv2.y};
+    float* ru = a.rows_u + (size_t)b * a.PU + 32;
+    for (int r0 = 0; r0 < ell; r0 += 32) {
+      const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
+      const int cnt = min(32, ell - r0);
+      float dtau_l = 0.f;                          // lane j collects d tau of token r0 + j
+      for (int j = 0; j < cnt; j += 2) {
+        const bool okB = j + 1 < cnt;
+        const int idA = __shfl_sync(0xffffffffu, me.id, j), crA = __shfl_sync(0xffffffffu, me.crow, j);
+        const int idB = __shfl_sync(0xffffffffu, me.id, (j + 1) & 31), crB = __shfl_sync(0xffffffffu, me.crow, (j + 1) & 31);
+        const float tA = __shfl_sync(0xffffffffu, me.tau, j), tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
+        const float2 eA = ldg2(row_ptr(a, L, idA, crA));
+        const float2 eB = okB ? ldg2(row_ptr(a, L, idB, crB)) : make_float2(0.f, 0.f);
+        const float x[4] = {eA.x * tA, eA.y * tA, okB ? eB.x * tB : 0.f, okB ? eB.y * tB : 0.f};
+        float dx[4];
+        tile_bwd(x, okB, o, dol, mx, inv, wl, wlt, L.lane, dx, G);
+        // gradient of the gathered slices (tau * dX) and of tau (<dX, e>)
+        const float rA0 = dx[0] * tA, rA1 = dx[1] * tA;
+        sq_acc = fmaf(rA0, rA0, sq_acc); sq_acc = fmaf(rA1, rA1, sq_acc);
+        st2(a.rows_i + ((size_t)b * a.SI + r0 + j) * 64 + L.f0, rA0, rA1);
+        const float dtA = warp_sum_f(fmaf(dx[0], eA.x, dx[1] * eA.y));
+        if (L.lane == j) dtau_l = dtA;
+        if (okB) {
+          const float rB0 = dx[2] * tB, rB1 = dx[3] * tB;
+          sq_acc = fmaf(rB0, rB0, sq_acc); sq_acc = fmaf(rB1, rB1, sq_acc);
+          st2(a.rows_i + ((size_t)b * a.SI + r0 + j + 1) * 64 + L.f0, rB0, rB1);
+          const float dtB = warp_sum_f(fmaf(dx[2], eB.x, dx[3] * eB.y));
+          if (L.lane == j + 1) dtau_l = dtB;
+        }
+      }
+      if (L.lane < cnt) {
+        ggamma = fmaf(dtau_l, me.pt, ggamma);
+        const float dp = dtau_l * gamma * me.ht;   // d usert_emb[u, t]
+        sq_acc = fmaf(dp, dp, sq_acc);
+        ru[r0 + L.lane] = dp;
+      }
+    }
+    for (int tt = ell + L.lane; tt < a.PU - 32; tt += 32) ru[tt] = 0.f;
+  }
+
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float r1 = G.W1[k][jj], r2 = G.W2[k][jj];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (L.g == 0) { red[warp][k * 8 + 2 * L.t + jj] = r1; red[warp][72 + k * 8 + 2 * L.t + jj] = r2; }
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    float r1 = G.b1[jj], r2 = G.b2[jj];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (L.g == 0) { red[warp][64 + 2 * L.t + jj] = r1; red[warp][136 + 2 * L.t + jj] = r2; }
+  }
+  {
+    const float r1 = warp_sum_f(ggamma), r2 = warp_sum_f(sq_acc);
+    if (L.lane == 0) { red[warp][144] = r1; red[warp][145] = r2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 146) {
+    float r = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < MMA_WARPS; ++wv) r += red[wv][threadIdx.x];
+    const int dst = threadIdx.x < 144 ? TLSAN_OFF_W1L + threadIdx.x
+                                      : (threadIdx.x == 144 ? TLSAN_OFF_GAMMA : TLSAN_PART_SUMSQ);
+    a.part[(size_t)blockIdx.x * TLSAN_PART + dst] = r;
+  }
+}
+
+// ------------------------------------------------------------------ dWd = O^T dZ, dbd = sum dZ
+// Each CTA owns a contiguous range of samples; thread (r4, c4) accumulates a 4x4 block of the
+// 64x64 kernel gradient over the range in sample order; partials go to part[cta] (fixed-order
+// second stage in k_finalize1).
+__global__ void __launch_bounds__(256) k_dense_grad(const float* __restrict__ scratch, int B, float* __restrict__ part) {
+  __shared__ __align__(16) float so[32 * 64];
+  __shared__ __align__(16) float sz[32 * 64];
+  const int per = (B + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(B, lo + per);
+  const int r4 = threadIdx.x >> 4, c4 = threadIdx.x & 15;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  float bsum = 0.f;   // threads < 64: dbd[threadIdx.x]
+  for (int base = lo; base < hi; base += 32) {
+    const int n = min(32, hi - base);
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {   // float4 granularity: 16 per 64-float row
+      const int sidx = e >> 4, q = e & 15;
+      float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vz = vo;
+      if (sidx < n) {
+        const float* sc = scratch + (size_t)(base + sidx) * (TLSAN_SCR * 64);
+        vo = *reinterpret_cast<const float4*>(sc + 64 + 4 * q);
+        vz = *reinterpret_cast<const float4*>(sc + 256 + 4 * q);
+      }
+      *reinterpret_cast<float4*>(so + sidx * 64 + 4 * q) = vo;
+      *reinterpret_cast<float4*>(sz + sidx * 64 + 4 * q) = vz;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int ss = 0; ss < 32; ++ss) {
+      const float4 o4 = *reinterpret_cast<const float4*>(so + ss * 64 + 4 * r4);
+      const float4 z4 = *reinterpret_cast<const float4*>(sz + ss * 64 + 4 * c4);
+      const float oo[4] = {o4.x, o4.y, o4.z, o4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i * 4 + j] = fmaf(oo[i], zz[j], acc[i * 4 + j]);
+    }
+    if (threadIdx.x < 64)
+      for (int ss = 0; ss < 32; ++ss) bsum += sz[ss * 64 + threadIdx.x];
+    __syncthreads();
+  }
+  float* p = part + (size_t)blockIdx.x * TLSAN_PART;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(p + TLSAN_OFF_WD + (4 * r4 + i) * 64 + 4 * c4) =
+        make_float4(acc[i * 4], acc[i * 4 + 1], acc[i * 4 + 2], acc[i * 4 + 3]);
+  if (threadIdx.x < 64) p[TLSAN_OFF_BD + threadIdx.x] = bsum;
+}
+
+// ------------------------------------------------------------------ launchers
+FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b);
+
+static int mma_grid(int B) {
+  const int need = (B + MMA_WARPS - 1) / MMA_WARPS;
+  const int cap = tlsan_num_sms() * 2;
+  return need < cap ? need : cap;
+}
+
+int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
+                           float* logits, float* ut, cudaStream_t st) {
+  FArgs a = tlsan_make_fargs(d, p, b);
+  a.logits = logits; a.ut = ut;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_a_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemMma)));
+    attr_set = true;
+  }
+  k_fwd_a_mma<false><<<mma_grid(d.B), MMA_THREADS, sizeof(SmemMma), st>>>(a, ncand);
+  TLSAN_CHECK_LAUNCH("k_fwd_a_mma<score>");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
+                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st) {
+  FArgs a = tlsan_make_fargs(d, p, b);
+  a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
+  a.rows_u = reinterpret_cast<float*>(ws + w.rows_u);
+  a.gscal = reinterpret_cast<float*>(ws + w.gscal);
+  a.scratch = reinterpret_cast<float*>(ws + w.scratch);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_a_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemMma)));
+    attr_set = true;
+  }
+  const int g = mma_grid(d.B);
+  *grid_a = g; *grid_b = g;
+  a.part = reinterpret_cast<float*>(ws + w.part_a);
+  k_fwd_a_mma<true><<<g, MMA_THREADS, sizeof(SmemMma), st>>>(a, 1);
+  TLSAN_CHECK_LAUNCH("k_fwd_a_mma<train>");
+  tlsan_profile_mark(TLSAN_PHASE_FUSED_A, st);
+  a.part = reinterpret_cast<float*>(ws + w.part_b);
+  k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
+  TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
+  int gc = (d.B + 255) / 256;
+  const int cap = tlsan_num_sms();
+  if (gc > cap) gc = cap;
+  *grid_c = gc;
+  k_dense_grad<<<gc, 256, 0, st>>>(a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c));
+  TLSAN_CHECK_LAUNCH("k_dense_grad");
+  tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
+  return TLSAN_OK;
+}

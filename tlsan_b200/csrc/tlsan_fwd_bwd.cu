@@ -16,25 +16,7 @@
 
 __constant__ float c_small[292];  // dense[0..288) (both FWA weight sets) ; [288] = gamma
 
-struct FArgs {
-  int B, L, S, NI, NC, NU, SI, PU;
-  float invB;
-  const float* emb;
-  const float* usert;
-  const float* item_b;
-  const float* dense;
-  const int* icl;
-  const int *u, *i, *i2, *c, *sl, *sl_new, *hist_i, *hist_i_new;
-  const float *y, *hist_t;
-  // outputs
-  float* logits;   // score: [B][ncand]
-  float* ut;       // score: optional [B][64]
-  float* rows_i;   // train: [B*SI][64] per-occurrence gradient rows (item half | cate half)
-  float* rows_u;   // train: [B][PU]   user_emb grad (32) | usert_emb grad (L)
-  float* gscal;    // train: [B] d loss / d logit  (item_b gradient per occurrence)
-  float* scratch;  // train: [B][4][64]  do_long | o_long | max | 1/denominator
-  float* part;     // train: [grid][TLSAN_PART] per-CTA partial sums
-};
+#include "tlsan_fused.cuh"
 
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8]) {
@@ -255,7 +237,7 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_fused(const FArgs a, const
       float inv[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) inv[q] = 1.f / st.den[q];
-      float* sc = a.scratch + (size_t)b * 256 + 8 * h;
+      float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + 8 * h;
       st8(sc + 64, o);
       st8(sc + 128, st.mx);
       st8(sc + 192, inv);
@@ -404,7 +386,7 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_fused(const FArgs a, const
 #pragma unroll
     for (int q = 0; q < 8; ++q) dol[q] = 0.f;
     dense_apply(sm.dz + sidx * 64, sm.wdt, h, dol);
-    if (valid) st8(a.scratch + (size_t)b * 256 + 8 * h, dol);
+    if (valid) st8(a.scratch + (size_t)b * (TLSAN_SCR * 64) + 8 * h, dol);
     __syncthreads();
   }
 
@@ -485,7 +467,7 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_bwd_long(const FArgs a) {
     const int ell = valid ? __ldg(a.sl + bb) : 0;
     float dol[8], o[8], mx[8], inv[8];
     {
-      const float* sc = a.scratch + (size_t)bb * 256 + 8 * h;
+      const float* sc = a.scratch + (size_t)bb * (TLSAN_SCR * 64) + 8 * h;
       ld8_plain(sc, dol); ld8_plain(sc + 64, o); ld8_plain(sc + 128, mx); ld8_plain(sc + 192, inv);
     }
     float* ru = a.rows_u + (size_t)bb * a.PU + 32;
@@ -594,7 +576,7 @@ int tlsan_launch_upload_consts(const float* dense, cudaStream_t st) {
   return TLSAN_OK;
 }
 
-static FArgs make_args(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b) {
+FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b) {
   FArgs a;
   a.B = d.B; a.L = d.L; a.S = d.S; a.NI = d.NI; a.NC = d.NC; a.NU = d.NU;
   a.SI = d.L + d.S + 2; a.PU = (int)tlsan_align_up(32 + d.L, 4);
@@ -617,7 +599,7 @@ int tlsan_launch_score(const tlsan_dims_t& d, const tlsan_params_t& p, const tls
                        float* logits, float* ut, cudaStream_t st) {
   int rc = tlsan_launch_upload_consts(p.dense, st);
   if (rc) return rc;
-  FArgs a = make_args(d, p, b);
+  FArgs a = tlsan_make_fargs(d, p, b);
   a.logits = logits; a.ut = ut;
   static bool attr_set = false;
   if (!attr_set) {
@@ -634,7 +616,7 @@ int tlsan_launch_fwd_bwd(const tlsan_dims_t& d, const tlsan_params_t& p, const t
                          char* ws, int* grid_a, int* grid_b, cudaStream_t st) {
   int rc = tlsan_launch_upload_consts(p.dense, st);
   if (rc) return rc;
-  FArgs a = make_args(d, p, b);
+  FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.rows_u = reinterpret_cast<float*>(ws + w.rows_u);
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);

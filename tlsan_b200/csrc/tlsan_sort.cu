@@ -29,77 +29,95 @@ __global__ void k_build_keys(int B, int L, int S, int NI, int NC, const int* __r
   keys[g] = key;
 }
 
-// one warp = one chunk of TLSAN_SORT_CHUNK consecutive keys
+// One warp = one chunk of TLSAN_SORT_CHUNK consecutive keys, 8 warps (chunks) per CTA.
+// Histograms are kept per CTA: hist[digit][cta]; the scatter kernel recounts its 8 chunks
+// to split the CTA's range among its warps (keys are L2-resident, the recount is cheap).
+__device__ __forceinline__ void count_chunk(const int* __restrict__ keys, long long n, int chunk, int shift,
+                                            int lane, int* cnt /* [256] smem, zeroed */) {
+  const long long base = (long long)chunk * TLSAN_SORT_CHUNK;
+#pragma unroll 4
+  for (int it = 0; it < TLSAN_SORT_CHUNK / 32; ++it) {
+    const long long idx = base + it * 32 + lane;
+    const int key = idx < n ? keys[idx] : TLSAN_INVALID_KEY;
+    if (key != TLSAN_INVALID_KEY) atomicAdd(&cnt[(key >> shift) & 255], 1);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_radix_hist(const int* __restrict__ keys, long long ncap,
                                                     const int* __restrict__ nvalid, int shift, int nchunks,
-                                                    int* __restrict__ hist) {
+                                                    int nblk, int* __restrict__ hist) {
   __shared__ int cnt[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = blockIdx.x * 8 + warp;
   for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
   __syncwarp();
   const long long n = nvalid ? (long long)*nvalid : ncap;
-  if (chunk < nchunks) {
-    const long long base = (long long)chunk * TLSAN_SORT_CHUNK;
-    for (int it = 0; it < TLSAN_SORT_CHUNK / 32; ++it) {
-      const long long idx = base + it * 32 + lane;
-      const int key = idx < n ? keys[idx] : TLSAN_INVALID_KEY;
-      if (key != TLSAN_INVALID_KEY) atomicAdd(&cnt[warp][(key >> shift) & 255], 1);
-    }
-    __syncwarp();
-    for (int d = lane; d < 256; d += 32) hist[(size_t)d * nchunks + chunk] = cnt[warp][d];
-  }
+  if (chunk < nchunks) count_chunk(keys, n, chunk, shift, lane, cnt[warp]);
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += cnt[w][threadIdx.x];
+  hist[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
 }
 
-// exclusive scan of hist[256*nchunks] in place (single CTA), total -> *total_out
+// exclusive scan of hist[n] in place (single CTA of 1024 threads, contiguous span per thread)
 __global__ void __launch_bounds__(1024) k_radix_scan(int* __restrict__ hist, int n, int* __restrict__ total_out) {
   __shared__ int wsum[32];
-  __shared__ int carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += hist[i];
+  int x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int idx = base + threadIdx.x;
-    const int v = idx < n ? hist[idx] : 0;
-    int x = v;
+  if (warp == 0) {
+    int w = wsum[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
     }
-    if (lane == 31) wsum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int w = wsum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
-      }
-      wsum[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int excl = carry + (warp > 0 ? wsum[warp - 1] : 0) + x - v;
-    if (idx < n) hist[idx] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wsum[31];
-    __syncthreads();
+    wsum[lane] = w;
   }
-  if (threadIdx.x == 0) *total_out = carry_s;
+  __syncthreads();
+  int run = (warp > 0 ? wsum[warp - 1] : 0) + x - s;   // exclusive prefix of this thread's span
+  for (int i = lo; i < hi; ++i) {
+    const int v = hist[i];
+    hist[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) *total_out = wsum[31];
 }
 
 __global__ void __launch_bounds__(256) k_radix_scatter(const int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                        long long ncap, const int* __restrict__ nvalid, int shift,
-                                                       int nchunks, const int* __restrict__ hist,
+                                                       int nchunks, int nblk, const int* __restrict__ hist,
                                                        int* __restrict__ keys_out, int* __restrict__ vals_out) {
   __shared__ int off[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = blockIdx.x * 8 + warp;
-  if (chunk >= nchunks) return;
-  for (int d = lane; d < 256; d += 32) off[warp][d] = hist[(size_t)d * nchunks + chunk];
+  for (int d = lane; d < 256; d += 32) off[warp][d] = 0;
   __syncwarp();
   const long long n = nvalid ? (long long)*nvalid : ncap;
+  if (chunk < nchunks) count_chunk(keys_in, n, chunk, shift, lane, off[warp]);
+  __syncthreads();
+  {  // counts -> start offsets: CTA base of the digit + counts of the lower warps
+    int run = hist[(size_t)threadIdx.x * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = off[w][threadIdx.x];
+      off[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  if (chunk >= nchunks) return;
   const long long base = (long long)chunk * TLSAN_SORT_CHUNK;
   const unsigned lt = (1u << lane) - 1u;
   for (int it = 0; it < TLSAN_SORT_CHUNK / 32; ++it) {
@@ -153,11 +171,11 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
   int* kout = keys_b; int* vout = vals_b;
   for (int pass = 0; pass < passes; ++pass) {
     const int* nv = pass == 0 ? nullptr : nvalid;
-    k_radix_hist<<<nblk, 256, 0, st>>>(kin, nocc, nv, 8 * pass, w.nchunks, hist);
+    k_radix_hist<<<nblk, 256, 0, st>>>(kin, nocc, nv, 8 * pass, w.nchunks, nblk, hist);
     TLSAN_CHECK_LAUNCH("k_radix_hist");
-    k_radix_scan<<<1, 1024, 0, st>>>(hist, 256 * w.nchunks, nvalid);
+    k_radix_scan<<<1, 1024, 0, st>>>(hist, 256 * nblk, nvalid);
     TLSAN_CHECK_LAUNCH("k_radix_scan");
-    k_radix_scatter<<<nblk, 256, 0, st>>>(kin, vin, nocc, nv, 8 * pass, w.nchunks, hist, kout, vout);
+    k_radix_scatter<<<nblk, 256, 0, st>>>(kin, vin, nocc, nv, 8 * pass, w.nchunks, nblk, hist, kout, vout);
     TLSAN_CHECK_LAUNCH("k_radix_scatter");
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }

@@ -27,13 +27,22 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
     for (int base = lo; base < hi; base += 32) {
       const int mine = base + lane < hi ? vals[base + lane] : 0;
       const int cnt = min(32, hi - base);
-#pragma unroll 4
-      for (int k = 0; k < cnt; ++k) {
-        const int occ = __shfl_sync(0xffffffffu, mine, k);
-        const int b = occ / SLOTS, j = occ - b * SLOTS;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(rows_i + ((size_t)b * SI + j) * 64) + lane);
-        acc.x += v.x; acc.y += v.y;
-        if (j == L + S) accb += __ldg(gscal + b);
+      for (int k0 = 0; k0 < cnt; k0 += 8) {   // 8 independent 256-B row reads in flight, added in order
+        float2 v[8];
+        float gb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int occ = __shfl_sync(0xffffffffu, mine, (k0 + k) & 31);
+          const int b = occ / SLOTS, j = occ - b * SLOTS;
+          const bool on = k0 + k < cnt;
+          v[k] = on ? __ldg(reinterpret_cast<const float2*>(rows_i + ((size_t)b * SI + j) * 64) + lane)
+                    : make_float2(0.f, 0.f);
+          gb[k] = (on && j == L + S) ? __ldg(gscal + b) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k0 + k < cnt) { acc.x += v[k].x; acc.y += v[k].y; accb += gb[k]; }
+        }
       }
     }
     reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
@@ -60,14 +69,19 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
 }
 
 // ------------------------------------------------------------------ dense partials
+// part_a: fused kernel A (short FWA, loss, sumsq; + dense grads in the FFMA variant)
+// part_b: long backward (long FWA, gamma, sumsq) ; part_c: k_dense_grad (dense kernel/bias), grid_c = 0 if unused
 __global__ void k_finalize1(const float* __restrict__ part_a, int grid_a, const float* __restrict__ part_b,
-                            int grid_b, float* __restrict__ dgrad) {
+                            int grid_b, const float* __restrict__ part_c, int grid_c, float* __restrict__ dgrad) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= TLSAN_PART) return;
-  const bool from_a = (e >= TLSAN_OFF_W1S && e < TLSAN_OFF_WD) || (e >= TLSAN_OFF_WD && e < TLSAN_OFF_BD + 64) ||
+  const bool is_dense = e >= TLSAN_OFF_WD && e < TLSAN_OFF_BD + 64;
+  const bool from_a = (e >= TLSAN_OFF_W1S && e < TLSAN_OFF_WD) || (is_dense && grid_c == 0) ||
                       e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ;
   const bool from_b = e < TLSAN_OFF_W1S || e == TLSAN_OFF_GAMMA || e == TLSAN_PART_SUMSQ;
   float s = 0.f;
+  if (is_dense)
+    for (int c = 0; c < grid_c; ++c) s += part_c[(size_t)c * TLSAN_PART + e];
   if (from_a)
     for (int c = 0; c < grid_a; ++c) s += part_a[(size_t)c * TLSAN_PART + e];
   if (from_b)
@@ -121,10 +135,17 @@ __global__ void __launch_bounds__(256) k_finalize2(const float* __restrict__ dgr
   float s = 0.f;
   for (int e = threadIdx.x; e < TLSAN_DENSE_COUNT; e += 256) s = fmaf(dgrad[e], dgrad[e], s);
   const float dense_sq = block_sum_256(s, sh);
+  __shared__ double shd[256];
+  {
+    double t = 0.0;
+    for (int c = threadIdx.x; c < ntsq; c += 256)
+      t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
+    shd[threadIdx.x] = t;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int c = 0; c < ntsq; ++c)
-      t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
+    for (int c = 0; c < 256; ++c) t += shd[c];
     const double sq = (double)dgrad[TLSAN_PART_SUMSQ] + (double)dense_sq + (double)reg * (double)reg * t;
     const float norm = (float)sqrt(sq);
     const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
@@ -254,9 +275,11 @@ int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, c
   return TLSAN_OK;
 }
 
-int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, float* dgrad, cudaStream_t st) {
+int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,
+                           cudaStream_t st) {
   k_finalize1<<<(TLSAN_PART + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.part_a), grid_a,
                                                         reinterpret_cast<const float*>(ws + w.part_b), grid_b,
+                                                        reinterpret_cast<const float*>(ws + w.part_c), grid_c,
                                                         dgrad);
   TLSAN_CHECK_LAUNCH("k_finalize1");
   return TLSAN_OK;
