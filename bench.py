@@ -81,47 +81,55 @@ def table_bytes(L):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, polled through NVML every ~2 ms
+    (nvidia-smi -lms cannot sample a sub-100-ms region)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
-
-    def start(self):
+        self.index, self.sm, self.bits, self.h, self.stop_flag, self.t = index, [], 0, None, False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                p = torch.cuda.get_device_properties(index)
+                bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                      # pragma: no cover
+            self.err = repr(e)
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.bits |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    self.bits |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.002)
+
+    def start(self):
+        if self.h is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max,
+                "samples": len(self.sm), "reasons": reasons}
 
 
 def cpu_port_throughput(L, budget_s, B=1024, seed=99):
@@ -188,7 +196,7 @@ def workload_config(args, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=65536)

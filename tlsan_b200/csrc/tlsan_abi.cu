@@ -58,7 +58,7 @@ static int check_dims(const tlsan_dims_t* d) {
   REQUIRE(d->S >= 1, TLSAN_E_DIMS, "S must be >= 1 (got %d)", d->S);
   REQUIRE(d->NI > 0 && d->NU > 0 && d->NC > 0, TLSAN_E_DIMS, "table sizes must be > 0");
   REQUIRE((long long)d->NI + d->NC + d->NU < (1ll << 30), TLSAN_E_DIMS, "row space too large");
-  REQUIRE((long long)d->B * (d->L + d->S + 3) < (1ll << 31) - 1, TLSAN_E_DIMS, "B*(L+S+3) overflows int32");
+  REQUIRE((long long)d->B * 2 * (d->L + d->S + 3) < (1ll << 31) - 1, TLSAN_E_DIMS, "B*(L+S+3) overflows int32");
   return TLSAN_OK;
 }
 

@@ -15,7 +15,7 @@
 #define TLSAN_PART_SUMSQ (TLSAN_DENSE_PAD + 1)
 #define TLSAN_PART 4456
 #define TLSAN_SCR 5            // 64-float slots per sample in scratch: do_long | o_long | max | 1/den | dz
-#define TLSAN_SORT_CHUNK 2048  // keys per warp in one radix pass
+#define TLSAN_SORT_CTA_KEYS 4096  // keys per CTA in one radix pass (16 warps x 256)
 
 void tlsan_set_error(const char* fmt, ...);
 
@@ -46,6 +46,7 @@ static inline size_t tlsan_align_up(size_t x, size_t a) { return (x + a - 1) / a
 // Workspace carve-up (byte offsets from a 256-B aligned base).
 struct TlsanWs {
   int SLOTS;  // occurrence slots per sample: L long, S short, candidate, u_cate, user
+  int SP, SPSH;  // slot stride = next power of two >= SLOTS (occurrence id = b * SP + j), log2(SP)
   int SI;     // slots with a 64-float payload (all but the user slot)
   int PU;     // floats per user payload: 32 (user_emb grad) + L (usert_emb grad), padded to 4
   int NR;     // unified row space NI + NC + NU
@@ -65,15 +66,18 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.SI = d.L + d.S + 2;
   w.PU = (int)tlsan_align_up(32 + d.L, 4);
   w.NR = d.NI + d.NC + d.NU;
-  w.nocc = (int64_t)d.B * w.SLOTS;
-  w.nchunks = (int)((w.nocc + TLSAN_SORT_CHUNK - 1) / TLSAN_SORT_CHUNK);
+  w.SPSH = 0;
+  while ((1 << w.SPSH) < w.SLOTS) ++w.SPSH;
+  w.SP = 1 << w.SPSH;
+  w.nocc = (int64_t)d.B * w.SP;
+  w.nchunks = (int)((w.nocc + TLSAN_SORT_CTA_KEYS - 1) / TLSAN_SORT_CTA_KEYS);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = tlsan_align_up(o + bytes, 256); return r; };
   w.keys_a = take(w.nocc * 4);
   w.keys_b = take(w.nocc * 4);
   w.vals_a = take(w.nocc * 4);
   w.vals_b = take(w.nocc * 4);
-  w.hist = take((size_t)256 * w.nchunks * 4 + 1024);
+  w.hist = take((size_t)256 * (w.nchunks + 1) * 4 + 1024);   // per-CTA digit counts + 256 digit totals
   w.nvalid = take(64);
   w.seg_off = take((size_t)(w.NR + 2) * 4);
   w.rows_i = take((size_t)d.B * w.SI * 64 * 4);

@@ -3,7 +3,7 @@
 // The sort is stable and keyed only by the row id, so inside a segment occurrences stay in
 // (sample, slot) order and the later segmented reduce adds them in one fixed order.
 //
-// Occurrence slots of sample b (id = b*SLOTS + j):
+// Occurrence slots of sample b (id = b*SP + j, SP = next power of two >= L+S+3):
 //   j <  L        long-term token j        key = hist_i[b][j]        (valid iff j < sl[b])
 //   j <  L+S      short-term token j-L     key = hist_i_new[b][j-L]  (valid iff j-L < sl_new[b])
 //   j == L+S      candidate                key = i[b]
@@ -12,117 +12,126 @@
 // Keys live in the unified row space of tlsan_params_t::emb.
 #include "tlsan_common.cuh"
 
-__global__ void k_build_keys(int B, int L, int S, int NI, int NC, const int* __restrict__ u,
-                             const int* __restrict__ cand, const int* __restrict__ c, const int* __restrict__ sl,
-                             const int* __restrict__ sl_new, const int* __restrict__ hist_i,
-                             const int* __restrict__ hist_i_new, int* __restrict__ keys) {
-  const int SLOTS = L + S + 3;
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)B * SLOTS) return;
-  const int b = (int)(g / SLOTS), j = (int)(g - (long long)b * SLOTS);
-  int key;
-  if (j < L) key = j < sl[b] ? hist_i[(size_t)b * L + j] : TLSAN_INVALID_KEY;
-  else if (j < L + S) key = (j - L) < sl_new[b] ? hist_i_new[(size_t)b * S + (j - L)] : TLSAN_INVALID_KEY;
-  else if (j == L + S) key = cand[b];
-  else if (j == L + S + 1) key = NI + c[b];
-  else key = NI + NC + u[b];
-  keys[g] = key;
+// key of occurrence id `g` straight from the batch (pass 1 never materialises the key array)
+struct KeySrc {
+  int B, L, S, spsh, NI, NC;
+  const int *u, *cand, *c, *sl, *sl_new, *hist_i, *hist_i_new;
+};
+__device__ __forceinline__ int occ_key(const KeySrc& k, long long g) {
+  const int b = (int)(g >> k.spsh), j = (int)(g & ((1 << k.spsh) - 1));
+  int key = TLSAN_INVALID_KEY;                      // also the padding slots j >= L+S+3
+  if (j < k.L) { if (j < __ldg(k.sl + b)) key = __ldg(k.hist_i + (size_t)b * k.L + j); }
+  else if (j < k.L + k.S) { if ((j - k.L) < __ldg(k.sl_new + b)) key = __ldg(k.hist_i_new + (size_t)b * k.S + (j - k.L)); }
+  else if (j == k.L + k.S) key = __ldg(k.cand + b);
+  else if (j == k.L + k.S + 1) key = k.NI + __ldg(k.c + b);
+  else if (j == k.L + k.S + 2) key = k.NI + k.NC + __ldg(k.u + b);
+  return key;
 }
 
-// One warp = one chunk of TLSAN_SORT_CHUNK consecutive keys, 8 warps (chunks) per CTA.
-// Histograms are kept per CTA: hist[digit][cta]; the scatter kernel recounts its 8 chunks
-// to split the CTA's range among its warps (keys are L2-resident, the recount is cheap).
-__device__ __forceinline__ void count_chunk(const int* __restrict__ keys, long long n, int chunk, int shift,
-                                            int lane, int* cnt /* [256] smem, zeroed */) {
-  const long long base = (long long)chunk * TLSAN_SORT_CHUNK;
-#pragma unroll 4
-  for (int it = 0; it < TLSAN_SORT_CHUNK / 32; ++it) {
-    const long long idx = base + it * 32 + lane;
-    const int key = idx < n ? keys[idx] : TLSAN_INVALID_KEY;
-    if (key != TLSAN_INVALID_KEY) atomicAdd(&cnt[(key >> shift) & 255], 1);
+// Radix pass geometry: a CTA of 16 warps owns TLSAN_SORT_CTA_KEYS = 4096 consecutive keys; a warp
+// owns 256 of them, loaded up front as 8 coalesced loads per lane (so the serial ranking loop
+// below runs from registers).  Histograms are kept per CTA: hist[digit][cta].
+#define SORT_WARPS 16
+#define SORT_KPL 8     // keys per lane
+#define SORT_KPW (32 * SORT_KPL)
+
+template <bool FROM_BATCH>
+__device__ __forceinline__ void load_keys(const int* __restrict__ keys, const KeySrc& src, long long n,
+                                          long long wbase, int lane, int (&k)[SORT_KPL]) {
+#pragma unroll
+  for (int it = 0; it < SORT_KPL; ++it) {
+    const long long idx = wbase + it * 32 + lane;
+    k[it] = idx < n ? (FROM_BATCH ? occ_key(src, idx) : keys[idx]) : TLSAN_INVALID_KEY;
   }
 }
 
-__global__ void __launch_bounds__(256) k_radix_hist(const int* __restrict__ keys, long long ncap,
-                                                    const int* __restrict__ nvalid, int shift, int nchunks,
-                                                    int nblk, int* __restrict__ hist) {
-  __shared__ int cnt[8][256];
+template <bool FROM_BATCH>
+__global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_hist(const int* __restrict__ keys, const KeySrc src,
+                                                                 long long ncap, const int* __restrict__ nvalid,
+                                                                 int shift, int nblk, int* __restrict__ hist) {
+  __shared__ int cnt[256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * 8 + warp;
-  for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
-  __syncwarp();
+  if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+  __syncthreads();
   const long long n = nvalid ? (long long)*nvalid : ncap;
-  if (chunk < nchunks) count_chunk(keys, n, chunk, shift, lane, cnt[warp]);
-  __syncthreads();
-  int t = 0;
+  int k[SORT_KPL];
+  load_keys<FROM_BATCH>(keys, src, n, ((long long)blockIdx.x * SORT_WARPS + warp) * SORT_KPW, lane, k);
 #pragma unroll
-  for (int w = 0; w < 8; ++w) t += cnt[w][threadIdx.x];
-  hist[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
+  for (int it = 0; it < SORT_KPL; ++it)
+    if (k[it] != TLSAN_INVALID_KEY) atomicAdd(&cnt[(k[it] >> shift) & 255], 1);
+  __syncthreads();
+  if (threadIdx.x < 256) hist[(size_t)threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// exclusive scan of hist[n] in place (single CTA of 1024 threads, contiguous span per thread)
-__global__ void __launch_bounds__(1024) k_radix_scan(int* __restrict__ hist, int n, int* __restrict__ total_out) {
-  __shared__ int wsum[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += hist[i];
-  int x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) wsum[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    int w = wsum[lane];
+// Exclusive scan of every digit's row hist[d][0..nblk) in place (one warp per digit, coalesced
+// 32-wide steps) and the digit totals -> tot[d].  The scatter kernel adds the scan over digits.
+__global__ void __launch_bounds__(256) k_radix_scan_rows(int* __restrict__ hist, int nblk, int* __restrict__ tot) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int* row = hist + (size_t)d * nblk;
+  int run = 0;
+  for (int base = 0; base < nblk; base += 32) {
+    const int i = base + lane;
+    const int v = i < nblk ? row[i] : 0;
+    int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += y;
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    wsum[lane] = w;
+    if (i < nblk) row[i] = run + x - v;
+    run += __shfl_sync(0xffffffffu, x, 31);
   }
-  __syncthreads();
-  int run = (warp > 0 ? wsum[warp - 1] : 0) + x - s;   // exclusive prefix of this thread's span
-  for (int i = lo; i < hi; ++i) {
-    const int v = hist[i];
-    hist[i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 1023) *total_out = wsum[31];
+  if (lane == 0) tot[d] = run;
 }
 
-__global__ void __launch_bounds__(256) k_radix_scatter(const int* __restrict__ keys_in, const int* __restrict__ vals_in,
-                                                       long long ncap, const int* __restrict__ nvalid, int shift,
-                                                       int nchunks, int nblk, const int* __restrict__ hist,
-                                                       int* __restrict__ keys_out, int* __restrict__ vals_out) {
-  __shared__ int off[8][256];
+template <bool FROM_BATCH>
+__global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
+    const int* __restrict__ keys_in, const KeySrc src, const int* __restrict__ vals_in, long long ncap,
+    const int* __restrict__ nvalid, int* __restrict__ nvalid_out, int shift, int nblk, const int* __restrict__ hist,
+    const int* __restrict__ tot, int* __restrict__ keys_out, int* __restrict__ vals_out) {
+  __shared__ int off[SORT_WARPS][256];
+  __shared__ int dbase[256];
+  __shared__ int wtot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * 8 + warp;
   for (int d = lane; d < 256; d += 32) off[warp][d] = 0;
   __syncwarp();
   const long long n = nvalid ? (long long)*nvalid : ncap;
-  if (chunk < nchunks) count_chunk(keys_in, n, chunk, shift, lane, off[warp]);
-  __syncthreads();
-  {  // counts -> start offsets: CTA base of the digit + counts of the lower warps
-    int run = hist[(size_t)threadIdx.x * nblk + blockIdx.x];
+  const long long wbase = ((long long)blockIdx.x * SORT_WARPS + warp) * SORT_KPW;
+  int k[SORT_KPL];
+  load_keys<FROM_BATCH>(keys_in, src, n, wbase, lane, k);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+  for (int it = 0; it < SORT_KPL; ++it)
+    if (k[it] != TLSAN_INVALID_KEY) atomicAdd(&off[warp][(k[it] >> shift) & 255], 1);
+  if (threadIdx.x < 256) {  // exclusive scan of the 256 digit totals (8 warps x 32)
+    const int v = tot[threadIdx.x];
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[warp] = x;
+    dbase[threadIdx.x] = x - v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {  // counts -> start offsets: digit base + CTA base in the digit + lower warps
+    int pre = 0;
+    for (int w = 0; w < warp; ++w) pre += wtot[w];
+    if (blockIdx.x == 0 && threadIdx.x == 255) *nvalid_out = pre + dbase[255] + tot[255];
+    int run = pre + dbase[threadIdx.x] + hist[(size_t)threadIdx.x * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
       const int c = off[w][threadIdx.x];
       off[w][threadIdx.x] = run;
       run += c;
     }
   }
   __syncthreads();
-  if (chunk >= nchunks) return;
-  const long long base = (long long)chunk * TLSAN_SORT_CHUNK;
   const unsigned lt = (1u << lane) - 1u;
-  for (int it = 0; it < TLSAN_SORT_CHUNK / 32; ++it) {
-    const long long idx = base + it * 32 + lane;
-    const int key = idx < n ? keys_in[idx] : TLSAN_INVALID_KEY;
+#pragma unroll
+  for (int it = 0; it < SORT_KPL; ++it) {      // in index order: the pass is stable
+    const int key = k[it];
     const bool act = key != TLSAN_INVALID_KEY;
     const int digit = act ? (key >> shift) & 255 : 256 + lane;  // inactive lanes match only themselves
     const unsigned m = __match_any_sync(0xffffffffu, digit);
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const int* __restrict__ k
     if (act && rank == 0) off[warp][digit] += __popc(m);
     __syncwarp();
     if (act) {
+      const long long idx = wbase + it * 32 + lane;
       keys_out[pos] = key;
       vals_out[pos] = vals_in ? vals_in[idx] : (int)idx;
     }
@@ -160,22 +170,30 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
   int* nvalid = reinterpret_cast<int*>(ws + w.nvalid);
   int* seg_off = reinterpret_cast<int*>(ws + w.seg_off);
   const long long nocc = w.nocc;
-  k_build_keys<<<(unsigned)((nocc + 255) / 256), 256, 0, st>>>(d.B, d.L, d.S, d.NI, d.NC, b.u, b.i, b.c, b.sl,
-                                                               b.sl_new, b.hist_i, b.hist_i_new, keys_a);
-  TLSAN_CHECK_LAUNCH("k_build_keys");
+  KeySrc src;
+  src.B = d.B; src.L = d.L; src.S = d.S; src.spsh = w.SPSH; src.NI = d.NI; src.NC = d.NC;
+  src.u = b.u; src.cand = b.i; src.c = b.c; src.sl = b.sl; src.sl_new = b.sl_new;
+  src.hist_i = b.hist_i; src.hist_i_new = b.hist_i_new;
   int bits = 1;
   while ((1ll << bits) < (long long)w.NR) ++bits;
   const int passes = (bits + 7) / 8;
-  const int nblk = (w.nchunks + 7) / 8;
-  const int* kin = keys_a; const int* vin = nullptr;
+  const int nblk = (int)((nocc + SORT_WARPS * SORT_KPW - 1) / (SORT_WARPS * SORT_KPW));
+  int* tot = hist + (size_t)256 * nblk;
+  const int* kin = nullptr; const int* vin = nullptr;
   int* kout = keys_b; int* vout = vals_b;
   for (int pass = 0; pass < passes; ++pass) {
     const int* nv = pass == 0 ? nullptr : nvalid;
-    k_radix_hist<<<nblk, 256, 0, st>>>(kin, nocc, nv, 8 * pass, w.nchunks, nblk, hist);
+    if (pass == 0) k_radix_hist<true><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, nocc, nv, 8 * pass, nblk, hist);
+    else k_radix_hist<false><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, nocc, nv, 8 * pass, nblk, hist);
     TLSAN_CHECK_LAUNCH("k_radix_hist");
-    k_radix_scan<<<1, 1024, 0, st>>>(hist, 256 * nblk, nvalid);
-    TLSAN_CHECK_LAUNCH("k_radix_scan");
-    k_radix_scatter<<<nblk, 256, 0, st>>>(kin, vin, nocc, nv, 8 * pass, w.nchunks, nblk, hist, kout, vout);
+    k_radix_scan_rows<<<32, 256, 0, st>>>(hist, nblk, tot);
+    TLSAN_CHECK_LAUNCH("k_radix_scan_rows");
+    if (pass == 0)
+      k_radix_scatter<true><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, vin, nocc, nv, nvalid, 8 * pass, nblk, hist,
+                                                             tot, kout, vout);
+    else
+      k_radix_scatter<false><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, vin, nocc, nv, nvalid, 8 * pass, nblk, hist,
+                                                              tot, kout, vout);
     TLSAN_CHECK_LAUNCH("k_radix_scatter");
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }

@@ -8,8 +8,11 @@
 #include "tlsan_common.cuh"
 
 // ------------------------------------------------------------------ segmented reduce
-// one warp per row of the unified row space; occurrences are visited in sorted (stable) order
-__global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int L, int S, int PU,
+// One warp per row of the unified row space; occurrences are visited in sorted (stable) order.
+// Item / category rows: each half-warp reads one 256-B gradient row per step (16 lanes x float4),
+// even occurrences in lanes 0-15, odd ones in lanes 16-31, 8 steps (16 rows) in flight; the two
+// half-sums are combined at the end -- a fixed order, independent of timing.
+__global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int L, int S, int spsh, int PU,
                                                     const int* __restrict__ seg_off, const int* __restrict__ vals,
                                                     const float* __restrict__ rows_i,
                                                     const float* __restrict__ rows_u,
@@ -19,33 +22,39 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int NR = NI + NC + NU;
   if (r >= NR) return;
-  const int SLOTS = L + S + 3, SI = L + S + 2;
+  const int SI = L + S + 2, smask = (1 << spsh) - 1;
   const int lo = seg_off[r], hi = seg_off[r + 1];
   if (r < NI + NC) {
-    float2 acc = make_float2(0.f, 0.f);
+    const int hw = lane >> 4, q = lane & 15;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float accb = 0.f;
     for (int base = lo; base < hi; base += 32) {
       const int mine = base + lane < hi ? vals[base + lane] : 0;
       const int cnt = min(32, hi - base);
-      for (int k0 = 0; k0 < cnt; k0 += 8) {   // 8 independent 256-B row reads in flight, added in order
-        float2 v[8];
+      for (int k0 = 0; k0 < cnt; k0 += 16) {
+        float4 v[8];
         float gb[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int occ = __shfl_sync(0xffffffffu, mine, (k0 + k) & 31);
-          const int b = occ / SLOTS, j = occ - b * SLOTS;
-          const bool on = k0 + k < cnt;
-          v[k] = on ? __ldg(reinterpret_cast<const float2*>(rows_i + ((size_t)b * SI + j) * 64) + lane)
-                    : make_float2(0.f, 0.f);
-          gb[k] = (on && j == L + S) ? __ldg(gscal + b) : 0.f;
+          const int kk = k0 + 2 * k + hw;
+          const int occ = __shfl_sync(0xffffffffu, mine, kk & 31);
+          const int b = occ >> spsh, j = occ & smask;
+          const bool on = kk < cnt;
+          v[k] = on ? __ldg(reinterpret_cast<const float4*>(rows_i + ((size_t)b * SI + j) * 64) + q)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          gb[k] = (on && j == L + S && q == 0) ? __ldg(gscal + b) : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (k0 + k < cnt) { acc.x += v[k].x; acc.y += v[k].y; accb += gb[k]; }
+          acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+          accb += gb[k];
         }
       }
     }
-    reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    accb += __shfl_xor_sync(0xffffffffu, accb, 16);
+    if (hw == 0) reinterpret_cast<float4*>(g_i + (size_t)r * 64)[q] = acc;
     if (r < NI && lane == 0) g_b[r] = accb;
   } else {
     const int u = r - NI - NC;
@@ -55,7 +64,7 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
       const int cnt = min(32, hi - base);
       for (int k = 0; k < cnt; ++k) {
         const int occ = __shfl_sync(0xffffffffu, mine, k);
-        const int b = occ / SLOTS;
+        const int b = occ >> spsh;
         const float* src = rows_u + (size_t)b * PU;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -71,22 +80,36 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
 // ------------------------------------------------------------------ dense partials
 // part_a: fused kernel A (short FWA, loss, sumsq; + dense grads in the FFMA variant)
 // part_b: long backward (long FWA, gamma, sumsq) ; part_c: k_dense_grad (dense kernel/bias), grid_c = 0 if unused
-__global__ void k_finalize1(const float* __restrict__ part_a, int grid_a, const float* __restrict__ part_b,
-                            int grid_b, const float* __restrict__ part_c, int grid_c, float* __restrict__ dgrad) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= TLSAN_PART) return;
-  const bool is_dense = e >= TLSAN_OFF_WD && e < TLSAN_OFF_BD + 64;
-  const bool from_a = (e >= TLSAN_OFF_W1S && e < TLSAN_OFF_WD) || (is_dense && grid_c == 0) ||
-                      e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ;
-  const bool from_b = e < TLSAN_OFF_W1S || e == TLSAN_OFF_GAMMA || e == TLSAN_PART_SUMSQ;
+// CTA = 32 entries x 8 row groups: group q adds partial rows q, q+8, ... (coalesced 128-B reads),
+// then the 8 group sums are added in order.  Fixed order, no atomics.
+__global__ void __launch_bounds__(256) k_finalize1(const float* __restrict__ part_a, int grid_a,
+                                                   const float* __restrict__ part_b, int grid_b,
+                                                   const float* __restrict__ part_c, int grid_c,
+                                                   float* __restrict__ dgrad) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
   float s = 0.f;
-  if (is_dense)
-    for (int c = 0; c < grid_c; ++c) s += part_c[(size_t)c * TLSAN_PART + e];
-  if (from_a)
-    for (int c = 0; c < grid_a; ++c) s += part_a[(size_t)c * TLSAN_PART + e];
-  if (from_b)
-    for (int c = 0; c < grid_b; ++c) s += part_b[(size_t)c * TLSAN_PART + e];
-  dgrad[e] = s;
+  if (e < TLSAN_PART) {
+    const bool is_dense = e >= TLSAN_OFF_WD && e < TLSAN_OFF_BD + 64;
+    const bool from_a = (e >= TLSAN_OFF_W1S && e < TLSAN_OFF_WD) || (is_dense && grid_c == 0) ||
+                        e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ;
+    const bool from_b = e < TLSAN_OFF_W1S || e == TLSAN_OFF_GAMMA || e == TLSAN_PART_SUMSQ;
+    if (is_dense)
+      for (int c = q; c < grid_c; c += 8) s += part_c[(size_t)c * TLSAN_PART + e];
+    if (from_a)
+      for (int c = q; c < grid_a; c += 8) s += part_a[(size_t)c * TLSAN_PART + e];
+    if (from_b)
+      for (int c = q; c < grid_b; c += 8) s += part_b[(size_t)c * TLSAN_PART + e];
+  }
+  sh[q][lane] = s;
+  __syncthreads();
+  if (q == 0 && e < TLSAN_PART) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][lane];
+    dgrad[e] = t;
+  }
 }
 
 __device__ __forceinline__ float block_sum_256(float v, float* sh) {
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(256) k_label_rank(int NI, const float* __restr
 // ------------------------------------------------------------------ launchers
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st) {
-  k_row_reduce<<<(w.NR + 7) / 8, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, d.S, w.PU,
+  k_row_reduce<<<(w.NR + 7) / 8, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU,
                                                reinterpret_cast<const int*>(ws + w.seg_off), sorted_vals,
                                                reinterpret_cast<const float*>(ws + w.rows_i),
                                                reinterpret_cast<const float*>(ws + w.rows_u),
@@ -277,7 +300,7 @@ int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, c
 
 int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,
                            cudaStream_t st) {
-  k_finalize1<<<(TLSAN_PART + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.part_a), grid_a,
+  k_finalize1<<<(TLSAN_PART + 31) / 32, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.part_a), grid_a,
                                                         reinterpret_cast<const float*>(ws + w.part_b), grid_b,
                                                         reinterpret_cast<const float*>(ws + w.part_c), grid_c,
                                                         dgrad);
