@@ -80,56 +80,74 @@ def table_bytes(L):
     return 4 * (33 * NI + 32 * NU + L * NU + 32 * NC)
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+bus = sys.argv[1]
+try:
+    h = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), bits, flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region, polled through NVML every ~2 ms
-    (nvidia-smi -lms cannot sample a sub-100-ms region)."""
+    """SM clock + throttle reasons DURING the timed region: a side process polls NVML every
+    ~2 ms (started early; samples are filtered to the [mark_begin, mark_end] window)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index):
-        self.index, self.sm, self.bits, self.h, self.stop_flag, self.t = index, [], 0, None, False, None
+        self.proc, self.t0, self.t1 = None, None, None
         try:
-            import pynvml
             import torch
-            self.nv = pynvml
-            pynvml.nvmlInit()
-            try:
-                p = torch.cuda.get_device_properties(index)
-                bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
-                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
-            except Exception:
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            p = torch.cuda.get_device_properties(index)
+            bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, bus, str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.lines = []
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
         except Exception as e:                      # pragma: no cover
             self.err = repr(e)
-            self.h = None
 
-    def _loop(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    self.bits |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    self.bits |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            except Exception:
-                pass
-            time.sleep(0.002)
+    def mark_begin(self):
+        self.t0 = time.time()
 
-    def start(self):
-        if self.h is not None:
-            self.t = threading.Thread(target=self._loop, daemon=True)
-            self.t.start()
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.h is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
-        self.stop_flag = True
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml sampler unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
         self.t.join(timeout=1)
-        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
-        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max,
-                "samples": len(self.sm), "reasons": reasons}
+        sm, bits, mx = [], 0, None
+        for ln in self.lines:
+            f = ln.split()
+            try:
+                if f[0] == "max":
+                    mx = int(f[1])
+                elif self.t0 <= float(f[0]) <= self.t1:
+                    sm.append(int(f[1])); bits |= int(f[2])
+            except Exception:
+                pass
+        reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": reasons}
 
 
 def cpu_port_throughput(L, budget_s, B=1024, seed=99):
@@ -248,24 +266,26 @@ def main():
     for w in range(args.warmup):
         model.train_staged(dev_batches[w % len(dev_batches)], 1.0)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.tlsan_launch_count()
     _lib.check(lib.tlsan_profile_begin(args.steps))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if clocks:
+        clocks.mark_begin()
     e0.record()
     for k in range(args.steps):
         model.train_staged(dev_batches[k % len(dev_batches)], 1.0)
     e1.record()
     barrier()
+    if clocks:
+        clocks.mark_end()
     ms = e0.elapsed_time(e1)
     phase = np.zeros((args.steps, len(_lib.PHASES)), np.float32)
     nrec = C.c_int32()
     _lib.check(lib.tlsan_profile_end(phase.ctypes.data, C.byref(nrec)))
     launches = lib.tlsan_launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if clocks else None
     t = torch.tensor([ms], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

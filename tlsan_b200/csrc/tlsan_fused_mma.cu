@@ -27,11 +27,10 @@ struct BMat { uint32_t h0, h1, l0, l1; };          // B fragment (b0, b1) split 
 struct FwaW { BMat W1, W2; float b1[2], b2[2]; };  // forward weights of one FWA
 struct FwaWT { BMat W2T, W1T; };                   // transposed fragments for the backward
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> tf32 by truncation (one LOP3).  `cvt.rna.tf32.f32` is emulated with ~5 integer
+// instructions on sm_100a (ncu: it was a quarter of the backward tile); with the hi/lo split
+// truncation loses nothing: lo = x - hi is exact and its own truncation error is ~2^-21 relative.
+__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ BMat make_b(float b0, float b1) {
   BMat m;
   m.h0 = to_tf32(b0); m.h1 = to_tf32(b1);
@@ -211,36 +210,6 @@ __device__ __forceinline__ const float* row_ptr(const FArgs& a, const LaneGeo& L
   return a.emb + (size_t)(L.half ? crow : id) * 32 + L.col;
 }
 
-// Per-lane slice of one sample's metadata, fetched one sample AHEAD of the compute in two
-// stages so that no dependent load ever sits directly behind the load it depends on
-// (stage 1: addresses known from b ; stage 2: addresses that need stage-1 values).
-struct SMeta {
-  int u, ell, s, cand, uc;
-  int lid; float lht; int sid;            // stage 1: long token `lane`, short item `lane`
-  float lpu; int lcrow, scrow, ccrow;     // stage 2
-};
-__device__ __forceinline__ void meta_stage1(const FArgs& a, int b, int lane, SMeta& m) {
-  m.u = __ldg(a.u + b); m.ell = __ldg(a.sl + b); m.s = __ldg(a.sl_new + b);
-  m.cand = __ldg(a.i + b); m.uc = __ldg(a.c + b);
-  m.lid = lane < a.L ? __ldg(a.hist_i + (size_t)b * a.L + lane) : 0;
-  m.lht = lane < a.L ? __ldg(a.hist_t + (size_t)b * a.L + lane) : 0.f;
-  m.sid = lane < a.S ? __ldg(a.hist_i_new + (size_t)b * a.S + lane) : 0;
-}
-__device__ __forceinline__ void meta_stage2(const FArgs& a, int lane, SMeta& m) {
-  if (lane >= m.ell) { m.lid = 0; m.lht = 0.f; }   // never dereference padding ids
-  if (lane >= m.s) m.sid = 0;
-  m.lpu = lane < m.ell ? __ldg(a.usert + (size_t)m.u * a.L + lane) : 0.f;
-  m.lcrow = a.NI + __ldg(a.icl + m.lid);
-  m.scrow = a.NI + __ldg(a.icl + m.sid);
-  m.ccrow = a.NI + __ldg(a.icl + m.cand);
-}
-__device__ __forceinline__ LongMeta long_meta_round0(const SMeta& m, float gamma) {
-  LongMeta me;
-  me.id = m.lid; me.crow = m.lcrow; me.ht = m.lht;
-  me.pt = m.lpu * m.lht; me.tau = gamma * me.pt;
-  return me;
-}
-
 // one tile's inputs: two gathered token slices (float2 each) and their tau
 struct Pair { float2 eA, eB; float tA, tB; bool okB; };
 __device__ __forceinline__ Pair fetch_pair(const FArgs& a, const LaneGeo& L, const LongMeta& me, int j, int cnt) {
@@ -256,23 +225,20 @@ __device__ __forceinline__ Pair fetch_pair(const FArgs& a, const LaneGeo& L, con
 }
 
 // long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state
-__device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, int b, const SMeta& m, float gamma,
+__device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, int b, int u, int ell, float gamma,
                                              const FwaW& w, Soft2& st) {
   st.init();
-  for (int r0 = 0; r0 < m.ell; r0 += 32) {
-    const LongMeta me = r0 == 0 ? long_meta_round0(m, gamma) : load_long_meta(a, b, m.u, r0 + L.lane, m.ell, gamma);
-    const int cnt = min(32, m.ell - r0);
-    Pair cur = fetch_pair(a, L, me, 0, cnt);
+  for (int r0 = 0; r0 < ell; r0 += 32) {
+    const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
+    const int cnt = min(32, ell - r0);
     for (int j = 0; j < cnt; j += 2) {
-      Pair nxt = cur;
-      if (j + 2 < cnt) nxt = fetch_pair(a, L, me, j + 2, cnt);    // gathers of the next tile in flight
+      const Pair cur = fetch_pair(a, L, me, j, cnt);
       const float x[4] = {cur.eA.x * cur.tA, cur.eA.y * cur.tA, cur.okB ? cur.eB.x * cur.tB : 0.f,
                           cur.okB ? cur.eB.y * cur.tB : 0.f};
       float m1[4], m2[4];
       tile_maps(x, w, m1, m2);
       st.push(m2[0], m2[1], x[0], x[1]);
       if (cur.okB) st.push(m2[2], m2[3], x[2], x[3]);
-      cur = nxt;
     }
   }
 }
@@ -326,20 +292,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, con
   float* vec = sm.vec[warp];
   const int nwarps = gridDim.x * MMA_WARPS;
 
-  SMeta mt;
-  {
-    const int b0 = blockIdx.x * MMA_WARPS + warp;
-    if (b0 < a.B) { meta_stage1(a, b0, L.lane, mt); meta_stage2(a, L.lane, mt); }
-  }
   for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
-    const SMeta m = mt;
-    const int u = m.u, s = m.s, cand = m.cand, uc = m.uc;
-    const bool has_next = b + nwarps < a.B;
-    if (has_next) meta_stage1(a, b + nwarps, L.lane, mt);        // next sample, stage 1
+    const int u = __ldg(a.u + b), ell = __ldg(a.sl + b), s = __ldg(a.sl_new + b);
+    const int cand = __ldg(a.i + b), uc = __ldg(a.c + b);
     // ---- long-term FWA forward
     Soft2 st;
-    long_forward(a, L, b, m, gamma, wl, st);
-    if (has_next) meta_stage2(a, L.lane, mt);                    // next sample, stage 2
+    long_forward(a, L, b, u, ell, gamma, wl, st);
     float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
     if (TRAIN) {
       float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
@@ -359,12 +317,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, con
     Soft2 ss; ss.init();
     for (int r0 = 0; r0 < ntok; r0 += 32) {       // round covers tokens r0 .. r0+31 (token n >= 1 is item n-1)
       // lane l holds the meta of item r0 + l, i.e. of token r0 + l + 1
-      int id_l = m.sid, crow_l = m.scrow;
-      if (r0 > 0) {
-        const int item = r0 + L.lane;
-        id_l = item < s ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
-        crow_l = a.NI + __ldg(a.icl + id_l);
-      }
+      const int item = r0 + L.lane;
+      const int id_l = item < s ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
+      const int crow_l = a.NI + __ldg(a.icl + id_l);
       const int cnt = min(32, ntok - r0);          // tokens in this round
       for (int j = 0; j < cnt; j += 2) {
         float x[4]; bool okB;
@@ -395,7 +350,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, con
     // ---- user vector, candidate, logit (model.py:84-95,135-137)
     const float2 p = ldg2(a.emb + (size_t)(L.half ? a.NI + uc : a.NI + a.NC + u) * 32 + L.col);
     const float ut[2] = {v[0] + p.x, v[1] + p.y};
-    const float2 q = ldg2(row_ptr(a, L, cand, m.ccrow));
+    const int ccrow = a.NI + __ldg(a.icl + cand);
+    const float2 q = ldg2(row_ptr(a, L, cand, ccrow));
     const float logit = warp_sum_f(fmaf(ut[0], q.x, ut[1] * q.y)) + __ldg(a.item_b + cand);
 
     if (!TRAIN) {
@@ -429,12 +385,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, con
     // short-term FWA backward, d v = du
     float dz[2] = {0.f, 0.f};
     for (int r0 = 0; r0 < ntok; r0 += 32) {
-      int id_l = m.sid, crow_l = m.scrow;
-      if (r0 > 0) {
-        const int item = r0 + L.lane;
-        id_l = item < s ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
-        crow_l = a.NI + __ldg(a.icl + id_l);
-      }
+      const int item = r0 + L.lane;
+      const int id_l = item < s ? __ldg(a.hist_i_new + (size_t)b * a.S + item) : 0;
+      const int crow_l = a.NI + __ldg(a.icl + id_l);
       const int cnt = min(32, ntok - r0);
       for (int j = 0; j < cnt; j += 2) {
         float x[4], dx[4];
@@ -531,16 +484,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
   float ggamma = 0.f, sq_acc = 0.f;
   const int nwarps = gridDim.x * MMA_WARPS;
 
-  SMeta mt;
-  {
-    const int b0 = blockIdx.x * MMA_WARPS + warp;
-    if (b0 < a.B) { meta_stage1(a, b0, L.lane, mt); meta_stage2(a, L.lane, mt); }
-  }
   for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
-    const SMeta m = mt;
-    const int u = m.u, ell = m.ell;
-    const bool has_next = b + nwarps < a.B;
-    if (has_next) meta_stage1(a, b + nwarps, L.lane, mt);
+    const int u = __ldg(a.u + b), ell = __ldg(a.sl + b);
     const float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
     const float2 dol2 = *reinterpret_cast<const float2*>(sc);
     const float2 o2 = *reinterpret_cast<const float2*>(sc + 64);
@@ -549,14 +494,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
     const float dol[2] = {dol2.x, dol2.y}, o[2] = {o2.x, o2.y}, mx[2] = {mx2.x, mx2.y}, inv[2] = {inv2.x, inv2.y};
     float* ru = a.rows_u + (size_t)b * a.PU + 32;
     for (int r0 = 0; r0 < ell; r0 += 32) {
-      const LongMeta me = r0 == 0 ? long_meta_round0(m, gamma) : load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
+      const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
       const int cnt = min(32, ell - r0);
       float dtau_l = 0.f;                          // lane j collects d tau of token r0 + j
-      Pair cur = fetch_pair(a, L, me, 0, cnt);
       for (int j = 0; j < cnt; j += 2) {
-        Pair nxt = cur;
-        if (j + 2 < cnt) nxt = fetch_pair(a, L, me, j + 2, cnt);
-        else if (r0 == 0 && has_next) meta_stage2(a, L.lane, mt);   // last tile: next sample's stage 2
+        const Pair cur = fetch_pair(a, L, me, j, cnt);
         const bool okB = cur.okB;
         const float2 eA = cur.eA, eB = cur.eB;
         const float tA = cur.tA, tB = cur.tB;
@@ -576,7 +518,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
           const float dtB = warp_sum_f(fmaf(dx[2], eB.x, dx[3] * eB.y));
           if (L.lane == j + 1) dtau_l = dtB;
         }
-        cur = nxt;
       }
       if (L.lane < cnt) {
         ggamma = fmaf(dtau_l, me.pt, ggamma);
