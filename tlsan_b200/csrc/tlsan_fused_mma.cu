@@ -14,10 +14,12 @@
 // The per-feature softmax over the sequence (model.py:386) is an online softmax per lane.
 // A warp touches one token as one 256-B coalesced float2 access (item row | cate row).
 //
-//   k_score_mma   forward, 1 or 2 candidates (Model.eval_auc, model.py:237-263)
-//   k_fwd_a_mma   forward + loss + backward of logit / short FWA / dense input (model.py:84-137,164-172)
-//   k_bwd_long_mma  backward of the long FWA and of the time-aware position term (model.py:98-109)
-//   k_dense_grad  dWd = O^T dZ, dbd = sum dZ over the batch (tf.layers.dense, model.py:347)
+//   k_fwd_mma<0>     scoring, fused forward, 1 or 2 candidates (Model.eval_auc, model.py:237-263)
+//   k_fwd_mma<1>     long-term FWA forward (model.py:98-109,334-345)
+//   k_dense_fwd_mma  z = o_long Wd + bd as one batched GEMM (model.py:347)
+//   k_fwd_mma<2>     short FWA forward + logit + loss + backward of logit / short FWA (model.py:135-137,164-172,350-364)
+//   k_dense_bwd_mma  d o_long = dz Wd^T ; dWd = O^T dZ ; dbd
+//   k_bwd_long_mma   backward of the long FWA and of the time-aware position term (model.py:98-109)
 #include "tlsan_fused.cuh"
 
 #define MMA_THREADS 256
@@ -245,11 +247,10 @@ __device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, i
 
 // shared-memory image of the dense layer (natural layouts: lane reads float2 at [k][f0])
 struct SmemMma {
-  float wd[64 * 64];    // Wd[k][f]
-  float wdt[64 * 64];   // Wd^T: wdt[j][f] = Wd[f][j]
+  float red[MMA_WARPS][160];     // MODE 2: end-of-kernel reduction staging
+  float vec[MMA_WARPS][64];      // MODE 0: per-warp staging of o_long
   float bd[64];
-  float vec[MMA_WARPS][64];  // per-warp staging of o_long / dz
-  float red[MMA_WARPS][160];
+  float wd[64 * 64];             // MODE 0: Wd[k][f]
 };
 
 // out[jj] += sum_k vec[k] * W[k][f0 + jj]
@@ -268,50 +269,63 @@ __device__ __forceinline__ void dense2(const float* __restrict__ vec, const floa
   }
 }
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, const int ncand) {
+// MODE 0: scoring, fully fused (long FWA -> dense -> short FWA -> logits), dense as FFMA from smem
+// MODE 1: training, long-term FWA forward only: o_long and its softmax statistics -> scratch
+// MODE 2: training, short-term FWA forward (z read from scratch) + logit + loss + backward of
+//         logit / short FWA -> gradient rows, dz -> scratch.  The 64x64 dense layer between
+//         MODE 1 and MODE 2 (and its backward) runs as batched tensor-core GEMMs (k_dense_*).
+template <int MODE>
+__global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(const FArgs a, const int ncand) {
+  constexpr bool TRAIN = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemMma& sm = *reinterpret_cast<SmemMma*>(smem_raw);
-  for (int e = threadIdx.x; e < 64 * 64; e += MMA_THREADS) {
-    const float wv = a.dense[TLSAN_OFF_WD + e];
-    sm.wd[e] = wv;
-    if (TRAIN) sm.wdt[(e & 63) * 64 + (e >> 6)] = wv;
+  if (MODE == 0) {
+    for (int e = threadIdx.x; e < 64 * 64; e += MMA_THREADS) sm.wd[e] = a.dense[TLSAN_OFF_WD + e];
+    if (threadIdx.x < 64) sm.bd[threadIdx.x] = a.dense[TLSAN_OFF_BD + threadIdx.x];
+    __syncthreads();
   }
-  if (threadIdx.x < 64) sm.bd[threadIdx.x] = a.dense[TLSAN_OFF_BD + threadIdx.x];
-  __syncthreads();
 
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
   const float gamma = a.dense[TLSAN_OFF_GAMMA];
-  const FwaW wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
-  const FwaW ws = load_fwa(a.dense, TLSAN_OFF_W1S, L.g, L.t);
+  FwaW wl, ws;
   FwaWT wst;
   FwaGrad G;
   float loss_acc = 0.f, sq_acc = 0.f;
+  if (MODE != 2) wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+  if (MODE != 1) ws = load_fwa(a.dense, TLSAN_OFF_W1S, L.g, L.t);
   if (TRAIN) { wst = load_fwa_t(a.dense, TLSAN_OFF_W1S, L.g, L.t); G.init(); }
   float* vec = sm.vec[warp];
   const int nwarps = gridDim.x * MMA_WARPS;
 
   for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
-    const int u = __ldg(a.u + b), ell = __ldg(a.sl + b), s = __ldg(a.sl_new + b);
-    const int cand = __ldg(a.i + b), uc = __ldg(a.c + b);
-    // ---- long-term FWA forward
-    Soft2 st;
-    long_forward(a, L, b, u, ell, gamma, wl, st);
-    float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
-    if (TRAIN) {
-      float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
-      st2(sc + 64, o[0], o[1]);
-      st2(sc + 128, st.mx[0], st.mx[1]);
-      st2(sc + 192, 1.f / st.den[0], 1.f / st.den[1]);
-    }
-    __syncwarp();
-    st2(vec + L.f0, o[0], o[1]);
-    __syncwarp();
-    // ---- z = o_long Wd + bd   (model.py:347)
+    const int u = __ldg(a.u + b);
     float z[2] = {0.f, 0.f};
-    dense2(vec, sm.wd, L.f0, z);
-    z[0] += sm.bd[L.f0]; z[1] += sm.bd[L.f0 + 1];
+    if (MODE != 2) {
+      // ---- long-term FWA forward
+      const int ell = __ldg(a.sl + b);
+      Soft2 st;
+      long_forward(a, L, b, u, ell, gamma, wl, st);
+      const float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
+      if (MODE == 1) {
+        float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
+        st2(sc + 64, o[0], o[1]);
+        st2(sc + 128, st.mx[0], st.mx[1]);
+        st2(sc + 192, 1.f / st.den[0], 1.f / st.den[1]);
+        continue;
+      }
+      __syncwarp();
+      st2(vec + L.f0, o[0], o[1]);
+      __syncwarp();
+      // ---- z = o_long Wd + bd   (model.py:347)
+      dense2(vec, sm.wd, L.f0, z);
+      z[0] += sm.bd[L.f0]; z[1] += sm.bd[L.f0 + 1];
+    } else {
+      const float2 zz = *reinterpret_cast<const float2*>(a.scratch + (size_t)b * (TLSAN_SCR * 64) + 320 + L.f0);
+      z[0] = zz.x; z[1] = zz.y;
+    }
+    const int s = __ldg(a.sl_new + b);
+    const int cand = __ldg(a.i + b), uc = __ldg(a.c + b);
     // ---- short-term FWA forward over s+1 tokens (model.py:350-364)
     const int ntok = s + 1;
     Soft2 ss; ss.init();
@@ -418,17 +432,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_fwd_a_mma(const FArgs a, con
         }
       }
     }
-    // ---- d o_long = dz Wd^T ; dz and o_long go to scratch for k_dense_grad / k_bwd_long_mma
-    __syncwarp();
-    st2(vec + L.f0, dz[0], dz[1]);
-    __syncwarp();
-    float dol[2] = {0.f, 0.f};
-    dense2(vec, sm.wdt, L.f0, dol);
-    {
-      float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
-      st2(sc, dol[0], dol[1]);
-      st2(sc + 256, dz[0], dz[1]);
-    }
+    // ---- dz -> scratch: k_dense_bwd_mma turns it into d o_long, dWd and dbd
+    st2(a.scratch + (size_t)b * (TLSAN_SCR * 64) + 256 + L.f0, dz[0], dz[1]);
   }
 
   if (TRAIN) {
@@ -567,62 +572,172 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
   }
 }
 
-// ------------------------------------------------------------------ dWd = O^T dZ, dbd = sum dZ
-// Each CTA owns a contiguous range of samples; thread (r4, c4) accumulates a 4x4 block of the
-// 64x64 kernel gradient over the range in sample order; partials go to part[cta] (fixed-order
-// second stage in k_finalize1).
-__global__ void __launch_bounds__(256) k_dense_grad(const float* __restrict__ scratch, int B, float* __restrict__ part) {
-  __shared__ __align__(16) float so[32 * 64];
-  __shared__ __align__(16) float sz[32 * 64];
-  const int per = (B + gridDim.x - 1) / gridDim.x;
-  const int lo = blockIdx.x * per, hi = min(B, lo + per);
-  const int r4 = threadIdx.x >> 4, c4 = threadIdx.x & 15;
-  float acc[16];
+// ------------------------------------------------------------------ dense 64x64 layer as batched GEMMs
+// tf.layers.dense (model.py:347) over the whole batch on the tensor cores (3xTF32 mma.sync):
+//   k_dense_fwd_mma : Z = O Wd + bd                       (scratch slot 1 -> slot 5)
+//   k_dense_bwd_mma : dO = dZ Wd^T (slot 4 -> slot 0) ; dWd = O^T dZ, dbd = sum dZ -> part[cta]
+// The B operand is pre-split into tf32 hi / lo images in shared memory, row stride 68 floats
+// (fragment reads are bank-conflict free); A slot t <-> column 2t, slot t+4 <-> column 2t+1.
+#define GEMM_LD 68
+struct SmemGemm { float hi[64 * GEMM_LD]; float lo[64 * GEMM_LD]; };
+
+__device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&h)[4], uint32_t (&l)[4]) {
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-  float bsum = 0.f;   // threads < 64: dbd[threadIdx.x]
-  for (int base = lo; base < hi; base += 32) {
-    const int n = min(32, hi - base);
-    for (int e = threadIdx.x; e < 32 * 16; e += 256) {   // float4 granularity: 16 per 64-float row
-      const int sidx = e >> 4, q = e & 15;
+  for (int i = 0; i < 4; ++i) {
+    h[i] = to_tf32(x[i]);
+    l[i] = to_tf32(x[i] - __uint_as_float(h[i]));
+  }
+}
+// acc += A(16x8) B(8x8), B fragment read from the hi/lo images at rows (k0+2t, k0+2t+1), column n0+g
+__device__ __forceinline__ void gemm_step(float (&acc)[4], const uint32_t (&h)[4], const uint32_t (&l)[4],
+                                          const SmemGemm& sb, int k0, int n0, int g, int t) {
+  const int i0 = (k0 + 2 * t) * GEMM_LD + n0 + g, i1 = i0 + GEMM_LD;
+  const uint32_t bh0 = __float_as_uint(sb.hi[i0]), bh1 = __float_as_uint(sb.hi[i1]);
+  const uint32_t bl0 = __float_as_uint(sb.lo[i0]), bl1 = __float_as_uint(sb.lo[i1]);
+  mma_tf32(acc, l[0], l[2], l[1], l[3], bh0, bh1);
+  mma_tf32(acc, h[0], h[2], h[1], h[3], bl0, bl1);
+  mma_tf32(acc, h[0], h[2], h[1], h[3], bh0, bh1);
+}
+
+__global__ void __launch_bounds__(128) k_dense_fwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
+                                                       int B) {
+  __shared__ SmemGemm sb;
+  __shared__ float sbd[64];
+  for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+    const float w = dense[TLSAN_OFF_WD + e];
+    const float h = __uint_as_float(to_tf32(w));
+    sb.hi[(e >> 6) * GEMM_LD + (e & 63)] = h;
+    sb.lo[(e >> 6) * GEMM_LD + (e & 63)] = __uint_as_float(to_tf32(w - h));
+  }
+  if (threadIdx.x < 64) sbd[threadIdx.x] = dense[TLSAN_OFF_BD + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ntiles = (B + 15) / 16;
+  for (int tile = blockIdx.x * 4 + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * 4) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const bool vA = rA < B, vB = rB < B;
+    const float* pA = scratch + (size_t)rA * (TLSAN_SCR * 64) + 64 + 2 * t;
+    const float* pB = scratch + (size_t)rB * (TLSAN_SCR * 64) + 64 + 2 * t;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      acc[nt][0] = acc[nt][2] = sbd[nt * 8 + 2 * t];
+      acc[nt][1] = acc[nt][3] = sbd[nt * 8 + 2 * t + 1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const float2 a = vA ? *reinterpret_cast<const float2*>(pA + ks * 8) : make_float2(0.f, 0.f);
+      const float2 c = vB ? *reinterpret_cast<const float2*>(pB + ks * 8) : make_float2(0.f, 0.f);
+      const float x[4] = {a.x, a.y, c.x, c.y};
+      uint32_t h[4], l[4];
+      split4(x, h, l);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, nt * 8, g, t);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (vA) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + 320 + nt * 8 + 2 * t, acc[nt][0], acc[nt][1]);
+      if (vB) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + 320 + nt * 8 + 2 * t, acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
+#define TILE_LD 72
+__global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
+                                                       int B, float* __restrict__ part) {
+  __shared__ SmemGemm sb;                          // Wd^T: image[j][f] = Wd[f][j]
+  __shared__ __align__(16) float so[16 * TILE_LD];
+  __shared__ __align__(16) float sz[16 * TILE_LD];
+  for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+    const float w = dense[TLSAN_OFF_WD + e];        // Wd[f = e>>6][j = e&63]
+    const float h = __uint_as_float(to_tf32(w));
+    sb.hi[(e & 63) * GEMM_LD + (e >> 6)] = h;
+    sb.lo[(e & 63) * GEMM_LD + (e >> 6)] = __uint_as_float(to_tf32(w - h));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int ntiles = (B + 15) / 16;
+  const int per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int t_lo = blockIdx.x * per, t_hi = min(ntiles, t_lo + per);
+  float accw[8][4];                                 // dWd rows 16*warp .. +15, all 64 columns
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) accw[nt][0] = accw[nt][1] = accw[nt][2] = accw[nt][3] = 0.f;
+  float bsum = 0.f;                                 // threads < 64: dbd[threadIdx.x]
+  for (int tile = t_lo; tile < t_hi; ++tile) {
+    __syncthreads();                                // previous tile fully consumed (and sb written)
+    for (int e = threadIdx.x; e < 16 * 16; e += 128) {
+      const int r = e >> 4, q = e & 15, row = tile * 16 + r;
       float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vz = vo;
-      if (sidx < n) {
-        const float* sc = scratch + (size_t)(base + sidx) * (TLSAN_SCR * 64);
+      if (row < B) {
+        const float* sc = scratch + (size_t)row * (TLSAN_SCR * 64);
         vo = *reinterpret_cast<const float4*>(sc + 64 + 4 * q);
         vz = *reinterpret_cast<const float4*>(sc + 256 + 4 * q);
       }
-      *reinterpret_cast<float4*>(so + sidx * 64 + 4 * q) = vo;
-      *reinterpret_cast<float4*>(sz + sidx * 64 + 4 * q) = vz;
+      *reinterpret_cast<float4*>(so + r * TILE_LD + 4 * q) = vo;
+      *reinterpret_cast<float4*>(sz + r * TILE_LD + 4 * q) = vz;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int ss = 0; ss < 32; ++ss) {
-      const float4 o4 = *reinterpret_cast<const float4*>(so + ss * 64 + 4 * r4);
-      const float4 z4 = *reinterpret_cast<const float4*>(sz + ss * 64 + 4 * c4);
-      const float oo[4] = {o4.x, o4.y, o4.z, o4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    // (a) d o_long = dZ Wd^T : this warp computes output columns 16*warp .. +15 for the 16 rows
+    {
+      float acc[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i * 4 + j] = fmaf(oo[i], zz[j], acc[i * 4 + j]);
+      for (int ks = 0; ks < 8; ++ks) {
+        const float2 a = *reinterpret_cast<const float2*>(sz + g * TILE_LD + ks * 8 + 2 * t);
+        const float2 c = *reinterpret_cast<const float2*>(sz + (g + 8) * TILE_LD + ks * 8 + 2 * t);
+        const float x[4] = {a.x, a.y, c.x, c.y};
+        uint32_t h[4], l[4];
+        split4(x, h, l);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, warp * 16 + nt * 8, g, t);
+      }
+      const int rA = tile * 16 + g, rB = rA + 8;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = warp * 16 + nt * 8 + 2 * t;
+        if (rA < B) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + col, acc[nt][0], acc[nt][1]);
+        if (rB < B) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + col, acc[nt][2], acc[nt][3]);
+      }
     }
-    if (threadIdx.x < 64)
-      for (int ss = 0; ss < 32; ++ss) bsum += sz[ss * 64 + threadIdx.x];
-    __syncthreads();
+    // (b) dWd[k][j] += sum_s O[s][k] dZ[s][j] : M = k (rows 16*warp..), N = j, K = the 16 samples
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int s0 = ks * 8, m0 = warp * 16;
+      // A[m][slot] = O[s0 + slot][m0 + m] : a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4)
+      const float xa[4] = {so[(s0 + t) * TILE_LD + m0 + g], so[(s0 + t + 4) * TILE_LD + m0 + g],
+                           so[(s0 + t) * TILE_LD + m0 + g + 8], so[(s0 + t + 4) * TILE_LD + m0 + g + 8]};
+      uint32_t h[4], l[4];
+      split4(xa, h, l);   // mma3 order: a0 = x[0], a1 = x[2], a2 = x[1], a3 = x[3]
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float b0 = sz[(s0 + t) * TILE_LD + nt * 8 + g], b1 = sz[(s0 + t + 4) * TILE_LD + nt * 8 + g];
+        const uint32_t bh0 = to_tf32(b0), bh1 = to_tf32(b1);
+        const uint32_t bl0 = to_tf32(b0 - __uint_as_float(bh0)), bl1 = to_tf32(b1 - __uint_as_float(bh1));
+        mma_tf32(accw[nt], l[0], l[2], l[1], l[3], bh0, bh1);
+        mma_tf32(accw[nt], h[0], h[2], h[1], h[3], bl0, bl1);
+        mma_tf32(accw[nt], h[0], h[2], h[1], h[3], bh0, bh1);
+      }
+    }
+    if (threadIdx.x < 64) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) bsum += sz[r * TILE_LD + threadIdx.x];
+    }
   }
   float* p = part + (size_t)blockIdx.x * TLSAN_PART;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(p + TLSAN_OFF_WD + (4 * r4 + i) * 64 + 4 * c4) =
-        make_float4(acc[i * 4], acc[i * 4 + 1], acc[i * 4 + 2], acc[i * 4 + 3]);
+  for (int nt = 0; nt < 8; ++nt) {
+    st2(p + TLSAN_OFF_WD + (warp * 16 + g) * 64 + nt * 8 + 2 * t, accw[nt][0], accw[nt][1]);
+    st2(p + TLSAN_OFF_WD + (warp * 16 + g + 8) * 64 + nt * 8 + 2 * t, accw[nt][2], accw[nt][3]);
+  }
   if (threadIdx.x < 64) p[TLSAN_OFF_BD + threadIdx.x] = bsum;
 }
 
 // ------------------------------------------------------------------ launchers
 FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b);
 
-static int mma_grid(int B) {
+static int mma_grid(int B, int ctas_per_sm) {
   const int need = (B + MMA_WARPS - 1) / MMA_WARPS;
-  const int cap = tlsan_num_sms() * 2;
+  const int cap = tlsan_num_sms() * ctas_per_sm;
   return need < cap ? need : cap;
 }
 
@@ -632,12 +747,12 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
   a.logits = logits; a.ut = ut;
   static bool attr_set = false;
   if (!attr_set) {
-    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_a_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SmemMma)));
     attr_set = true;
   }
-  k_fwd_a_mma<false><<<mma_grid(d.B), MMA_THREADS, sizeof(SmemMma), st>>>(a, ncand);
-  TLSAN_CHECK_LAUNCH("k_fwd_a_mma<score>");
+  k_fwd_mma<0><<<mma_grid(d.B, 2), MMA_THREADS, sizeof(SmemMma), st>>>(a, ncand);
+  TLSAN_CHECK_LAUNCH("k_fwd_mma<score>");
   return TLSAN_OK;
 }
 
@@ -648,27 +763,29 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
   a.rows_u = reinterpret_cast<float*>(ws + w.rows_u);
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_a_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemMma)));
-    attr_set = true;
-  }
-  const int g = mma_grid(d.B);
+  const int sms = tlsan_num_sms();
+  const int ntile16 = (d.B + 15) / 16;
+  // forward: long FWA -> dense GEMM -> short FWA + loss + backward of logit / short FWA
+  k_fwd_mma<1><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, 1);
+  TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
+  int gg = (ntile16 + 3) / 4;
+  if (gg > sms * 4) gg = sms * 4;
+  k_dense_fwd_mma<<<gg, 128, 0, st>>>(p.dense, a.scratch, d.B);
+  TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
+  const int g = mma_grid(d.B, 2);
   *grid_a = g; *grid_b = g;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
-  k_fwd_a_mma<true><<<g, MMA_THREADS, sizeof(SmemMma), st>>>(a, 1);
-  TLSAN_CHECK_LAUNCH("k_fwd_a_mma<train>");
+  k_fwd_mma<2><<<g, MMA_THREADS, sizeof(float) * MMA_WARPS * 160, st>>>(a, 1);
+  TLSAN_CHECK_LAUNCH("k_fwd_mma<short>");
   tlsan_profile_mark(TLSAN_PHASE_FUSED_A, st);
+  // backward: dense GEMMs (d o_long, dWd, dbd) -> long FWA
+  int gc = ntile16 < sms * 2 ? ntile16 : sms * 2;
+  *grid_c = gc;
+  k_dense_bwd_mma<<<gc, 128, 0, st>>>(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c));
+  TLSAN_CHECK_LAUNCH("k_dense_bwd_mma");
   a.part = reinterpret_cast<float*>(ws + w.part_b);
   k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
-  int gc = (d.B + 255) / 256;
-  const int cap = tlsan_num_sms();
-  if (gc > cap) gc = cap;
-  *grid_c = gc;
-  k_dense_grad<<<gc, 256, 0, st>>>(a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c));
-  TLSAN_CHECK_LAUNCH("k_dense_grad");
   tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
   return TLSAN_OK;
 }
