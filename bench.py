@@ -64,16 +64,20 @@ def synth_batches(rng, n_batches, B, L):
 
 
 def algorithmic_bytes(batch, L):
-    """SURVEY.md 8d byte model, evaluated on the actual lengths of `batch`.  Returns per-batch
-    totals: (scoring1, train_per_sample_total, fused_a, bwd_long)."""
+    """SURVEY.md 8d byte model, evaluated on the actual lengths of `batch` (totals per batch).
+    Per sample: R = 2(l+s)+4 embedding rows of 128 B.  The per-kernel figures split the train-step
+    formula by which kernel touches what; scratch traffic is never credited."""
     sl = np.asarray(batch[6], np.int64); s = np.asarray(batch[7], np.int64)
-    B = len(sl); S = batch[4].shape[1]
+    S = batch[4].shape[1]
     R = 2 * (sl + s) + 4
     scoring1 = 4 * (2 * L + S + 6) + 4 * (sl + s + 1) + 128 * R + (4 * L + 4) + 4
     train = scoring1 + 2 * (128 * R + 4 * sl + 4) + 4
-    fused_a = scoring1 + 128 * (2 * s + 4) + 4            # reads of the forward + short/cand/user grad rows
+    long_fwd = 4 * (2 * L + 2) + 4 * sl + 128 * 2 * sl + 4 * L                 # ids, hist_t, icl, rows, usert row
+    short = 4 * (S + 6) + 4 * (s + 1) + 128 * (2 * s + 4) + 4 + 128 * (2 * s + 4) + 8   # reads + gradient rows written
     bwd_long = 4 * 2 * L + 4 * sl + 128 * 2 * sl + 4 * L + 128 * 2 * sl + 4 * sl
-    return int(scoring1.sum()), int(train.sum()), int(fused_a.sum()), int(bwd_long.sum()), B
+    reduce_ = 128 * R + 4 * sl + 4                                              # every gradient row read once
+    return {"scoring1": int(scoring1.sum()), "train": int(train.sum()), "long_fwd": int(long_fwd.sum()),
+            "short": int(short.sum()), "bwd_long": int(bwd_long.sum()), "reduce": int(reduce_.sum())}
 
 
 def table_bytes(L):
@@ -115,12 +119,19 @@ class ClockSampler:
             self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, bus, str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.lines = []
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.lines.append(ln)
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
         except Exception as e:                      # pragma: no cover
             self.err = repr(e)
 
     def mark_begin(self):
+        t_end = time.time() + 5.0                  # the side process needs ~1 s to import + nvmlInit
+        while self.proc is not None and not self.lines and time.time() < t_end:
+            time.sleep(0.01)
         self.t0 = time.time()
 
     def mark_end(self):
@@ -249,6 +260,7 @@ def main():
     B, L = args.batch, args.Ls
     cfg = O.default_config(NU, NI, NC, Ls=L)
     icl = np.random.default_rng(1234).integers(0, NC, NI).astype(np.int32)     # same on every rank
+    clocks = ClockSampler(local_rank) if rank == 0 else None       # side process; started early
     model = Model(cfg, icl, seed=1234, process_group=pg)
     rng = np.random.default_rng(1234 + 1000 * rank)
     host_batches = synth_batches(rng, args.resident, B, L)
@@ -266,7 +278,6 @@ def main():
     for w in range(args.warmup):
         model.train_staged(dev_batches[w % len(dev_batches)], 1.0)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.tlsan_launch_count()
     _lib.check(lib.tlsan_profile_begin(args.steps))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -338,15 +349,14 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     ph = phase[:nrec.value].mean(axis=0)
+    phases_ms = {n: float(v) for n, v in zip(_lib.PHASES, ph)}
     per_batch = [algorithmic_bytes(b, L) for b in host_batches]
     used = [per_batch[k % len(per_batch)] for k in range(args.steps)]
-    a_bytes = float(np.mean([u[2] for u in used])); b_bytes = float(np.mean([u[3] for u in used]))
-    train_bytes = float(np.mean([u[1] for u in used])) + 2 * table_bytes(L) + 2 * 4 * 4449
-    ia, ib = _lib.PHASES.index("fused_a"), _lib.PHASES.index("bwd_long")
-    if ph[ia] >= ph[ib]:
-        kname, kbytes, kms = "k_fused<true>", a_bytes, float(ph[ia])
-    else:
-        kname, kbytes, kms = "k_bwd_long", b_bytes, float(ph[ib])
+    mean_bytes = {k: float(np.mean([u[k] for u in used])) for k in used[0]}
+    train_bytes = mean_bytes["train"] + 2 * table_bytes(L) + 2 * 4 * 4449
+    # dominant kernel = the longest of the per-sample gather kernels (each phase below is ONE kernel)
+    pname = max(("long_fwd", "short", "bwd_long", "reduce"), key=lambda n: phases_ms[n])
+    kname, kbytes, kms = _lib.PHASE_KERNEL[pname], mean_bytes[pname], phases_ms[pname]
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname)
@@ -355,8 +365,10 @@ def main():
     achieved = kbytes / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms": kms, "algorithmic_bytes_per_launch": kbytes,
-                "phases_ms": {n: float(v) for n, v in zip(_lib.PHASES, ph)},
+                "kernel_ms": kms, "algorithmic_bytes_per_launch": kbytes, "phases_ms": phases_ms,
+                "per_kernel": {_lib.PHASE_KERNEL[n]: {"ms": phases_ms[n], "algorithmic_GBps": mean_bytes[n] / (phases_ms[n] * 1e-3) / 1e9,
+                                                      "frac": mean_bytes[n] / (phases_ms[n] * 1e-3) / 1e9 / peak}
+                               for n in ("long_fwd", "short", "bwd_long", "reduce")},
                 "step": {"algorithmic_bytes": train_bytes,
                          "achieved": train_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "frac": train_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}}

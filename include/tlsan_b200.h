@@ -159,12 +159,15 @@ int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
  *   CUDA events on its stream at phase boundaries; tlsan_profile_end waits for them and fills
  *   ms[step][TLSAN_PHASE_COUNT] (elapsed per phase), returning the number of steps recorded. */
 enum {
-  TLSAN_PHASE_SORT = 0,    /* keys + radix sort + segment bounds */
-  TLSAN_PHASE_FUSED_A = 1, /* k_fused<train>: forward, loss, backward of logit/short/dense */
-  TLSAN_PHASE_BWD_LONG = 2,/* k_bwd_long */
-  TLSAN_PHASE_REDUCE = 3,  /* k_finalize1 + k_row_reduce */
-  TLSAN_PHASE_APPLY = 4,   /* table sumsq, finalize2, row / cate updates */
-  TLSAN_PHASE_COUNT = 5
+  TLSAN_PHASE_SORT = 0,      /* radix sort of the occurrence keys + segment bounds */
+  TLSAN_PHASE_LONG_FWD = 1,  /* long-term FWA forward */
+  TLSAN_PHASE_DENSE_FWD = 2, /* z = o_long Wd + bd (batched GEMM) */
+  TLSAN_PHASE_SHORT = 3,     /* short-term FWA forward + logit + loss + its backward */
+  TLSAN_PHASE_DENSE_BWD = 4, /* d o_long, dWd, dbd (batched GEMM) */
+  TLSAN_PHASE_BWD_LONG = 5,  /* long-term FWA backward */
+  TLSAN_PHASE_REDUCE = 6,    /* k_finalize1 + k_row_reduce */
+  TLSAN_PHASE_APPLY = 7,     /* table sumsq, finalize2, row / cate updates */
+  TLSAN_PHASE_COUNT = 8
 };
 long long tlsan_launch_count(void);
 int tlsan_profile_begin(int32_t max_steps);

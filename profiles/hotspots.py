@@ -14,7 +14,8 @@ def main(path, kernel, n=40):
         if cur is None: continue
         if cur["hdr"] is None: cur["hdr"] = r; continue
         if len(r) == len(cur["hdr"]): cur["data"].append(r)
-    b = blocks[0]; hdr, data = b["hdr"], b["data"]
+    import os
+    b = blocks[int(os.environ.get("INST", "0"))]; hdr, data = b["hdr"], b["data"]
     col = lambda name: hdr.index(name)
     iS, iSrc, iEx = col("# Samples"), col("Source"), col("Instructions Executed")
     names = ["stall_long_sb", "stall_wait", "stall_short_sb", "stall_math", "stall_barrier", "stall_not_selected", "stall_mio", "stall_lg"]

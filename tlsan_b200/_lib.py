@@ -51,7 +51,10 @@ _SIGS = {
     "tlsan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
 }
 EXPORTS = tuple(_SIGS)
-PHASES = ("sort", "fused_a", "bwd_long", "reduce", "apply")
+PHASES = ("sort", "long_fwd", "dense_fwd", "short", "dense_bwd", "bwd_long", "reduce", "apply")
+# kernel that dominates each phase (names as ncu prints them, default `hybrid` formulation)
+PHASE_KERNEL = {"long_fwd": "k_fwd_mma<1>", "short": "k_async<2>", "bwd_long": "k_bwd_long_mma",
+                "dense_fwd": "k_dense_fwd_mma", "dense_bwd": "k_dense_bwd_mma", "reduce": "k_row_reduce"}
 
 
 def lib():

@@ -30,16 +30,21 @@ void tlsan_profile_mark(int phase_done, cudaStream_t st) {
   cudaEventRecord(g_ev[(size_t)g_ev_step * (TLSAN_PHASE_COUNT + 1) + (phase_done + 1)], st);
 }
 
-// Both fused variants are sm_100a CUDA in this library; TLSAN_FUSED_IMPL=ffma selects the
-// CUDA-core formulation (kept for the mma-vs-FFMA comparison the design calls for).
-static bool use_mma() {
+// All fused variants are sm_100a CUDA in this library.  TLSAN_FUSED_IMPL selects an older
+// formulation for A/B measurements (the design asks for mma-vs-FFMA evidence):
+//   ffma  = CUDA-core maps, 4 samples per warp      (tlsan_fwd_bwd.cu)
+//   mma   = 3xTF32 mma tiles, synchronous gathers   (tlsan_fused_mma.cu)
+//   async = mma tiles + cp.async sample pipeline     (tlsan_fused_async.cu)
+//   (unset) hybrid = per kernel the faster of mma / async, see tlsan_launch_fwd_bwd_async   [default]
+static int fused_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TLSAN_FUSED_IMPL");
-    v = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    v = (e && strcmp(e, "ffma") == 0) ? 0 : (e && strcmp(e, "mma") == 0) ? 1 : (e && strcmp(e, "async") == 0) ? 2 : 3;
   }
-  return v == 1;
+  return v;
 }
+static bool use_mma() { return fused_impl() >= 1; }
 
 #define REQUIRE(cond, code, ...)      \
   do {                                \
@@ -152,7 +157,9 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SORT, st);
   int grid_a = 0, grid_b = 0, grid_c = 0;
-  if (use_mma()) rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, st);
+  if (fused_impl() >= 2)
+    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, st);
+  else if (fused_impl() == 1) rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
   if (rc) return rc;
   if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;

@@ -52,7 +52,7 @@ struct TlsanWs {
   int NR;     // unified row space NI + NC + NU
   int64_t nocc;
   int nchunks;
-  size_t keys_a, keys_b, vals_a, vals_b, hist, nvalid, seg_off;
+  size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
   size_t rows_i, rows_u, gscal, scratch;
   size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
@@ -77,6 +77,7 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.keys_b = take(w.nocc * 4);
   w.vals_a = take(w.nocc * 4);
   w.vals_b = take(w.nocc * 4);
+  w.inv = take(w.nocc * 4);
   w.hist = take((size_t)256 * (w.nchunks + 1) * 4 + 1024);   // per-CTA digit counts + 256 digit totals
   w.nvalid = take(64);
   w.seg_off = take((size_t)(w.NR + 2) * 4);
@@ -116,6 +117,9 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
                            float* logits, float* ut, cudaStream_t st);
 int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                              const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st);
+int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
+                               const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
+                               cudaStream_t st);
 int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,
                            cudaStream_t st);
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,

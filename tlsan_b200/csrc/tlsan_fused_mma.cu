@@ -20,211 +20,7 @@
 //   k_fwd_mma<2>     short FWA forward + logit + loss + backward of logit / short FWA (model.py:135-137,164-172,350-364)
 //   k_dense_bwd_mma  d o_long = dz Wd^T ; dWd = O^T dZ ; dbd
 //   k_bwd_long_mma   backward of the long FWA and of the time-aware position term (model.py:98-109)
-#include "tlsan_fused.cuh"
-
-#define MMA_THREADS 256
-#define MMA_WARPS 8
-
-struct BMat { uint32_t h0, h1, l0, l1; };          // B fragment (b0, b1) split into tf32 hi / lo
-struct FwaW { BMat W1, W2; float b1[2], b2[2]; };  // forward weights of one FWA
-struct FwaWT { BMat W2T, W1T; };                   // transposed fragments for the backward
-
-// fp32 -> tf32 by truncation (one LOP3).  `cvt.rna.tf32.f32` is emulated with ~5 integer
-// instructions on sm_100a (ncu: it was a quarter of the backward tile); with the hi/lo split
-// truncation loses nothing: lo = x - hi is exact and its own truncation error is ~2^-21 relative.
-__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
-__device__ __forceinline__ BMat make_b(float b0, float b1) {
-  BMat m;
-  m.h0 = to_tf32(b0); m.h1 = to_tf32(b1);
-  m.l0 = to_tf32(b0 - __uint_as_float(m.h0)); m.l1 = to_tf32(b1 - __uint_as_float(m.h1));
-  return m;
-}
-// out[n] = sum_f in[f] W[f][n]  : B[slot t] = W[2t][g], B[slot t+4] = W[2t+1][g]
-__device__ __forceinline__ BMat load_b(const float* __restrict__ W, int g, int t) {
-  return make_b(W[(2 * t) * 8 + g], W[(2 * t + 1) * 8 + g]);
-}
-// out[n] = sum_f in[f] W[n][f]  (transposed product of the backward)
-__device__ __forceinline__ BMat load_bt(const float* __restrict__ W, int g, int t) {
-  return make_b(W[g * 8 + 2 * t], W[g * 8 + 2 * t + 1]);
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// d += x B with 3xTF32.  x in D order {A:2t, A:2t+1, B:2t, B:2t+1}; as an A fragment:
-// a0 = (row g, slot t) = x[0], a1 = (row g+8, slot t) = x[2], a2 = (row g, slot t+4) = x[1], a3 = x[3].
-__device__ __forceinline__ void mma3(float (&d)[4], const float (&x)[4], const BMat& B) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    h[i] = to_tf32(x[i]);
-    l[i] = to_tf32(x[i] - __uint_as_float(h[i]));
-  }
-  // three independent accumulators: the HMMAs pipeline instead of chaining on one D fragment
-  float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-  mma_tf32(c1, l[0], l[2], l[1], l[3], B.h0, B.h1);
-  mma_tf32(c2, h[0], h[2], h[1], h[3], B.l0, B.l1);
-  mma_tf32(d, h[0], h[2], h[1], h[3], B.h0, B.h1);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] += c1[i] + c2[i];
-}
-// exp(x) for x <= 0 (softmax weights): one FMUL + MUFU.EX2, no denormal fix-up code
-__device__ __forceinline__ float exp_neg(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
-  return r;
-}
-
-__device__ __forceinline__ FwaW load_fwa(const float* __restrict__ dense, int base, int g, int t) {
-  FwaW w;
-  w.W1 = load_b(dense + base, g, t);
-  w.W2 = load_b(dense + base + 72, g, t);
-  w.b1[0] = dense[base + 64 + 2 * t]; w.b1[1] = dense[base + 64 + 2 * t + 1];
-  w.b2[0] = dense[base + 136 + 2 * t]; w.b2[1] = dense[base + 136 + 2 * t + 1];
-  return w;
-}
-__device__ __forceinline__ FwaWT load_fwa_t(const float* __restrict__ dense, int base, int g, int t) {
-  FwaWT w;
-  w.W2T = load_bt(dense + base + 72, g, t);
-  w.W1T = load_bt(dense + base, g, t);
-  return w;
-}
-
-// m1 = relu(x W1 + b1), m2 = m1 W2 + b2   (model.py:380-383)
-__device__ __forceinline__ void tile_maps(const float (&x)[4], const FwaW& w, float (&m1)[4], float (&m2)[4]) {
-  m1[0] = w.b1[0]; m1[1] = w.b1[1]; m1[2] = w.b1[0]; m1[3] = w.b1[1];
-  mma3(m1, x, w.W1);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m1[i] = fmaxf(m1[i], 0.f);
-  m2[0] = w.b2[0]; m2[1] = w.b2[1]; m2[2] = w.b2[0]; m2[3] = w.b2[1];
-  mma3(m2, m1, w.W2);
-}
-
-// online softmax over the sequence axis for the lane's two features
-struct Soft2 {
-  float mx[2], den[2], acc[2];
-  __device__ __forceinline__ void init() {
-    mx[0] = mx[1] = -INFINITY; den[0] = den[1] = 0.f; acc[0] = acc[1] = 0.f;
-  }
-  __device__ __forceinline__ void push(float m0, float m1, float x0, float x1) {
-    const float mm[2] = {m0, m1}, xx[2] = {x0, x1};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float d = mm[j] - mx[j];
-      const float e = exp_neg(-fabsf(d));
-      const bool up = d > 0.f;
-      const float c = up ? e : 1.f, n = up ? 1.f : e;
-      den[j] = fmaf(den[j], c, n);
-      acc[j] = fmaf(acc[j], c, n * xx[j]);
-      mx[j] = up ? mm[j] : mx[j];
-    }
-  }
-};
-
-// per-lane gradient accumulators of one FWA weight set: rows k = 0..7, the lane's 2 columns
-struct FwaGrad {
-  float W1[8][2], W2[8][2], b1[2], b2[2];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { W1[k][0] = W1[k][1] = 0.f; W2[k][0] = W2[k][1] = 0.f; }
-    b1[0] = b1[1] = b2[0] = b2[1] = 0.f;
-  }
-};
-
-// backward of one tile.  okB = second token of the tile is real.
-__device__ __forceinline__ void tile_bwd(const float (&x)[4], bool okB, const float (&o)[2], const float (&dout)[2],
-                                         const float (&mx)[2], const float (&inv)[2], const FwaW& w,
-                                         const FwaWT& wt, int lane, float (&dx)[4], FwaGrad& G) {
-  float m1[4], m2[4];
-  tile_maps(x, w, m1, m2);
-  float ado[4], dm2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int j = i & 1;
-    const float aw = exp_neg(m2[i] - mx[j]) * inv[j];
-    const float on = (i < 2 || okB) ? 1.f : 0.f;
-    ado[i] = on * aw * dout[j];
-    dm2[i] = ado[i] * (x[i] - o[j]);
-  }
-  G.b2[0] += dm2[0] + dm2[2]; G.b2[1] += dm2[1] + dm2[3];
-  float dpre[4] = {0.f, 0.f, 0.f, 0.f};
-  mma3(dpre, dm2, wt.W2T);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dpre[i] = m1[i] > 0.f ? dpre[i] : 0.f;
-  G.b1[0] += dpre[0] + dpre[2]; G.b1[1] += dpre[1] + dpre[3];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dx[i] = ado[i];
-  mma3(dx, dpre, wt.W1T);
-  // dW2[k][j] += m1[k] dm2[j], dW1[k][j] += x[k] dpre[j]: the 8 k-values of a row live in the
-  // 4 lanes of the row's quad (2 each) -> quad shuffles, then FFMA on the lane's 2 columns.
-  const int qbase = lane & ~3;
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-#pragma unroll
-    for (int tq = 0; tq < 4; ++tq) {
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int k = 2 * tq + jj;
-        const float mk = __shfl_sync(0xffffffffu, m1[2 * r + jj], qbase + tq);
-        const float xk = __shfl_sync(0xffffffffu, x[2 * r + jj], qbase + tq);
-        G.W2[k][0] = fmaf(mk, dm2[2 * r], G.W2[k][0]);
-        G.W2[k][1] = fmaf(mk, dm2[2 * r + 1], G.W2[k][1]);
-        G.W1[k][0] = fmaf(xk, dpre[2 * r], G.W1[k][0]);
-        G.W1[k][1] = fmaf(xk, dpre[2 * r + 1], G.W1[k][1]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-
-// lane geometry: features f0, f0+1 of the 64-float token; which table half; offset inside the row
-struct LaneGeo {
-  int lane, g, t, f0, half, col;
-  __device__ __forceinline__ void init() {
-    lane = threadIdx.x & 31; g = lane >> 2; t = lane & 3;
-    f0 = 8 * g + 2 * t; half = g >> 2; col = (g & 3) * 8 + 2 * t;
-  }
-};
-
-// ---- token meta of up to 32 tokens, one per lane (coalesced), broadcast by shuffle
-struct LongMeta { int id, crow; float tau, pt, ht; };
-__device__ __forceinline__ LongMeta load_long_meta(const FArgs& a, int b, int u, int tt, int ell, float gamma) {
-  LongMeta m;
-  const bool ok = tt < ell;
-  m.id = ok ? __ldg(a.hist_i + (size_t)b * a.L + tt) : 0;
-  m.ht = ok ? __ldg(a.hist_t + (size_t)b * a.L + tt) : 0.f;
-  const float pu = ok ? __ldg(a.usert + (size_t)u * a.L + tt) : 0.f;
-  m.pt = pu * m.ht;                  // P[u,t] * hist_t    (model.py:99)
-  m.tau = gamma * m.pt;              // gamma * (...)      (model.py:109)
-  m.crow = a.NI + __ldg(a.icl + m.id);
-  return m;
-}
-__device__ __forceinline__ const float* row_ptr(const FArgs& a, const LaneGeo& L, int id, int crow) {
-  return a.emb + (size_t)(L.half ? crow : id) * 32 + L.col;
-}
-
-// one tile's inputs: two gathered token slices (float2 each) and their tau
-struct Pair { float2 eA, eB; float tA, tB; bool okB; };
-__device__ __forceinline__ Pair fetch_pair(const FArgs& a, const LaneGeo& L, const LongMeta& me, int j, int cnt) {
-  Pair p;
-  p.okB = j + 1 < cnt;
-  const int idA = __shfl_sync(0xffffffffu, me.id, j), crA = __shfl_sync(0xffffffffu, me.crow, j);
-  const int idB = __shfl_sync(0xffffffffu, me.id, (j + 1) & 31), crB = __shfl_sync(0xffffffffu, me.crow, (j + 1) & 31);
-  p.tA = __shfl_sync(0xffffffffu, me.tau, j);
-  p.tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
-  p.eA = ldg2(row_ptr(a, L, idA, crA));
-  p.eB = p.okB ? ldg2(row_ptr(a, L, idB, crB)) : make_float2(0.f, 0.f);
-  return p;
-}
+#include "tlsan_mma_common.cuh"
 
 // long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state
 __device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, int b, int u, int ell, float gamma,
@@ -388,14 +184,15 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
     const float sig = logit >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
     const float gl = (sig - yb) * a.invB;                               // d loss / d logit
     if (L.lane == 0) { loss_acc += bce; sq_acc = fmaf(gl, gl, sq_acc); a.gscal[b] = gl; }
-    float* rcand = a.rows_i + ((size_t)b * a.SI + a.L + a.S) * 64 + L.f0;
+    float* rcand = grad_row(a, b, a.L + a.S) + L.f0;
+    float* rvirt = grad_row(a, b, a.L + a.S + 1) + L.f0;
     const float dq[2] = {gl * ut[0], gl * ut[1]};
     const float du[2] = {gl * q.x, gl * q.y};
     sq_acc = fmaf(dq[0], dq[0], sq_acc); sq_acc = fmaf(dq[1], dq[1], sq_acc);
     sq_acc = fmaf(du[0], du[0], sq_acc); sq_acc = fmaf(du[1], du[1], sq_acc);
     st2(rcand, dq[0], dq[1]);                                           // -> item_emb[i] | cate_emb[icl[i]]
-    if (L.half) st2(rcand + 64, du[0], du[1]);                          // -> cate_emb[u_cate]
-    else { st2(rcand + 64, 0.f, 0.f); st2(a.rows_u + (size_t)b * a.PU + L.f0, du[0], du[1]); }  // -> user_emb[u]
+    if (L.half) st2(rvirt, du[0], du[1]);                               // -> cate_emb[u_cate]
+    else { st2(rvirt, 0.f, 0.f); st2(a.rows_u + (size_t)b * a.PU + L.f0, du[0], du[1]); }  // -> user_emb[u]
     // short-term FWA backward, d v = du
     float dz[2] = {0.f, 0.f};
     for (int r0 = 0; r0 < ntok; r0 += 32) {
@@ -424,11 +221,11 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
         if (nA == 0) { dz[0] = dx[0]; dz[1] = dx[1]; }
         else {
           sq_acc = fmaf(dx[0], dx[0], sq_acc); sq_acc = fmaf(dx[1], dx[1], sq_acc);
-          st2(a.rows_i + ((size_t)b * a.SI + a.L + (nA - 1)) * 64 + L.f0, dx[0], dx[1]);
+          st2(grad_row(a, b, a.L + (nA - 1)) + L.f0, dx[0], dx[1]);
         }
         if (okB) {
           sq_acc = fmaf(dx[2], dx[2], sq_acc); sq_acc = fmaf(dx[3], dx[3], sq_acc);
-          st2(a.rows_i + ((size_t)b * a.SI + a.L + (nB - 1)) * 64 + L.f0, dx[2], dx[3]);
+          st2(grad_row(a, b, a.L + (nB - 1)) + L.f0, dx[2], dx[3]);
         }
       }
     }
@@ -442,7 +239,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        float r1 = G.W1[k][jj], r2 = G.W2[k][jj];
+        float r1 = G.w1(k, jj), r2 = G.w2(k, jj);
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
           r1 += __shfl_xor_sync(0xffffffffu, r1, o);
@@ -502,8 +299,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
       const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
       const int cnt = min(32, ell - r0);
       float dtau_l = 0.f;                          // lane j collects d tau of token r0 + j
+      const int inv_l = L.lane < cnt ? __ldg(a.inv + ((size_t)b << a.spsh) + r0 + L.lane) : 0;   // sorted ranks
       for (int j = 0; j < cnt; j += 2) {
         const Pair cur = fetch_pair(a, L, me, j, cnt);
+        const int posA = __shfl_sync(0xffffffffu, inv_l, j), posB = __shfl_sync(0xffffffffu, inv_l, (j + 1) & 31);
         const bool okB = cur.okB;
         const float2 eA = cur.eA, eB = cur.eB;
         const float tA = cur.tA, tB = cur.tB;
@@ -513,13 +312,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
         // gradient of the gathered slices (tau * dX) and of tau (<dX, e>)
         const float rA0 = dx[0] * tA, rA1 = dx[1] * tA;
         sq_acc = fmaf(rA0, rA0, sq_acc); sq_acc = fmaf(rA1, rA1, sq_acc);
-        st2(a.rows_i + ((size_t)b * a.SI + r0 + j) * 64 + L.f0, rA0, rA1);
+        st2(a.rows_i + (size_t)posA * 64 + L.f0, rA0, rA1);
         const float dtA = warp_sum_f(fmaf(dx[0], eA.x, dx[1] * eA.y));
         if (L.lane == j) dtau_l = dtA;
         if (okB) {
           const float rB0 = dx[2] * tB, rB1 = dx[3] * tB;
           sq_acc = fmaf(rB0, rB0, sq_acc); sq_acc = fmaf(rB1, rB1, sq_acc);
-          st2(a.rows_i + ((size_t)b * a.SI + r0 + j + 1) * 64 + L.f0, rB0, rB1);
+          st2(a.rows_i + (size_t)posB * 64 + L.f0, rB0, rB1);
           const float dtB = warp_sum_f(fmaf(dx[2], eB.x, dx[3] * eB.y));
           if (L.lane == j + 1) dtau_l = dtB;
         }
@@ -538,7 +337,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
   for (int k = 0; k < 8; ++k) {
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
-      float r1 = G.W1[k][jj], r2 = G.W2[k][jj];
+      float r1 = G.w1(k, jj), r2 = G.w2(k, jj);
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) {
         r1 += __shfl_xor_sync(0xffffffffu, r1, o);
@@ -599,11 +398,11 @@ __device__ __forceinline__ void gemm_step(float (&acc)[4], const uint32_t (&h)[4
   mma_tf32(acc, h[0], h[2], h[1], h[3], bh0, bh1);
 }
 
-__global__ void __launch_bounds__(128) k_dense_fwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
+__global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
                                                        int B) {
   __shared__ SmemGemm sb;
   __shared__ float sbd[64];
-  for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
     const float w = dense[TLSAN_OFF_WD + e];
     const float h = __uint_as_float(to_tf32(w));
     sb.hi[(e >> 6) * GEMM_LD + (e & 63)] = h;
@@ -611,33 +410,39 @@ __global__ void __launch_bounds__(128) k_dense_fwd_mma(const float* __restrict__
   }
   if (threadIdx.x < 64) sbd[threadIdx.x] = dense[TLSAN_OFF_BD + threadIdx.x];
   __syncthreads();
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int half = warp & 1;                       // output columns 32*half .. +31
   const int ntiles = (B + 15) / 16;
-  for (int tile = blockIdx.x * 4 + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * 4) {
+  for (int tile = blockIdx.x * 4 + (warp >> 1); tile < ntiles; tile += gridDim.x * 4) {
     const int rA = tile * 16 + g, rB = rA + 8;
     const bool vA = rA < B, vB = rB < B;
     const float* pA = scratch + (size_t)rA * (TLSAN_SCR * 64) + 64 + 2 * t;
     const float* pB = scratch + (size_t)rB * (TLSAN_SCR * 64) + 64 + 2 * t;
-    float acc[8][4];
+    float2 xa[8], xb[8];                            // the whole A fragment up front: 16 loads in flight
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      acc[nt][0] = acc[nt][2] = sbd[nt * 8 + 2 * t];
-      acc[nt][1] = acc[nt][3] = sbd[nt * 8 + 2 * t + 1];
+    for (int ks = 0; ks < 8; ++ks) {
+      xa[ks] = vA ? *reinterpret_cast<const float2*>(pA + ks * 8) : make_float2(0.f, 0.f);
+      xb[ks] = vB ? *reinterpret_cast<const float2*>(pB + ks * 8) : make_float2(0.f, 0.f);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      acc[nt][0] = acc[nt][2] = sbd[half * 32 + nt * 8 + 2 * t];
+      acc[nt][1] = acc[nt][3] = sbd[half * 32 + nt * 8 + 2 * t + 1];
     }
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      const float2 a = vA ? *reinterpret_cast<const float2*>(pA + ks * 8) : make_float2(0.f, 0.f);
-      const float2 c = vB ? *reinterpret_cast<const float2*>(pB + ks * 8) : make_float2(0.f, 0.f);
-      const float x[4] = {a.x, a.y, c.x, c.y};
+      const float x[4] = {xa[ks].x, xa[ks].y, xb[ks].x, xb[ks].y};
       uint32_t h[4], l[4];
       split4(x, h, l);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, nt * 8, g, t);
+      for (int nt = 0; nt < 4; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, half * 32 + nt * 8, g, t);
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (vA) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + 320 + nt * 8 + 2 * t, acc[nt][0], acc[nt][1]);
-      if (vB) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + 320 + nt * 8 + 2 * t, acc[nt][2], acc[nt][3]);
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = 320 + half * 32 + nt * 8 + 2 * t;
+      if (vA) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + col, acc[nt][0], acc[nt][1]);
+      if (vB) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + col, acc[nt][2], acc[nt][3]);
     }
   }
 }
@@ -735,10 +540,43 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
 // ------------------------------------------------------------------ launchers
 FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b);
 
+
 static int mma_grid(int B, int ctas_per_sm) {
   const int need = (B + MMA_WARPS - 1) / MMA_WARPS;
   const int cap = tlsan_num_sms() * ctas_per_sm;
   return need < cap ? need : cap;
+}
+
+int tlsan_launch_dense_fwd(const float* dense, float* scratch, int B, cudaStream_t st) {
+  const int ntile16 = (B + 15) / 16;
+  int gg = (ntile16 + 3) / 4;
+  if (gg > tlsan_num_sms() * 4) gg = tlsan_num_sms() * 4;
+  k_dense_fwd_mma<<<gg, 256, 0, st>>>(dense, scratch, B);
+  TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_dense_bwd(const float* dense, float* scratch, int B, float* part, int* grid_c, cudaStream_t st) {
+  const int ntile16 = (B + 15) / 16;
+  const int gc = ntile16 < tlsan_num_sms() * 4 ? ntile16 : tlsan_num_sms() * 4;
+  *grid_c = gc;
+  k_dense_bwd_mma<<<gc, 128, 0, st>>>(dense, scratch, B, part);
+  TLSAN_CHECK_LAUNCH("k_dense_bwd_mma");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_long_fwd_mma(const FArgs& a, cudaStream_t st) {
+  k_fwd_mma<1><<<mma_grid(a.B, 3), MMA_THREADS, 0, st>>>(a, 1);
+  TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
+  return TLSAN_OK;
+}
+
+int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st) {
+  const int g = mma_grid(a.B, 2);
+  *grid_b = g;
+  k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
+  TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
+  return TLSAN_OK;
 }
 
 int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
@@ -760,29 +598,27 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
                              const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
+  a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
   a.rows_u = reinterpret_cast<float*>(ws + w.rows_u);
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
-  const int sms = tlsan_num_sms();
-  const int ntile16 = (d.B + 15) / 16;
   // forward: long FWA -> dense GEMM -> short FWA + loss + backward of logit / short FWA
   k_fwd_mma<1><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
-  int gg = (ntile16 + 3) / 4;
-  if (gg > sms * 4) gg = sms * 4;
-  k_dense_fwd_mma<<<gg, 128, 0, st>>>(p.dense, a.scratch, d.B);
-  TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
+  tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
+  int rc;
+  if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
+  tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   const int g = mma_grid(d.B, 2);
   *grid_a = g; *grid_b = g;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   k_fwd_mma<2><<<g, MMA_THREADS, sizeof(float) * MMA_WARPS * 160, st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short>");
-  tlsan_profile_mark(TLSAN_PHASE_FUSED_A, st);
+  tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
   // backward: dense GEMMs (d o_long, dWd, dbd) -> long FWA
-  int gc = ntile16 < sms * 2 ? ntile16 : sms * 2;
-  *grid_c = gc;
-  k_dense_bwd_mma<<<gc, 128, 0, st>>>(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c));
-  TLSAN_CHECK_LAUNCH("k_dense_bwd_mma");
+  if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))
+    return rc;
+  tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
   k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long_mma");

@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_fused(const FArgs a, const
         sq_acc = fmaf(g, g, sq_acc);  // item_b gather slice
         a.gscal[b] = g;
       }
-      float* rcand = a.rows_i + ((size_t)b * a.SI + a.L + a.S) * 64 + 8 * h;
-      float* rvirt = rcand + 64;
+      float* rcand = grad_row(a, b, a.L + a.S) + 8 * h;
+      float* rvirt = grad_row(a, b, a.L + a.S + 1) + 8 * h;
       float dq[8], du[8], zero[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_fused(const FArgs a, const
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) sq_acc = fmaf(dx[q], dx[q], sq_acc);
-          st8(a.rows_i + ((size_t)b * a.SI + a.L + (t - 1)) * 64 + 8 * h, dx);
+          st8(grad_row(a, b, a.L + (t - 1)) + 8 * h, dx);
         }
       }
     }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(TLSAN_THREADS, 1) k_bwd_long(const FArgs a) {
         row[q] = dx[q] * tau;            // gradient of the gathered embedding slice
         sq_acc = fmaf(row[q], row[q], sq_acc);
       }
-      st8(a.rows_i + ((size_t)b * a.SI + t) * 64 + 8 * h, row);
+      st8(grad_row(a, b, t) + 8 * h, row);
       const float dtau = oct_sum(dtp);
       if (h == 0) {
         ggamma = fmaf(dtau, pt, ggamma);
@@ -585,7 +585,7 @@ FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tls
   a.u = b.u; a.i = b.i; a.i2 = b.i2; a.c = b.c; a.sl = b.sl; a.sl_new = b.sl_new;
   a.hist_i = b.hist_i; a.hist_i_new = b.hist_i_new; a.y = b.y; a.hist_t = b.hist_t;
   a.logits = nullptr; a.ut = nullptr; a.rows_i = nullptr; a.rows_u = nullptr; a.gscal = nullptr;
-  a.scratch = nullptr; a.part = nullptr;
+  a.scratch = nullptr; a.part = nullptr; a.inv = nullptr; a.spsh = 0;
   return a;
 }
 
@@ -618,6 +618,7 @@ int tlsan_launch_fwd_bwd(const tlsan_dims_t& d, const tlsan_params_t& p, const t
   if (rc) return rc;
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
+  a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
   a.rows_u = reinterpret_cast<float*>(ws + w.rows_u);
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
@@ -632,7 +633,9 @@ int tlsan_launch_fwd_bwd(const tlsan_dims_t& d, const tlsan_params_t& p, const t
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   k_fused<true><<<g, TLSAN_THREADS, sizeof(SmemDense), st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fused<train>");
-  tlsan_profile_mark(TLSAN_PHASE_FUSED_A, st);
+  // this variant fuses long forward, dense and short into one kernel: report it all as SHORT
+  tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st); tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
+  tlsan_profile_mark(TLSAN_PHASE_SHORT, st); tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
   k_bwd_long<<<g, TLSAN_THREADS, 0, st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long");

@@ -89,7 +89,8 @@ template <bool FROM_BATCH>
 __global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
     const int* __restrict__ keys_in, const KeySrc src, const int* __restrict__ vals_in, long long ncap,
     const int* __restrict__ nvalid, int* __restrict__ nvalid_out, int shift, int nblk, const int* __restrict__ hist,
-    const int* __restrict__ tot, int* __restrict__ keys_out, int* __restrict__ vals_out) {
+    const int* __restrict__ tot, int* __restrict__ keys_out, int* __restrict__ vals_out,
+    int* __restrict__ inv_out /* last pass only: occurrence id -> sorted rank */) {
   __shared__ int off[SORT_WARPS][256];
   __shared__ int dbase[256];
   __shared__ int wtot[8];
@@ -143,8 +144,10 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
     __syncwarp();
     if (act) {
       const long long idx = wbase + it * 32 + lane;
+      const int val = vals_in ? vals_in[idx] : (int)idx;
       keys_out[pos] = key;
-      vals_out[pos] = vals_in ? vals_in[idx] : (int)idx;
+      vals_out[pos] = val;
+      if (inv_out) inv_out[val] = pos;
     }
   }
 }
@@ -188,12 +191,13 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
     TLSAN_CHECK_LAUNCH("k_radix_hist");
     k_radix_scan_rows<<<32, 256, 0, st>>>(hist, nblk, tot);
     TLSAN_CHECK_LAUNCH("k_radix_scan_rows");
+    int* inv = pass == passes - 1 ? reinterpret_cast<int*>(ws + w.inv) : nullptr;
     if (pass == 0)
       k_radix_scatter<true><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, vin, nocc, nv, nvalid, 8 * pass, nblk, hist,
-                                                             tot, kout, vout);
+                                                             tot, kout, vout, inv);
     else
       k_radix_scatter<false><<<nblk, 32 * SORT_WARPS, 0, st>>>(kin, src, vin, nocc, nv, nvalid, 8 * pass, nblk, hist,
-                                                              tot, kout, vout);
+                                                              tot, kout, vout, inv);
     TLSAN_CHECK_LAUNCH("k_radix_scatter");
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }

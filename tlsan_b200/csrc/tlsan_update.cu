@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
   const int lane = threadIdx.x & 31;
   const int NR = NI + NC + NU;
   const int W = gridDim.x * 8;
-  const int SI = L + S + 2, smask = (1 << spsh) - 1;
+  const int smask = (1 << spsh) - 1;
   const int hw = lane >> 4, q = lane & 15;
   int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   int2 seg_c = r < NR ? make_int2(seg_off[r], seg_off[r + 1]) : make_int2(0, 0);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int 
             const int occ = __shfl_sync(0xffffffffu, mine, kk & 31);
             const int b = occ >> spsh, j = occ & smask;
             const bool on = kk < cnt;
-            v[k] = on ? __ldg(reinterpret_cast<const float4*>(rows_i + ((size_t)b * SI + j) * 64) + q)
+            v[k] = on ? __ldg(reinterpret_cast<const float4*>(rows_i + (size_t)(base + kk) * 64) + q)   // sorted rows
                       : make_float4(0.f, 0.f, 0.f, 0.f);
             gb[k] = (on && j == L + S && q == 0) ? __ldg(gscal + b) : 0.f;
           }
@@ -160,28 +160,39 @@ __global__ void __launch_bounds__(256) k_table_sumsq(const float* __restrict__ e
 }
 
 // global norm (TF style: un-aggregated slices, see oracle header), clip scale, loss, dense SGD
-__global__ void __launch_bounds__(256) k_finalize2(const float* __restrict__ dgrad, const float* __restrict__ tsq,
-                                                   int ntsq, float invB, float lr, float reg, float clip,
-                                                   float* __restrict__ dense, float* __restrict__ stats) {
-  __shared__ float sh[8];
-  __shared__ float s_scale;
-  float s = 0.f;
-  for (int e = threadIdx.x; e < TLSAN_DENSE_COUNT; e += 256) s = fmaf(dgrad[e], dgrad[e], s);
-  const float dense_sq = block_sum_256(s, sh);
-  __shared__ double shd[256];
-  {
-    double t = 0.0;
-    for (int c = threadIdx.x; c < ntsq; c += 256)
-      t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
-    shd[threadIdx.x] = t;
-  }
+__device__ __forceinline__ double block_sum_1024d(double v, double* sh) {   // fixed order: lanes, then warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) r += sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dgrad, const float* __restrict__ tsq,
+                                                    int ntsq, float invB, float lr, float reg, float clip,
+                                                    float* __restrict__ dense, float* __restrict__ stats) {
+  __shared__ double sh[32];
+  float g[5];
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int e = threadIdx.x + 1024 * q;
+    g[q] = e < TLSAN_DENSE_COUNT ? dgrad[e] : 0.f;
+    s += (double)g[q] * (double)g[q];
+  }
+  const double dense_sq = block_sum_1024d(s, sh);
+  double t = 0.0;
+  for (int c = threadIdx.x; c < ntsq; c += 1024)
+    t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
+  t = block_sum_1024d(t, sh);
+  const double sq = (double)dgrad[TLSAN_PART_SUMSQ] + dense_sq + (double)reg * (double)reg * t;
+  const float norm = (float)sqrt(sq);
+  const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int c = 0; c < 256; ++c) t += shd[c];
-    const double sq = (double)dgrad[TLSAN_PART_SUMSQ] + (double)dense_sq + (double)reg * (double)reg * t;
-    const float norm = (float)sqrt(sq);
-    const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
     const float l2 = (float)(0.5 * t);
     const float bce = dgrad[TLSAN_PART_LOSS] * invB;
     stats[TLSAN_STAT_LOSS] = bce + reg * l2;
@@ -189,11 +200,12 @@ __global__ void __launch_bounds__(256) k_finalize2(const float* __restrict__ dgr
     stats[TLSAN_STAT_NORM] = norm;
     stats[TLSAN_STAT_SCALE] = scale;
     stats[TLSAN_STAT_L2] = l2;
-    s_scale = scale;
   }
-  __syncthreads();
-  const float scale = s_scale;
-  for (int e = threadIdx.x; e < TLSAN_DENSE_COUNT; e += 256) dense[e] -= lr * (dgrad[e] * scale);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int e = threadIdx.x + 1024 * q;
+    if (e < TLSAN_DENSE_COUNT) dense[e] -= lr * (g[q] * scale);
+  }
 }
 
 // element-wise update of item_emb, user_emb, usert_emb and item_b from the reduced buffers
@@ -203,25 +215,35 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
                                                     const float* __restrict__ g_u, float lr, float reg,
                                                     const float* __restrict__ stats) {
   const float scale = stats[TLSAN_STAT_SCALE];
-  const long long n1 = (long long)NI * 32, n2 = n1 + (long long)NU * 32, n3 = n2 + (long long)NU * L, n4 = n3 + NI;
+  // float4 units: item rows (8 per row), user rows (8 per row); then scalars: usert, item_b
+  const long long v1 = (long long)NI * 8, v2 = v1 + (long long)NU * 8;
+  const long long n3 = (long long)NU * L, n4 = n3 + NI;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
-    if (e < n1) {
-      const long long r = e >> 5; const int q = (int)(e & 31);
-      const float w = emb[e];
-      emb[e] = w - lr * ((g_i[r * 64 + q] + reg * w) * scale);
-    } else if (e < n2) {
-      const long long x = e - n1; const long long u = x >> 5; const int q = (int)(x & 31);
-      float* wp = emb + (size_t)(NI + NC) * 32 + x;
-      const float w = *wp;
-      *wp = w - lr * ((g_u[u * PU + q] + reg * w) * scale);
-    } else if (e < n3) {
-      const long long x = e - n2; const long long u = x / L; const int t = (int)(x - u * L);
-      const float w = usert[x];
-      usert[x] = w - lr * ((g_u[u * PU + 32 + t] + reg * w) * scale);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < v2 + n4; e += stride) {
+    if (e < v2) {
+      float4* wp; float4 g;
+      if (e < v1) {
+        wp = reinterpret_cast<float4*>(emb) + e;
+        g = *reinterpret_cast<const float4*>(g_i + (e >> 3) * 64 + (e & 7) * 4);
+      } else {
+        const long long x = e - v1;
+        wp = reinterpret_cast<float4*>(emb + (size_t)(NI + NC) * 32) + x;
+        g = *reinterpret_cast<const float4*>(g_u + (x >> 3) * PU + (x & 7) * 4);
+      }
+      float4 w = *wp;
+      w.x -= lr * ((g.x + reg * w.x) * scale); w.y -= lr * ((g.y + reg * w.y) * scale);
+      w.z -= lr * ((g.z + reg * w.z) * scale); w.w -= lr * ((g.w + reg * w.w) * scale);
+      *wp = w;
     } else {
-      const long long x = e - n3;
-      item_b[x] = item_b[x] - lr * (g_b[x] * scale);
+      const long long x = e - v2;
+      if (x < n3) {
+        const long long u = x / L; const int t = (int)(x - u * L);
+        const float w = usert[x];
+        usert[x] = w - lr * ((g_u[u * PU + 32 + t] + reg * w) * scale);
+      } else {
+        const long long y = x - n3;
+        item_b[y] = item_b[y] - lr * (g_b[y] * scale);
+      }
     }
   }
 }
@@ -330,9 +352,9 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
                                       (long long)d.NU * 32, (long long)d.NU * d.L, tsq);
   TLSAN_CHECK_LAUNCH("k_table_sumsq");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 256, 0, st>>>(dgrad, tsq, ntsq, invB, lr, reg, clip, p.dense, stats);
+  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, invB, lr, reg, clip, p.dense, stats);
   TLSAN_CHECK_LAUNCH("k_finalize2");
-  const long long n4 = (long long)d.NI * 32 + (long long)d.NU * 32 + (long long)d.NU * d.L + d.NI;
+  const long long n4 = (long long)d.NI * 8 + (long long)d.NU * 8 + (long long)d.NU * d.L + d.NI;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tlsan_num_sms() * 8;
   if (blocks > cap) blocks = cap;
