@@ -153,6 +153,16 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
 int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut,
                      const int32_t* label, int32_t* rank, void* stream);
 
+/* Host helper (no GPU work): pack the 9-tuple of TLSAN/input.py:54,107 (int64 ids, fp32 hist_t) into
+ * ONE int32 staging buffer -- the int64->int32 feed cast of model.py:210-222 -- multi-threaded, with
+ * the id range checks TF's CPU gather performs.  Segment order (each rounded up to 4 words):
+ * u, i, second (i2 as int32, or y as fp32 bits), c, sl, sl_new, hist_i[B*L], hist_i_new[B*S],
+ * hist_t[B*L].  Returns TLSAN_E_DIMS and names the field in tlsan_last_error() if an id is out of range. */
+int tlsan_pack_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int64_t* i, const int64_t* i2,
+                          const float* y, const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t,
+                          const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* out,
+                          int64_t out_words, int32_t validate, int32_t nthreads);
+
 /* Instrumentation for bench.py (not on the product path).
  * tlsan_launch_count: kernels launched by this library since load (all threads).
  * tlsan_profile_begin(max_steps): from now on every tlsan_step_grads / tlsan_apply_flat records

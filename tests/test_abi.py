@@ -83,3 +83,38 @@ def test_product_package_never_imports_the_oracle():
                     elif isinstance(node, ast.ImportFrom):
                         names = [node.module or ""]
                     assert not any(n.split(".")[0] == "oracle" for n in names), f
+
+
+def test_host_packer_matches_numpy_and_validates(lib):
+    import numpy as np
+    from tests.util import synth_batch
+    from tlsan_b200.model import _pack_offsets, pack_batch
+    rng = np.random.default_rng(2)
+    for B, L, S, is_test in ((5, 3, 1, False), (1000, 10, 7, True), (30000, 10, 18, False)):
+        NI, NU, NC = 500, 300, 11
+        batch = synth_batch(rng, B, L, S, NI, NU, NC, is_test=is_test)
+        dims = _lib.Dims(B=B, L=L, S=S, NI=NI, NU=NU, NC=NC, B_global=B, reserved=0)
+        offs, total = _pack_offsets(B, L, S)
+        out = np.full(total, -7, np.int32)
+        pack_batch(lib, batch, dims, is_test, out)
+        ref = {"u": batch[0], "i": batch[1], "c": batch[8], "sl": batch[6], "sl_new": batch[7],
+               "hist_i": batch[3].ravel(), "hist_i_new": batch[4].ravel()}
+        for k, v in ref.items():
+            assert np.array_equal(out[offs[k]:offs[k] + len(v)], np.asarray(v, np.int32)), k
+        assert np.array_equal(out.view(np.float32)[offs["hist_t"]:offs["hist_t"] + B * L], batch[5].ravel())
+        sec = out[offs["second"]:offs["second"] + B]
+        if is_test:
+            assert np.array_equal(sec, batch[2].astype(np.int32))
+        else:
+            assert np.array_equal(sec.view(np.float32), batch[2].astype(np.float32))
+        good = out.copy()
+        for field, val in ((1, NI), (3, -1), (8, NC), (6, 0), (0, NU), (4, 2 ** 40)):
+            bad = [np.array(f) for f in batch]
+            bad[field].reshape(-1)[B // 2] = val
+            with pytest.raises(IndexError):
+                pack_batch(lib, tuple(bad), dims, is_test, out)
+        # lists (what the reference batcher returns) are accepted too
+        as_lists = tuple(f.tolist() if j in (0, 1, 2, 6, 7, 8) else f for j, f in enumerate(batch))
+        out2 = np.full(total, -7, np.int32)
+        pack_batch(lib, as_lists, dims, is_test, out2)
+        assert np.array_equal(out2, good)

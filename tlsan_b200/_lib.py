@@ -46,6 +46,7 @@ _SIGS = {
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
+    "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
     "tlsan_launch_count": (C.c_longlong, []),
     "tlsan_profile_begin": (C.c_int, [C.c_int32]),
     "tlsan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

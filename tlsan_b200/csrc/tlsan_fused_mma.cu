@@ -550,7 +550,7 @@ static int mma_grid(int B, int ctas_per_sm) {
 int tlsan_launch_dense_fwd(const float* dense, float* scratch, int B, cudaStream_t st) {
   const int ntile16 = (B + 15) / 16;
   int gg = (ntile16 + 3) / 4;
-  if (gg > tlsan_num_sms() * 4) gg = tlsan_num_sms() * 4;
+  if (gg > tlsan_num_sms() * 2) gg = tlsan_num_sms() * 2;   // one resident wave: the B image is built once per CTA
   k_dense_fwd_mma<<<gg, 256, 0, st>>>(dense, scratch, B);
   TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
   return TLSAN_OK;

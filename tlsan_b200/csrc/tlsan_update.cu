@@ -14,7 +14,7 @@
 // 16-31, 8 steps (16 rows) in flight; the two half-sums are combined at the end -- a fixed
 // order, independent of timing.  The segment bounds of the row after next and the occurrence
 // list of the next row are fetched while the current row is being summed.
-__global__ void __launch_bounds__(256) k_row_reduce(int NI, int NC, int NU, int L, int S, int spsh, int PU,
+__global__ void __launch_bounds__(256, 4) k_row_reduce(int NI, int NC, int NU, int L, int S, int spsh, int PU,
                                                     const int* __restrict__ seg_off, const int* __restrict__ vals,
                                                     const float* __restrict__ rows_i,
                                                     const float* __restrict__ rows_u,
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) k_label_rank(int NI, const float* __restr
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st) {
   int rgrid = (w.NR + 7) / 8;
-  if (rgrid > tlsan_num_sms() * 3) rgrid = tlsan_num_sms() * 3;
+  if (rgrid > tlsan_num_sms() * 4) rgrid = tlsan_num_sms() * 4;
   k_row_reduce<<<rgrid, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU,
                                                reinterpret_cast<const int*>(ws + w.seg_off), sorted_vals,
                                                reinterpret_cast<const float*>(ws + w.rows_i),

@@ -97,6 +97,30 @@ def _pack_offsets(B, L, S):
     return offs, o
 
 
+def pack_batch(lib, batch, dims, is_test, out, validate=True):
+    """Host-side feed (reference model.py:210-222): the 9-tuple -> packed int32 words in ``out``.
+    Out-of-range ids raise IndexError, like tf.gather on CPU (InvalidArgumentError)."""
+    def i64(x):
+        return np.ascontiguousarray(x, dtype=np.int64)
+    B, S = dims.B, dims.S
+    u, i, c, sl, sl_new = i64(batch[0]), i64(batch[1]), i64(batch[8]), i64(batch[6]), i64(batch[7])
+    hist_i = i64(batch[3])
+    hist_i_new = i64(batch[4])
+    if hist_i_new.shape[1] == 0:
+        hist_i_new = np.zeros((B, 1), np.int64)
+    hist_t = np.ascontiguousarray(batch[5], dtype=np.float32)
+    i2 = i64(batch[2]) if is_test else None
+    y = None if is_test else np.ascontiguousarray(batch[2], dtype=np.float32)
+    if hist_i.shape != (B, dims.L) or hist_t.shape != (B, dims.L) or hist_i_new.shape != (B, S):
+        raise ValueError("batch arrays have inconsistent shapes")
+    p = lambda a: None if a is None else a.ctypes.data
+    rc = lib.tlsan_pack_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
+                                   p(sl), p(sl_new), p(c), out.ctypes.data, out.size, 1 if validate else 0, 0)
+    if rc == -1:
+        raise IndexError(lib.tlsan_last_error().decode())
+    check(rc)
+
+
 class Model(object):
     def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True):
         self.config = config
@@ -199,54 +223,22 @@ class Model(object):
         return self._ws
 
     def stage_batch(self, batch, is_test=False):
-        """Pack the input.py 9-tuple into pinned memory and copy it to the device (one H2D)."""
-        hist_i = np.asarray(batch[3])
-        hist_i_new = np.asarray(batch[4])
-        B, L = hist_i.shape
-        S = max(int(hist_i_new.shape[1]), 1)
-        if L != self.L:
-            raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (L, self.L))
-        offs, total = _pack_offsets(B, L, S)
+        """Pack the input.py 9-tuple into pinned memory (tlsan_pack_batch_host: multi-threaded
+        int64->int32 cast + id range checks) and copy it to the device (one H2D)."""
+        B = len(batch[0])
+        S = max(int(np.shape(batch[4])[1]), 1)
+        if np.shape(batch[3])[1] != self.L:
+            raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (np.shape(batch[3])[1], self.L))
+        offs, total = _pack_offsets(B, self.L, S)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(),)
-        host = self._stage_cache[key][0]
-        h = host.numpy()
-        hf = h.view(np.float32)
-
-        def put(name, arr, n):
-            h[offs[name]:offs[name] + n] = np.asarray(arr).reshape(-1)
-
-        put("u", batch[0], B); put("i", batch[1], B); put("c", batch[8], B)
-        put("sl", batch[6], B); put("sl_new", batch[7], B)
-        if is_test:
-            put("second", batch[2], B)
-        else:
-            hf[offs["second"]:offs["second"] + B] = np.asarray(batch[2], dtype=np.float32)
-        put("hist_i", hist_i, B * L)
-        if hist_i_new.shape[1] == 0:
-            h[offs["hist_i_new"]:offs["hist_i_new"] + B] = 0
-        else:
-            put("hist_i_new", hist_i_new, B * S)
-        hf[offs["hist_t"]:offs["hist_t"] + B * L] = np.asarray(batch[5], dtype=np.float32).reshape(-1)
-        if self.validate:
-            self._validate(h, offs, B, L, S, is_test)
+            self._stage_cache[key] = torch.empty(total, dtype=torch.int32).pin_memory()
+        host = self._stage_cache[key]
+        pack_batch(self._lib, batch, self._dims(B, S), is_test, host.numpy(), self.validate)
         dev = torch.empty(total, dtype=torch.int32, device=self.device)
         dev.copy_(host, non_blocking=True)
         self.last_h2d_bytes = total * 4
-        return DeviceBatch(dev, B, L, S, offs, is_test)
-
-    def _validate(self, h, offs, B, L, S, is_test):
-        """Out-of-range ids raise, like tf.gather on CPU (InvalidArgumentError)."""
-        def rng(name, n, hi, lo=0):
-            a = h[offs[name]:offs[name] + n]
-            if a.min() < lo or a.max() >= hi:
-                raise IndexError("batch field %s out of range [%d, %d)" % (name, lo, hi))
-        rng("u", B, self.NU); rng("i", B, self.NI); rng("c", B, self.NC)
-        rng("hist_i", B * L, self.NI); rng("hist_i_new", B * S, self.NI)
-        rng("sl", B, L + 1, 1); rng("sl_new", B, S + 1, 0)
-        if is_test:
-            rng("second", B, self.NI)
+        return DeviceBatch(dev, B, self.L, S, offs, is_test)
 
     # ------------------------------------------------------------------ training
     def train_staged(self, db, lr, global_batch=None):
