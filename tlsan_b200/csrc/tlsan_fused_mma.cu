@@ -22,21 +22,25 @@
 //   k_bwd_long_mma   backward of the long FWA and of the time-aware position term (model.py:98-109)
 #include "tlsan_mma_common.cuh"
 
-// long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state
+// long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state.
+// buf = per-warp [32][64] row staging area.
 __device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, int b, int u, int ell, float gamma,
-                                             const FwaW& w, Soft2& st) {
+                                             const FwaW& w, float (*buf)[64], Soft2& st) {
   st.init();
   for (int r0 = 0; r0 < ell; r0 += 32) {
     const LongMeta me = load_long_meta(a, b, u, r0 + L.lane, ell, gamma);
     const int cnt = min(32, ell - r0);
+    stage_round_rows(a, me, cnt, L.lane, buf);
     for (int j = 0; j < cnt; j += 2) {
-      const Pair cur = fetch_pair(a, L, me, j, cnt);
-      const float x[4] = {cur.eA.x * cur.tA, cur.eA.y * cur.tA, cur.okB ? cur.eB.x * cur.tB : 0.f,
-                          cur.okB ? cur.eB.y * cur.tB : 0.f};
+      const bool okB = j + 1 < cnt;
+      const float tA = __shfl_sync(0xffffffffu, me.tau, j), tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
+      const float2 eA = *reinterpret_cast<const float2*>(&buf[j][L.f0]);
+      const float2 eB = okB ? *reinterpret_cast<const float2*>(&buf[j + 1][L.f0]) : make_float2(0.f, 0.f);
+      const float x[4] = {eA.x * tA, eA.y * tA, okB ? eB.x * tB : 0.f, okB ? eB.y * tB : 0.f};
       float m1[4], m2[4];
       tile_maps(x, w, m1, m2);
       st.push(m2[0], m2[1], x[0], x[1]);
-      if (cur.okB) st.push(m2[2], m2[3], x[2], x[3]);
+      if (okB) st.push(m2[2], m2[3], x[2], x[3]);
     }
   }
 }
@@ -44,6 +48,7 @@ __device__ __forceinline__ void long_forward(const FArgs& a, const LaneGeo& L, i
 // shared-memory image of the dense layer (natural layouts: lane reads float2 at [k][f0])
 struct SmemMma {
   float red[MMA_WARPS][160];     // MODE 2: end-of-kernel reduction staging
+  float rows[MMA_WARPS][32][64]; // MODE 0/1: per-warp staging of one round of long-term token rows
   float vec[MMA_WARPS][64];      // MODE 0: per-warp staging of o_long
   float bd[64];
   float wd[64 * 64];             // MODE 0: Wd[k][f]
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
       // ---- long-term FWA forward
       const int ell = __ldg(a.sl + b);
       Soft2 st;
-      long_forward(a, L, b, u, ell, gamma, wl, st);
+      long_forward(a, L, b, u, ell, gamma, wl, sm.rows[warp], st);
       const float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
       if (MODE == 1) {
         float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
@@ -276,7 +281,9 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
 
 // ------------------------------------------------------------------ backward of the long-term FWA
 __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) {
-  __shared__ float red[MMA_WARPS][160];
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  float (*rowsb)[32][64] = reinterpret_cast<float (*)[32][64]>(smem_b);          // [warp][32][64]
+  float (*red)[160] = reinterpret_cast<float (*)[160]>(smem_b);                   // reused after the loop
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
   const float gamma = a.dense[TLSAN_OFF_GAMMA];
@@ -300,8 +307,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
       const int cnt = min(32, ell - r0);
       float dtau_l = 0.f;                          // lane j collects d tau of token r0 + j
       const int inv_l = L.lane < cnt ? __ldg(a.inv + ((size_t)b << a.spsh) + r0 + L.lane) : 0;   // sorted ranks
+      stage_round_rows(a, me, cnt, L.lane, rowsb[warp]);
       for (int j = 0; j < cnt; j += 2) {
-        const Pair cur = fetch_pair(a, L, me, j, cnt);
+        Pair cur;
+        cur.okB = j + 1 < cnt;
+        cur.tA = __shfl_sync(0xffffffffu, me.tau, j); cur.tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
+        cur.eA = *reinterpret_cast<const float2*>(&rowsb[warp][j][L.f0]);
+        cur.eB = cur.okB ? *reinterpret_cast<const float2*>(&rowsb[warp][j + 1][L.f0]) : make_float2(0.f, 0.f);
         const int posA = __shfl_sync(0xffffffffu, inv_l, j), posB = __shfl_sync(0xffffffffu, inv_l, (j + 1) & 31);
         const bool okB = cur.okB;
         const float2 eA = cur.eA, eB = cur.eB;
@@ -332,6 +344,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
     }
     for (int tt = ell + L.lane; tt < a.PU - 32; tt += 32) ru[tt] = 0.f;
   }
+
+  __syncthreads();   // all warps are done with their staged rows: the area is reused for the reduction
 
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -565,16 +579,33 @@ int tlsan_launch_dense_bwd(const float* dense, float* scratch, int B, float* par
   return TLSAN_OK;
 }
 
+static const int kSmemLongFwd = (int)(sizeof(float) * MMA_WARPS * (160 + 32 * 64));   // red + rows of SmemMma
+static const int kSmemBwdLong = (int)(sizeof(float) * MMA_WARPS * 32 * 64);
+
+static int set_long_attrs() {
+  static bool done = false;
+  if (!done) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLongFwd));
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_long_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwdLong));
+    done = true;
+  }
+  return TLSAN_OK;
+}
+
 int tlsan_launch_long_fwd_mma(const FArgs& a, cudaStream_t st) {
-  k_fwd_mma<1><<<mma_grid(a.B, 3), MMA_THREADS, 0, st>>>(a, 1);
+  int rc = set_long_attrs();
+  if (rc) return rc;
+  k_fwd_mma<1><<<mma_grid(a.B, 3), MMA_THREADS, kSmemLongFwd, st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
   return TLSAN_OK;
 }
 
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st) {
+  int rc = set_long_attrs();
+  if (rc) return rc;
   const int g = mma_grid(a.B, 2);
   *grid_b = g;
-  k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
+  k_bwd_long_mma<<<g, MMA_THREADS, kSmemBwdLong, st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
   return TLSAN_OK;
 }
@@ -603,10 +634,9 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   // forward: long FWA -> dense GEMM -> short FWA + loss + backward of logit / short FWA
-  k_fwd_mma<1><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, 1);
-  TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
-  tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   int rc;
+  if ((rc = tlsan_launch_long_fwd_mma(a, st))) return rc;
+  tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   const int g = mma_grid(d.B, 2);
@@ -620,8 +650,7 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
-  k_bwd_long_mma<<<g, MMA_THREADS, 0, st>>>(a);
-  TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
+  if ((rc = tlsan_launch_bwd_long_mma(a, grid_b, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
   return TLSAN_OK;
 }
