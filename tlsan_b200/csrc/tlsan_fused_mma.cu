@@ -416,11 +416,16 @@ __global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restric
                                                        int B) {
   __shared__ SmemGemm sb;
   __shared__ float sbd[64];
-  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-    const float w = dense[TLSAN_OFF_WD + e];
-    const float h = __uint_as_float(to_tf32(w));
-    sb.hi[(e >> 6) * GEMM_LD + (e & 63)] = h;
-    sb.lo[(e >> 6) * GEMM_LD + (e & 63)] = __uint_as_float(to_tf32(w - h));
+  for (int e4 = threadIdx.x; e4 < 64 * 16; e4 += 256) {       // float4 loads: 4 independent per thread
+    const float4 w4 = *reinterpret_cast<const float4*>(dense + TLSAN_OFF_WD + 4 * e4);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = 4 * e4 + q;
+      const float h = __uint_as_float(to_tf32(wv[q]));
+      sb.hi[(e >> 6) * GEMM_LD + (e & 63)] = h;
+      sb.lo[(e >> 6) * GEMM_LD + (e & 63)] = __uint_as_float(to_tf32(wv[q] - h));
+    }
   }
   if (threadIdx.x < 64) sbd[threadIdx.x] = dense[TLSAN_OFF_BD + threadIdx.x];
   __syncthreads();
@@ -467,11 +472,16 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
   __shared__ SmemGemm sb;                          // Wd^T: image[j][f] = Wd[f][j]
   __shared__ __align__(16) float so[16 * TILE_LD];
   __shared__ __align__(16) float sz[16 * TILE_LD];
-  for (int e = threadIdx.x; e < 64 * 64; e += 128) {
-    const float w = dense[TLSAN_OFF_WD + e];        // Wd[f = e>>6][j = e&63]
-    const float h = __uint_as_float(to_tf32(w));
-    sb.hi[(e & 63) * GEMM_LD + (e >> 6)] = h;
-    sb.lo[(e & 63) * GEMM_LD + (e >> 6)] = __uint_as_float(to_tf32(w - h));
+  for (int e4 = threadIdx.x; e4 < 64 * 16; e4 += 128) {       // float4 loads: 8 independent per thread
+    const float4 w4 = *reinterpret_cast<const float4*>(dense + TLSAN_OFF_WD + 4 * e4);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = 4 * e4 + q;                      // Wd[f = e>>6][j = e&63]
+      const float h = __uint_as_float(to_tf32(wv[q]));
+      sb.hi[(e & 63) * GEMM_LD + (e >> 6)] = h;
+      sb.lo[(e & 63) * GEMM_LD + (e >> 6)] = __uint_as_float(to_tf32(wv[q] - h));
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int ntiles = (B + 15) / 16;
