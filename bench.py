@@ -203,7 +203,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = args.steps * B / dt
     sample = "each step = B=%d rows of the Electronics-shape workload (bounded sample of the 65536-row step)" % B
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -211,7 +211,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(args, B):
@@ -222,7 +222,28 @@ def workload_config(args, B):
                          "(gradient rows + tables + batch) exceeds the 126 MB L2"}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the ONE JSON
+    line of the contract is written to the saved real stdout by _emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -306,7 +327,7 @@ def main():
     # ---------------- end to end through Model.train with host batches
     if args.skip_extras:
         if rank == 0:
-            print(json.dumps({"ms_per_step": ms / args.steps, "phases_ms": dict(zip(_lib.PHASES, map(float, phase[:nrec.value].mean(axis=0))))}))
+            _emit({"ms_per_step": ms / args.steps, "phases_ms": dict(zip(_lib.PHASES, map(float, phase[:nrec.value].mean(axis=0))))})
         return
     for w in range(2):
         model.train(None, host_batches[w % len(host_batches)], 1.0)
@@ -321,6 +342,36 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
     h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
+
+    # ---------------- epoch loop over a device-resident dataset: GPU batch assembly + train step
+    from tlsan_b200.dataset import DeviceDataset
+    from tlsan_b200.input import CsrDataset
+    sl_all = np.concatenate([b[6] for b in host_batches]); ns_all = np.concatenate([b[7] for b in host_batches])
+    pre_off = np.zeros(len(sl_all) + 1, np.int64); np.cumsum(sl_all, out=pre_off[1:])
+    new_off = np.zeros(len(ns_all) + 1, np.int64); np.cumsum(ns_all, out=new_off[1:])
+    mask_l = np.arange(L)[None, :] < sl_all[:, None]
+    hi_all = np.concatenate([b[3] for b in host_batches]); ht_all = np.concatenate([b[5] for b in host_batches])
+    hn_all = np.concatenate([np.pad(b[4], ((0, 0), (0, S_MAX - b[4].shape[1]))) for b in host_batches])
+    mask_s = np.arange(S_MAX)[None, :] < ns_all[:, None]
+    csr = CsrDataset(np.concatenate([b[0] for b in host_batches]), pre_off, hi_all[mask_l], ht_all[mask_l], new_off,
+                     hn_all[mask_s], np.concatenate([b[1] for b in host_batches]),
+                     np.concatenate([b[2] for b in host_batches]), np.concatenate([b[8] for b in host_batches]), False)
+    dds = DeviceDataset(csr, is_test=False)
+    perm = torch.randperm(len(dds), device="cuda", dtype=torch.int32)
+    nb = len(dds) // B
+    for k in range(3):
+        model.train_staged(dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max"), 1.0)
+    barrier()
+    ds_steps = max(3, min(args.steps, 50))
+    e0.record()
+    for k in range(ds_steps):
+        model.train_staged(dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max"), 1.0)
+    e1.record()
+    barrier()
+    t_ds = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ds, op=dist.ReduceOp.MAX)
+    ms_ds = float(t_ds.item()) / ds_steps
 
     # ---------------- scoring (eval_auc-style, 2 candidates) device-resident
     test_b = list(host_batches[0]); test_b[2] = host_batches[1][1]
@@ -386,11 +437,14 @@ def main():
         "e2e": {"value": e2e_steps * B * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        "dataset_resident": {"metric": "train_samples_per_s", "value": B * world / (ms_ds * 1e-3), "unit": "samples/s",
+                             "what": "shuffled epoch loop over a CSR dataset resident in HBM: tlsan_collate (GPU batch "
+                                     "assembly in the input.py layout) + train step, no host batcher", "steps": ds_steps},
         "eval": {"metric": "eval_seqs_per_s", "value": B * world / (ms_score * 1e-3), "unit": "seqs/s",
                  "candidates": 2},
         "final_loss": loss,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

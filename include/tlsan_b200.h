@@ -163,6 +163,32 @@ int tlsan_pack_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int6
                           const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* out,
                           int64_t out_words, int32_t validate, int32_t nthreads);
 
+/* Device-resident dataset.  CSR image, in HBM, of the samples built by
+ * TLSAN/build_dataset.py:58-59,71: per sample r its user, its long-term history
+ * pre_items / pre_time [pre_off[r], pre_off[r+1]) (pre_time = float32(1/n), input.py:36,45), its session
+ * new_items [new_off[r], new_off[r+1]), the candidate, the label (train: second_f) or negative item
+ * (test: second_i) and u_cate. */
+typedef struct {
+  const int32_t* uid;
+  const int64_t* pre_off;
+  const int32_t* pre_items;
+  const float* pre_time;
+  const int64_t* new_off;
+  const int32_t* new_items;
+  const int32_t* cand;
+  const int32_t* second_i;
+  const float* second_f;
+  const int32_t* ucate;
+  int64_t n;
+} tlsan_dataset_t;
+
+/* Batch assembly on the GPU: rows idx[0..B) (device int32) in the layout of DataInput.__next__ /
+ * DataInputTest.__next__ (TLSAN/input.py:17-54,70-107) -- last Ls history entries left-aligned and zero
+ * padded, session zero padded to S columns -- written as the packed staging buffer of
+ * tlsan_pack_batch_host.  S must be >= the longest session among the rows (input.py uses the batch max). */
+int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int32_t L, int32_t S, int32_t is_test,
+                  int32_t* out, int64_t out_words, void* stream);
+
 /* Instrumentation for bench.py (not on the product path).
  * tlsan_launch_count: kernels launched by this library since load (all threads).
  * tlsan_profile_begin(max_steps): from now on every tlsan_step_grads / tlsan_apply_flat records

@@ -22,6 +22,11 @@ class Batch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("u", "i", "i2", "y", "hist_i", "hist_i_new", "hist_t", "sl", "sl_new", "c")]
 
 
+class Dataset(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("uid", "pre_off", "pre_items", "pre_time", "new_off", "new_items", "cand",
+                                          "second_i", "second_f", "ucate")] + [("n", C.c_int64)]
+
+
 class TlsanError(RuntimeError):
     pass
 
@@ -47,6 +52,8 @@ _SIGS = {
     "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
+    "tlsan_collate": (C.c_int, [C.POINTER(Dataset), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                C.c_int64, C.c_void_p]),
     "tlsan_launch_count": (C.c_longlong, []),
     "tlsan_profile_begin": (C.c_int, [C.c_int32]),
     "tlsan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
