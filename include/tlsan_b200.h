@@ -125,6 +125,13 @@ int tlsan_gather_concat(const tlsan_dims_t* dims, const tlsan_params_t* p, const
 int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
                 int32_t ncand, float* logits, float* ut, void* stream);
 
+/* Same logits as tlsan_score, faster for large batches: with a scratch workspace the 64x64 dense layer
+ * (model.py:347) leaves the per-sample kernel and runs as ONE batched tensor-core GEMM between the
+ * long-term and the short-term kernel. */
+int tlsan_score_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes);
+int tlsan_score_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, int32_t ncand,
+                   float* logits, float* ut, void* workspace, size_t workspace_bytes, void* stream);
+
 /* bytes of workspace tlsan_train_step / tlsan_step_grads need for `dims`. */
 int tlsan_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes);
 

@@ -242,3 +242,29 @@ def test_save_restore_roundtrip(dm, dm_model, tmp_path):
     assert m2.global_step.eval() == 1
     for k, v in m.state_dict().items():
         assert torch.equal(v, m2.state_dict()[k])
+
+
+def test_score_workspace_path_matches_fused_path_and_oracle():
+    """tlsan_score_ws (batched dense GEMM between the kernels, B >= 2048) vs tlsan_score vs oracle."""
+    rng = np.random.default_rng(17)
+    NU, NI, NC, L, S, B = 300, 2000, 13, 10, 5, 3001
+    cfg = _cfg(NU, NI, NC, L)
+    params = _params(cfg)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    model = model_from_params(params, icl, cfg)
+    batch = synth_batch(rng, B, L, S, NI, NU, NC, is_test=True)
+    db = model.stage_batch(batch, is_test=True)
+    lg_ws, ut_ws = model.score_staged(db, 2, want_ut=True)            # B >= 2048 -> workspace path
+    dims = model._dims(db.B, db.S)
+    lg = torch.empty(B, 2, device="cuda"); ut = torch.empty(B, 64, device="cuda")
+    from tlsan_b200 import _lib
+    _lib.check(model._lib.tlsan_score(C.byref(dims), C.byref(model._params), C.byref(db.c), 2, lg.data_ptr(),
+                                      ut.data_ptr(), model._stream()))
+    assert rel_err(lg_ws.cpu().numpy(), lg.cpu().numpy()) < 2e-6
+    assert rel_err(ut_ws.cpu().numpy(), ut.cpu().numpy()) < 2e-6
+    rows = rng.choice(B, 300, replace=False)
+    sub = tuple(np.asarray(f)[rows] for f in batch)
+    r1, _ = O.forward_logits(params, icl, sub, 1, config=cfg)
+    r2, _ = O.forward_logits(params, icl, sub, 2, config=cfg)
+    got = lg_ws.cpu().numpy()
+    assert rel_err(got[rows, 0], r1) < TOL and rel_err(got[rows, 1], r2) < TOL

@@ -41,6 +41,9 @@ _SIGS = {
                                       C.c_int64, C.c_void_p]),
     "tlsan_score": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p]),
+    "tlsan_score_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),
+    "tlsan_score_ws": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tlsan_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),
     "tlsan_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_float, C.c_float,
                                    C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),

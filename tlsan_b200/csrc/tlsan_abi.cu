@@ -119,6 +119,30 @@ int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_b
   return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
 }
 
+int tlsan_score_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(bytes != nullptr, TLSAN_E_NULL, "bytes is NULL");
+  *bytes = (size_t)dims->B * TLSAN_SCR * 64 * sizeof(float) + 256;
+  return TLSAN_OK;
+}
+
+int tlsan_score_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, int32_t ncand,
+                   float* logits, float* ut, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, false))) return rc;
+  REQUIRE(ncand == 1 || ncand == 2, TLSAN_E_DIMS, "ncand must be 1 or 2 (got %d)", ncand);
+  if ((rc = check_batch(b, false, ncand))) return rc;
+  REQUIRE(logits != nullptr && workspace != nullptr, TLSAN_E_NULL, "logits/workspace is NULL");
+  REQUIRE(ut == nullptr || aligned16(ut), TLSAN_E_ALIGN, "ut must be 16-B aligned");
+  REQUIRE(workspace_bytes >= (size_t)dims->B * TLSAN_SCR * 64 * sizeof(float) + 256, TLSAN_E_WORKSPACE,
+          "workspace too small");
+  float* scratch = reinterpret_cast<float*>(tlsan_align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  if (!use_mma()) return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
+  return tlsan_launch_score_ws(*dims, *p, *b, ncand, logits, ut, scratch, (cudaStream_t)stream);
+}
+
 int tlsan_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
   int rc;
   if ((rc = check_dims(dims))) return rc;

@@ -120,6 +120,8 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
                                cudaStream_t st);
+int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
+                          float* logits, float* ut, float* scratch, cudaStream_t st);
 int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,
                            cudaStream_t st);
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,

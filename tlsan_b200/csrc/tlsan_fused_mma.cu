@@ -75,9 +75,12 @@ __device__ __forceinline__ void dense2(const float* __restrict__ vec, const floa
 // MODE 2: training, short-term FWA forward (z read from scratch) + logit + loss + backward of
 //         logit / short FWA -> gradient rows, dz -> scratch.  The 64x64 dense layer between
 //         MODE 1 and MODE 2 (and its backward) runs as batched tensor-core GEMMs (k_dense_*).
+// MODE 3: scoring with a workspace: short-term FWA forward (z from scratch) + logits; used after
+//         MODE 1 + k_dense_fwd_mma by tlsan_score_ws (the dense layer leaves the per-sample kernel).
 template <int MODE>
-__global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(const FArgs a, const int ncand) {
+__global__ void __launch_bounds__(MMA_THREADS, (MODE == 1 || MODE == 3) ? 3 : 2) k_fwd_mma(const FArgs a, const int ncand) {
   constexpr bool TRAIN = MODE == 2;
+  constexpr bool LONG = MODE == 0 || MODE == 1;     // runs the long-term FWA itself
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemMma& sm = *reinterpret_cast<SmemMma*>(smem_raw);
   if (MODE == 0) {
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
   FwaWT wst;
   FwaGrad G;
   float loss_acc = 0.f, sq_acc = 0.f;
-  if (MODE != 2) wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+  if (LONG) wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
   if (MODE != 1) ws = load_fwa(a.dense, TLSAN_OFF_W1S, L.g, L.t);
   if (TRAIN) { wst = load_fwa_t(a.dense, TLSAN_OFF_W1S, L.g, L.t); G.init(); }
   float* vec = sm.vec[warp];
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MODE == 1 ? 3 : 2) k_fwd_mma(cons
   for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
     const int u = __ldg(a.u + b);
     float z[2] = {0.f, 0.f};
-    if (MODE != 2) {
+    if (LONG) {
       // ---- long-term FWA forward
       const int ell = __ldg(a.sl + b);
       Soft2 st;
@@ -632,6 +635,19 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
   }
   k_fwd_mma<0><<<mma_grid(d.B, 2), MMA_THREADS, sizeof(SmemMma), st>>>(a, ncand);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<score>");
+  return TLSAN_OK;
+}
+
+// scoring with a caller-provided scratch [B][TLSAN_SCR][64]: long FWA -> batched dense GEMM -> short FWA + logits
+int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
+                          float* logits, float* ut, float* scratch, cudaStream_t st) {
+  FArgs a = tlsan_make_fargs(d, p, b);
+  a.logits = logits; a.ut = ut; a.scratch = scratch;
+  int rc;
+  if ((rc = tlsan_launch_long_fwd_mma(a, st))) return rc;
+  if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
+  k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);
+  TLSAN_CHECK_LAUNCH("k_fwd_mma<short score>");
   return TLSAN_OK;
 }
 

@@ -191,6 +191,7 @@ class Model(object):
 
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
         self._ws = None
+        self._score_ws = None
         self._flat = None
         self._stage_cache = {}
         self.last_h2d_bytes = 0
@@ -280,8 +281,17 @@ class Model(object):
         dims = self._dims(db.B, db.S)
         logits = torch.empty(db.B, ncand, dtype=torch.float32, device=self.device)
         ut = torch.empty(db.B, 64, dtype=torch.float32, device=self.device) if want_ut else None
-        check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(db.c), ncand,
-                                    logits.data_ptr(), ut.data_ptr() if want_ut else None, self._stream()))
+        if db.B >= 2048:                                       # batched-dense path needs a scratch workspace
+            need = C.c_size_t()
+            check(self._lib.tlsan_score_workspace_bytes(C.byref(dims), C.byref(need)))
+            if self._score_ws is None or self._score_ws.numel() < need.value:
+                self._score_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+            check(self._lib.tlsan_score_ws(C.byref(dims), C.byref(self._params), C.byref(db.c), ncand,
+                                           logits.data_ptr(), ut.data_ptr() if want_ut else None,
+                                           self._score_ws.data_ptr(), self._score_ws.numel(), self._stream()))
+        else:
+            check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(db.c), ncand,
+                                        logits.data_ptr(), ut.data_ptr() if want_ut else None, self._stream()))
         return logits, ut
 
     def logits(self, batch, cand_index=1):
