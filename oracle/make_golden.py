@@ -5,7 +5,8 @@ committed because /root/reference does not exist on the GPU box.
 
   1. runs /root/reference/TLSAN/build_dataset.py as-is (runpy, cwd = scratch dir whose
      ``../Data`` is a symlink to /root/reference/Data; one shim: ``pd.value_counts`` was
-     removed in pandas 3) -> dataset.pkl, stored as CSR arrays in digital_music.npz;
+     removed in pandas 3) -> dataset.pkl, stored as CSR arrays in digital_music.npz; the raw
+     review columns it read are stored next to it (digital_music_reviews.npz);
   2. imports /root/reference/TLSAN/input.py as-is and records DataInput / DataInputTest
      outputs for several (batch_size, k) settings -> input_batches.npz;
   3. evaluates the oracle restatement (fp64 and fp32) on fixed seeded weights for the first
@@ -161,6 +162,15 @@ def main():
     for k, v in to_csr(test_set, True).items():
         d["test_" + k] = v
     np.savez_compressed(os.path.join(GOLD, "digital_music.npz"), **d)
+    # raw inputs of build_dataset.py (the three columns of reviews_df; item -> category is `icl`):
+    # lets tests rebuild the dataset with tlsan_b200.build_dataset and compare with the reference output
+    with open(os.path.join(REF, "Data", "Digital_Music.pkl"), "rb") as f:
+        reviews_df, meta_df = pickle.load(f)
+    assert np.array_equal(meta_df["categories"].values, np.asarray(icl))
+    np.savez_compressed(os.path.join(GOLD, "digital_music_reviews.npz"),
+                        reviewer=reviews_df["reviewerID"].values.astype(np.int32),
+                        asin=reviews_df["asin"].values.astype(np.int32),
+                        day=reviews_df["unixReviewTime"].values.astype(np.int32))
     # round trip must reproduce the pickled samples exactly (floats compared as float32,
     # which is all that ever reaches the graph)
     back = from_csr(d, "train_", False)
