@@ -196,6 +196,15 @@ typedef struct {
 int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int32_t L, int32_t S, int32_t is_test,
                   int32_t* out, int64_t out_words, void* stream);
 
+/* Building blocks of the row-sharded configuration (item_emb / item_b / icl sharded by
+ * row over the ranks, ids and rows exchanged with all-to-all; orchestration in tlsan_b200/sharded.py):
+ * tlsan_reduce_cate: out[NC][32] = category gradient from the flat buffer of tlsan_step_grads (CSR order);
+ * tlsan_sgd_dense:   W <- W - lr*((g + reg*W) * *scale) element-wise (g may be NULL: pure L2 decay);
+ * tlsan_sumsq:       partial[c] = sum of squares of a grid-strided slice of W (fixed order). */
+int tlsan_reduce_cate(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float* out, void* stream);
+int tlsan_sgd_dense(float* W, const float* g, int64_t n, float lr, float reg, const float* scale, void* stream);
+int tlsan_sumsq(const float* W, int64_t n, float* partial, int32_t npartial, void* stream);
+
 /* Instrumentation for bench.py (not on the product path).
  * tlsan_launch_count: kernels launched by this library since load (all threads).
  * tlsan_profile_begin(max_steps): from now on every tlsan_step_grads / tlsan_apply_flat records

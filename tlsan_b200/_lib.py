@@ -57,6 +57,9 @@ _SIGS = {
     "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
     "tlsan_collate": (C.c_int, [C.POINTER(Dataset), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int64, C.c_void_p]),
+    "tlsan_reduce_cate": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tlsan_sgd_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "tlsan_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "tlsan_launch_count": (C.c_longlong, []),
     "tlsan_profile_begin": (C.c_int, [C.c_int32]),
     "tlsan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
