@@ -196,14 +196,40 @@ typedef struct {
 int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int32_t L, int32_t S, int32_t is_test,
                   int32_t* out, int64_t out_words, void* stream);
 
-/* Building blocks of the row-sharded configuration (item_emb / item_b / icl sharded by
- * row over the ranks, ids and rows exchanged with all-to-all; orchestration in tlsan_b200/sharded.py):
- * tlsan_reduce_cate: out[NC][32] = category gradient from the flat buffer of tlsan_step_grads (CSR order);
- * tlsan_sgd_dense:   W <- W - lr*((g + reg*W) * *scale) element-wise (g may be NULL: pure L2 decay);
- * tlsan_sumsq:       partial[c] = sum of squares of a grid-strided slice of W (fixed order). */
+/* Row-sharded item tables (SURVEY 8e / BASELINE config 5, NI = 10 M; no counterpart in the reference, whose
+ * tables live in one TF process).  item_emb / item_b / icl are split by row over the ranks.  Per step a rank
+ * asks the owners for the rows its batch touches (NCCL all-to-all of ids, then of rows), runs the unchanged
+ * tlsan_step_grads on a COMPACT table (row r = r-th distinct id of its batch), sends the per-id gradient rows
+ * back, and every owner applies L2 + clip + SGD to its shard.  Orchestration: tlsan_b200/sharded.py.
+ * Exchange row = TLSAN_SHARD_ROW words: 32 floats item_emb row | item_b | icl (int bits) | 2 pad; gradient
+ * rows: 32 floats d item_emb | d item_b | 3 pad.
+ *   tlsan_shard_pack_rows     owner: out[k] = row local_ids[k] of its shard; *bad_flag = 1 on a foreign id
+ *   tlsan_shard_unpack_rows   requester: compact table row dst_index[k] <- packed row k
+ *   tlsan_shard_pack_grads    requester: out[k] = reduced gradient (item half + item_b) of compact row src_index[k]
+ *   tlsan_shard_accum_grads   owner: g_emb/g_b[local_ids[k]] += packed[k]; ids of one call are distinct
+ *   tlsan_reduce_cate         out[NC][32] = category gradient from the flat buffer of tlsan_step_grads
+ *   tlsan_sumsq               partial[c] = sum of squares of a grid-strided slice of W (fixed order)
+ *   tlsan_sgd_dense           W <- W - lr*((g + reg*W) * *scale) element-wise (g may be NULL: pure L2 decay)
+ *   tlsan_shard_apply_replicated  norm / clip scale / loss statistics and the update of cate_emb, user_emb,
+ *                             usert_emb and the small parameters from rank-summed gradients; item_sumsq =
+ *                             rank-summed partial sums of squares of the whole sharded item_emb. */
+#define TLSAN_SHARD_ROW 36
+int tlsan_shard_pack_rows(const float* emb_shard, const float* item_b_shard, const int32_t* icl_shard,
+                          const int32_t* local_ids, int64_t n, int64_t n_local, float* out, int32_t* bad_flag,
+                          void* stream);
+int tlsan_shard_unpack_rows(const float* packed, const int32_t* dst_index, int64_t n, float* emb_c, float* item_b_c,
+                            int32_t* icl_c, void* stream);
+int tlsan_shard_pack_grads(const float* g_i, const float* g_b, const int32_t* src_index, int64_t n, float* out,
+                           void* stream);
+int tlsan_shard_accum_grads(const float* packed, const int32_t* local_ids, int64_t n, float* g_emb, float* g_b,
+                            void* stream);
 int tlsan_reduce_cate(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float* out, void* stream);
 int tlsan_sgd_dense(float* W, const float* g, int64_t n, float lr, float reg, const float* scale, void* stream);
 int tlsan_sumsq(const float* W, int64_t n, float* partial, int32_t npartial, void* stream);
+int tlsan_shard_apply_replicated(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* gcate,
+                                 const float* g_u, const float* dgrad, const float* item_sumsq,
+                                 int32_t n_item_sumsq, float lr, float reg, float clip_norm, void* workspace,
+                                 size_t workspace_bytes, float* stats, void* stream);
 
 /* Instrumentation for bench.py (not on the product path).
  * tlsan_launch_count: kernels launched by this library since load (all threads).

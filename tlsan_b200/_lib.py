@@ -6,6 +6,7 @@ import os
 from .build import LIB
 
 DENSE_COUNT, DENSE_PAD, STAT_COUNT, MAX_L = 4449, 4452, 8, 96
+PART, SHARD_ROW = 4456, 36
 OFF = dict(W1L=0, B1L=64, W2L=72, B2L=136, W1S=144, B1S=208, W2S=216, B2S=280, WD=288, BD=4384, GAMMA=4448)
 STAT = dict(loss=0, bce=1, norm=2, scale=3, l2=4)
 
@@ -57,6 +58,15 @@ _SIGS = {
     "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
     "tlsan_collate": (C.c_int, [C.POINTER(Dataset), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int64, C.c_void_p]),
+    "tlsan_shard_pack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tlsan_shard_unpack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "tlsan_shard_pack_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tlsan_shard_accum_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tlsan_shard_apply_replicated": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                               C.c_size_t, C.c_void_p, C.c_void_p]),
     "tlsan_reduce_cate": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]),
     "tlsan_sgd_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "tlsan_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

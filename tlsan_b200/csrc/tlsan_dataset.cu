@@ -63,90 +63,3 @@ extern "C" int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int3
   TLSAN_CHECK_LAUNCH("k_collate");
   return TLSAN_OK;
 }
-
-// ------------------------------------------------------------------ helpers for row-sharded tables
-// (item_emb / item_b / icl sharded by row over the ranks, all-to-all exchange)
-
-// out[k][0..32) = sum of the cate halves of the reduced rows of category k (CSR order) + its direct row
-__global__ void __launch_bounds__(256) k_reduce_cate(int NI, const float* __restrict__ g_i,
-                                                     const int* __restrict__ cate_off,
-                                                     const int* __restrict__ cate_items, float* __restrict__ out) {
-  __shared__ float sh[8][32];
-  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lo = cate_off[k], hi = cate_off[k + 1];
-  float acc = 0.f;
-  for (int n = lo + warp; n < hi; n += 8) acc += __ldg(g_i + (size_t)__ldg(cate_items + n) * 64 + 32 + lane);
-  sh[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    float g = g_i[(size_t)(NI + k) * 64 + 32 + lane];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) g += sh[w][lane];
-    out[(size_t)k * 32 + lane] = g;
-  }
-}
-
-// W <- W - lr * ((g + reg * W) * scale), g optional (NULL = rows without a sparse gradient);
-// also accumulates sum(W_old^2) partials when sq != NULL (fixed grid, fixed order)
-__global__ void __launch_bounds__(256) k_sgd_dense(float* __restrict__ W, const float* __restrict__ g, long long n,
-                                                   float lr, float reg, const float* __restrict__ scale_p) {
-  const float scale = *scale_p;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-    const float w = W[e];
-    W[e] = w - lr * (((g ? g[e] : 0.f) + reg * w) * scale);
-  }
-}
-
-__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ W, long long n, float* __restrict__ partial) {
-  __shared__ float sh[8];
-  float s = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) s = fmaf(W[e], W[e], s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float r = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) r += sh[w];
-    partial[blockIdx.x] = r;
-  }
-}
-
-extern "C" int tlsan_reduce_cate(const tlsan_dims_t* d, const tlsan_params_t* p, const float* flat, float* out,
-                                 void* stream) {
-  if (!d || !p || !flat || !out || !p->cate_off || !p->cate_items) {
-    tlsan_set_error("tlsan_reduce_cate: NULL argument");
-    return TLSAN_E_NULL;
-  }
-  k_reduce_cate<<<d->NC, 256, 0, (cudaStream_t)stream>>>(d->NI, flat, p->cate_off, p->cate_items, out);
-  TLSAN_CHECK_LAUNCH("k_reduce_cate");
-  return TLSAN_OK;
-}
-
-extern "C" int tlsan_sgd_dense(float* W, const float* g, int64_t n, float lr, float reg, const float* scale,
-                               void* stream) {
-  if (!W || !scale || n < 0) {
-    tlsan_set_error("tlsan_sgd_dense: bad argument");
-    return TLSAN_E_NULL;
-  }
-  if (n == 0) return TLSAN_OK;
-  long long blocks = (n + 255) / 256;
-  const long long cap = (long long)tlsan_num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  k_sgd_dense<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, g, n, lr, reg, scale);
-  TLSAN_CHECK_LAUNCH("k_sgd_dense");
-  return TLSAN_OK;
-}
-
-extern "C" int tlsan_sumsq(const float* W, int64_t n, float* partial, int32_t npartial, void* stream) {
-  if (!W || !partial || npartial <= 0) {
-    tlsan_set_error("tlsan_sumsq: bad argument");
-    return TLSAN_E_NULL;
-  }
-  k_sumsq<<<npartial, 256, 0, (cudaStream_t)stream>>>(W, n, partial);
-  TLSAN_CHECK_LAUNCH("k_sumsq");
-  return TLSAN_OK;
-}

@@ -172,8 +172,10 @@ __device__ __forceinline__ double block_sum_1024d(double v, double* sh) {   // f
   return r;
 }
 
+// extra_sq[n_extra] (optional): partial sums of squares of table rows that live elsewhere (row-sharded item_emb)
 __global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dgrad, const float* __restrict__ tsq,
-                                                    int ntsq, float invB, float lr, float reg, float clip,
+                                                    int ntsq, const float* __restrict__ extra_sq, int n_extra,
+                                                    float invB, float lr, float reg, float clip,
                                                     float* __restrict__ dense, float* __restrict__ stats) {
   __shared__ double sh[32];
   float g[5];
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dg
   double t = 0.0;
   for (int c = threadIdx.x; c < ntsq; c += 1024)
     t += (double)tsq[c * 4] + (double)tsq[c * 4 + 1] + (double)tsq[c * 4 + 2] + (double)tsq[c * 4 + 3];
+  for (int c = threadIdx.x; c < n_extra; c += 1024) t += (double)extra_sq[c];
   t = block_sum_1024d(t, sh);
   const double sq = (double)dgrad[TLSAN_PART_SUMSQ] + dense_sq + (double)reg * (double)reg * t;
   const float norm = (float)sqrt(sq);
@@ -352,7 +355,7 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
                                       (long long)d.NU * 32, (long long)d.NU * d.L, tsq);
   TLSAN_CHECK_LAUNCH("k_table_sumsq");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, invB, lr, reg, clip, p.dense, stats);
+  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, nullptr, 0, invB, lr, reg, clip, p.dense, stats);
   TLSAN_CHECK_LAUNCH("k_finalize2");
   const long long n4 = (long long)d.NI * 8 + (long long)d.NU * 8 + (long long)d.NU * d.L + d.NI;
   long long blocks = (n4 + 255) / 256;
@@ -363,6 +366,32 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
   TLSAN_CHECK_LAUNCH("k_apply_rows");
   k_apply_cate<<<d.NC, 256, 0, st>>>(d.NI, p.emb, g_i, p.cate_off, p.cate_items, lr, reg, stats);
   TLSAN_CHECK_LAUNCH("k_apply_cate");
+  return TLSAN_OK;
+}
+
+// Replicated part of the row-sharded configuration (tlsan_shard.cu): the item slots of the compact table are
+// scratch, so the table kernels run with an item count of 0 on the tail of `p.emb` (cate rows first).
+int tlsan_launch_apply_replicated(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
+                                  const float* gcate, const float* g_u, const float* dgrad, const float* item_sumsq,
+                                  int n_item_sumsq, float lr, float reg, float clip, float* stats, cudaStream_t st) {
+  (void)gcate;
+  float* tsq = reinterpret_cast<float*>(ws + w.tsq);
+  int ntsq = tlsan_num_sms() * 2;
+  if (ntsq > TLSAN_MAX_GRID) ntsq = TLSAN_MAX_GRID;
+  float* tail = p.emb + (size_t)d.NI * 32;          // cate rows, then user rows
+  k_table_sumsq<<<ntsq, 256, 0, st>>>(tail, p.usert, 0, (long long)d.NC * 32, (long long)d.NU * 32,
+                                      (long long)d.NU * d.L, tsq);
+  TLSAN_CHECK_LAUNCH("k_table_sumsq");
+  const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
+  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, item_sumsq, n_item_sumsq, invB, lr, reg, clip, p.dense, stats);
+  TLSAN_CHECK_LAUNCH("k_finalize2");
+  const long long n4 = (long long)d.NU * 8 + (long long)d.NU * d.L;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)tlsan_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  k_apply_rows<<<(unsigned)blocks, 256, 0, st>>>(0, d.NC, d.NU, d.L, w.PU, tail, p.usert, nullptr, nullptr, nullptr,
+                                                 g_u, lr, reg, stats);
+  TLSAN_CHECK_LAUNCH("k_apply_rows");
   return TLSAN_OK;
 }
 

@@ -122,8 +122,9 @@ def pack_batch(lib, batch, dims, is_test, out, validate=True):
 
 
 class Model(object):
-    def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True):
-        self.config = config
+    @staticmethod
+    def _check_config(config):
+        """The kernels are built for the reference defaults that define the path (train.py:26-49)."""
         if config.get("num_blocks", 1) != 1:
             raise ValueError("num_blocks != 1 is ill-formed in the reference (model.py:331-364); unsupported")
         if (config.get("hidden_units", 64), config.get("num_heads", 8)) != (64, 8) or any(
@@ -134,6 +135,10 @@ class Model(object):
             raise ValueError("dropout > 0 is not supported (reference default 0.0, train.py:30)")
         if config.get("optimizer", "sgd") != "sgd":
             raise ValueError("only the reference default optimizer 'sgd' is implemented (train.py:40)")
+
+    def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True):
+        self.config = config
+        self._check_config(config)
         self._lib = _lib.lib()                                  # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.TlsanError("tlsan_b200 needs a CUDA device (no CPU fallback)")

@@ -1,0 +1,397 @@
+"""Row-sharded item tables (BASELINE config 5: a 10 M-item catalogue on 8 x B200).
+
+``item_emb`` (NI x 32), ``item_b`` and ``item_cate_list`` are split by row over the ranks of a process
+group; ``cate_emb``, ``user_emb``, ``usert_emb`` and the 4 449 small parameters stay replicated.  The reference
+has no counterpart (its tables live in one TF process, TLSAN/model.py:56-81); the arithmetic of a step is the
+same as ``Model.train`` -- the weights after a step equal the replicated model's up to fp32 summation order
+(tests/test_gpu_sharded.py).
+
+One step on every rank:
+
+1. distinct item ids of the local batch (``hist_i``, ``hist_i_new``, ``i`` [, ``i2``]), sorted        -> ``uniq``
+2. NCCL all-to-all of the ids to their owners, owners answer with 144-B exchange rows
+   (item_emb row | item_b | icl), all-to-all back                        (tlsan_shard_pack_rows / _unpack_rows)
+3. the rows land in a COMPACT table (row r = r-th distinct id; category and user rows follow at a fixed
+   offset), the batch ids are rewritten to compact indices, and the unchanged fused kernels run on it
+   (``tlsan_step_grads``: sort, forward, backward, deterministic segmented reduce)
+4. all-reduce (sum) of [user/usert gradients | small-parameter gradients, loss and norm partials | category
+   gradients | partial sums of squares of the item shards]                                    -- ONE collective
+5. per-id gradient rows travel back to the owners with the splits of (2); an owner adds the contributions in
+   rank order (deterministic) into a dense shard-shaped buffer and applies W <- W - lr*scale*(g + reg*W) to
+   every row of its shard (the L2 term touches all rows, model.py:164-169)     (tlsan_shard_accum_grads, tlsan_sgd_dense)
+6. the replicated tables are updated identically on every rank                 (tlsan_shard_apply_replicated)
+
+PyTorch supplies device memory, ``torch.unique`` / ``sort`` for the index bookkeeping of (1) and the NCCL
+collectives; every gather, scatter, reduction and update of table data is a kernel of libtlsan_b200.so.
+There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import PART, SHARD_ROW, STAT, Batch, Dims, Params, check
+from .model import DENSE_LAYOUT, DeviceBatch, Model, _pack_offsets, pack_batch
+
+NSQ = 256          # partial sums of squares per item shard
+
+
+def owner_of(ids, world, NI, partition):
+    """Owner rank of each global item id.  ``mod``: id % world (cyclic); ``block``: contiguous blocks of
+    ceil(NI / world) rows."""
+    if partition == "mod":
+        return ids % world
+    return ids // (-(-NI // world))
+
+
+def local_of(ids, world, NI, partition):
+    """Row index inside the owner's shard."""
+    if partition == "mod":
+        return ids // world
+    return ids % (-(-NI // world))
+
+
+def shard_ids(rank, world, NI, partition):
+    """Global ids of the rows of ``rank``'s shard, in shard order (numpy int64)."""
+    if partition == "mod":
+        return np.arange(rank, NI, world, dtype=np.int64)
+    blk = -(-NI // world)
+    return np.arange(min(rank * blk, NI), min((rank + 1) * blk, NI), dtype=np.int64)
+
+
+def exchange(send, in_splits, out_splits, group, world):
+    """all_to_all_single with explicit row splits (rows of ``send`` grouped by destination rank)."""
+    if world == 1:
+        return send
+    recv = torch.empty((int(sum(out_splits)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send.contiguous(), list(out_splits), list(in_splits), group=group)
+    return recv
+
+
+def route_ids(uniq, world, NI, partition, group):
+    """Step (2a): send every distinct id to its owner.  Returns (order, recv_ids, in_splits, out_splits):
+    ``uniq[order]`` is the send buffer (grouped by owner, ids ascending inside a group), ``recv_ids`` the ids
+    this rank must serve, grouped by requesting rank."""
+    owner = owner_of(uniq, world, NI, partition)
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world)
+    if world == 1:
+        n = [int(uniq.numel())]
+        return order, uniq[order], n, n
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    in_splits = [int(x) for x in counts.tolist()]
+    out_splits = [int(x) for x in recv_counts.tolist()]
+    recv_ids = exchange(uniq[order], in_splits, out_splits, group, world)
+    return order, recv_ids, in_splits, out_splits
+
+
+class ShardedModel(object):
+    """TLSAN with row-sharded item tables.  Same train / eval_auc surface as ``Model``."""
+
+    def __init__(self, config, item_cate_list, process_group=None, partition="mod", seed=1234, device=None,
+                 validate=True):
+        if partition not in ("mod", "block"):
+            raise ValueError("partition must be 'mod' or 'block'")
+        Model._check_config(config)
+        self._lib = _lib.lib()
+        if not torch.cuda.is_available():
+            raise _lib.TlsanError("tlsan_b200 needs a CUDA device (no CPU fallback)")
+        self.config = config
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if process_group is not None else 1
+        self.rank = dist.get_rank(process_group) if process_group is not None else 0
+        self.partition = partition
+        self.NI, self.NU, self.NC = int(config["item_count"]), int(config["user_count"]), int(config["cate_count"])
+        self.L = int(config["Ls"])
+        self.PU = (32 + self.L + 3) // 4 * 4
+        self.reg = float(config.get("regulation_rate", 0.00005))
+        self.clip = float(config.get("max_gradient_norm", 5.0))
+        self.validate = validate
+        dev = self.device
+
+        mine = shard_ids(self.rank, self.world, self.NI, partition)
+        self.n_local = int(mine.size)
+        icl = np.asarray(item_cate_list)
+        if icl.shape != (self.NI,) or icl.min() < 0 or icl.max() >= self.NC:
+            raise ValueError("item_cate_list must be int[item_count] with values in [0, cate_count)")
+        self.icl_shard = torch.from_numpy(np.ascontiguousarray(icl[mine].astype(np.int32))).to(dev)
+        # glorot_uniform like tf.get_variable (model.py:62-81); one stream per rank for the shard
+        g = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
+        lim = (6.0 / (self.NI + 32)) ** 0.5
+        self.item_emb_shard = (torch.rand(max(self.n_local, 1), 32, generator=g, device=dev) * 2 - 1) * lim
+        self.item_b_shard = torch.zeros(max(self.n_local, 1), device=dev)
+        gr = torch.Generator().manual_seed(seed)              # replicated part: same on every rank
+
+        def glorot(rows, cols):
+            return (torch.rand(rows, cols, generator=gr) * 2 - 1) * (6.0 / (rows + cols)) ** 0.5
+        self._tail = torch.cat([glorot(self.NC, 32), glorot(self.NU, 32)]).to(dev)   # cate rows, then user rows
+        self.usert_emb = torch.full((self.NU, self.L), -1.0, device=dev)
+        dense = torch.zeros(_lib.DENSE_PAD)
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            if name == "gamma_parameter":
+                dense[off] = 1.0
+            elif len(shape) == 2:
+                dense[off:off + shape[0] * shape[1]] = glorot(*shape).reshape(-1)
+        self.dense = dense.to(dev)
+
+        self.cap = 0
+        self._grow(1024)
+        self._g_emb = torch.zeros(max(self.n_local, 1), 32, device=dev)
+        self._g_b = torch.zeros(max(self.n_local, 1), device=dev)
+        self._bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
+        self._ws = None
+        self._score_ws = None
+        self._flat = None
+        self._stage_cache = {}
+        self.global_step = 0
+        self.last_unique = 0
+        self.last_exchange_bytes = 0
+        self.profile = None          # set to [] to collect (label, cuda event) marks per step (tools/bench_sharded.py)
+
+    # ------------------------------------------------------------------ compact table
+    def _grow(self, need):
+        """Compact table = [cap item slots | NC cate rows | NU user rows]; the tail holds the master copy of the
+        replicated cate_emb / user_emb, so growing the item capacity moves it."""
+        cap = max(1024, -(-int(need) // 1024) * 1024)
+        if cap <= self.cap:
+            return
+        dev = self.device
+        tail = self._tail if self.cap == 0 else self.emb_c[self.cap:]
+        emb_c = torch.zeros(cap + self.NC + self.NU, 32, device=dev)
+        emb_c[cap:] = tail
+        self.emb_c, self.cap, self._tail = emb_c, cap, None
+        self.item_b_c = torch.zeros(cap, device=dev)
+        self.icl_c = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.cate_off = torch.zeros(self.NC + 1, dtype=torch.int32, device=dev)
+        self.cate_items = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self._params = Params(emb=self.emb_c.data_ptr(), usert=self.usert_emb.data_ptr(),
+                              item_b=self.item_b_c.data_ptr(), dense=self.dense.data_ptr(),
+                              icl=self.icl_c.data_ptr(), cate_off=self.cate_off.data_ptr(),
+                              cate_items=self.cate_items.data_ptr())
+        self._ws = None
+        self._flat = None
+
+    @property
+    def cate_emb(self):
+        return self.emb_c[self.cap:self.cap + self.NC]
+
+    @property
+    def user_emb(self):
+        return self.emb_c[self.cap + self.NC:]
+
+    def _dims(self, B, S, B_global=None):
+        return Dims(B=B, L=self.L, S=S, NI=self.cap, NU=self.NU, NC=self.NC,
+                    B_global=int(B_global if B_global is not None else B), reserved=0)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _mark(self, label):
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((label, ev))
+
+    # ------------------------------------------------------------------ staging
+    def stage_batch(self, batch, is_test=False):
+        """Host 9-tuple (GLOBAL item ids) -> device, like Model.stage_batch; ids are range-checked against
+        the global item_count."""
+        B = len(batch[0])
+        S = max(int(np.shape(batch[4])[1]), 1)
+        if np.shape(batch[3])[1] != self.L:
+            raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (np.shape(batch[3])[1], self.L))
+        offs, total = _pack_offsets(B, self.L, S)
+        key = (B, S)
+        if key not in self._stage_cache:
+            self._stage_cache[key] = torch.empty(total, dtype=torch.int32).pin_memory()
+        host = self._stage_cache[key]
+        gd = Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC, B_global=B, reserved=0)
+        pack_batch(self._lib, batch, gd, is_test, host.numpy(), self.validate)
+        dev = torch.empty(total, dtype=torch.int32, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        return DeviceBatch(dev, B, self.L, S, offs, is_test)
+
+    def _id_fields(self, db):
+        f = [("hist_i", db.B * db.L), ("hist_i_new", db.B * db.S), ("i", db.B)]
+        if db.is_test:
+            f.append(("second", db.B))
+        return f
+
+    def _fetch(self, db):
+        """Steps (1)-(3a): returns (compact DeviceBatch, plan) with the touched rows in the compact table."""
+        lib, st = self._lib, self._stream()
+        fields = self._id_fields(db)
+        ids = torch.cat([db.buf[db.offs[k]:db.offs[k] + n] for k, n in fields])
+        uniq, inv = torch.unique(ids, sorted=True, return_inverse=True)
+        n_u = int(uniq.numel())
+        self._grow(n_u)
+        order, recv_ids, in_splits, out_splits = route_ids(uniq.to(torch.int64), self.world, self.NI, self.partition,
+                                                           self.pg)
+        n_recv = int(recv_ids.numel())
+        local = local_of(recv_ids, self.world, self.NI, self.partition).to(torch.int32)
+        rows_out = torch.empty(max(n_recv, 1), SHARD_ROW, dtype=torch.float32, device=self.device)
+        check(lib.tlsan_shard_pack_rows(self.item_emb_shard.data_ptr(), self.item_b_shard.data_ptr(),
+                                        self.icl_shard.data_ptr(), local.data_ptr(), n_recv, self.n_local,
+                                        rows_out.data_ptr(), self._bad.data_ptr(), st))
+        rows_in = exchange(rows_out[:n_recv], out_splits, in_splits, self.pg, self.world)
+        order32 = order.to(torch.int32)
+        check(lib.tlsan_shard_unpack_rows(rows_in.data_ptr(), order32.data_ptr(), n_u, self.emb_c.data_ptr(),
+                                          self.item_b_c.data_ptr(), self.icl_c.data_ptr(), st))
+        # compact batch: same packed buffer with the id fields rewritten
+        cbuf = db.buf.clone()
+        inv32, o = inv.to(torch.int32), 0
+        for k, n in fields:
+            cbuf[db.offs[k]:db.offs[k] + n] = inv32[o:o + n]
+            o += n
+        cb = DeviceBatch(cbuf, db.B, db.L, db.S, db.offs, db.is_test)
+        self.last_unique = n_u
+        self.last_exchange_bytes = (n_u + n_recv) * (4 + 4 * SHARD_ROW)
+        plan = dict(n_u=n_u, order32=order32, local=local, in_splits=in_splits, out_splits=out_splits, n_recv=n_recv)
+        return cb, plan
+
+    def _compact_csr(self, n_u):
+        """Items of the compact table grouped by category (stable), for the hierarchical category reduce."""
+        icl = self.icl_c[:n_u]
+        self.cate_items[:n_u] = torch.sort(icl, stable=True).indices.to(torch.int32)
+        self.cate_off[1:] = torch.cumsum(torch.bincount(icl, minlength=self.NC), 0).to(torch.int32)
+
+    # ------------------------------------------------------------------ training
+    def train_staged(self, db, lr, global_batch=None):
+        lib, st = self._lib, self._stream()
+        self._mark("start")
+        cb, plan = self._fetch(db)
+        n_u = plan["n_u"]
+        self._compact_csr(n_u)
+        self._mark("fetch_rows")
+        Bg = global_batch if global_batch is not None else db.B * self.world
+        dims = self._dims(db.B, db.S, Bg)
+        need = C.c_size_t()
+        check(lib.tlsan_workspace_bytes(C.byref(dims), C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        f_gb = (self.cap + self.NC) * 64
+        f_gu = f_gb + (self.cap + 3) // 4 * 4
+        f_dgrad = f_gu + self.NU * self.PU
+        n_flat = C.c_int64()
+        check(lib.tlsan_flat_count(C.byref(dims), C.byref(n_flat)))
+        assert n_flat.value == f_dgrad + PART
+        f_cate, f_sq = f_dgrad + PART, f_dgrad + PART + self.NC * 32
+        total = f_sq + NSQ
+        if self._flat is None or self._flat.numel() != total:
+            self._flat = torch.empty(total, dtype=torch.float32, device=self.device)
+        flat = self._flat
+        fp = lambda off: flat.data_ptr() + 4 * off
+        check(lib.tlsan_step_grads(C.byref(dims), C.byref(self._params), C.byref(cb.c), self._ws.data_ptr(),
+                                   self._ws.numel(), flat.data_ptr(), st))
+        check(lib.tlsan_reduce_cate(C.byref(dims), C.byref(self._params), flat.data_ptr(), fp(f_cate), st))
+        check(lib.tlsan_sumsq(self.item_emb_shard.data_ptr(), self.n_local * 32, fp(f_sq), NSQ, st))
+        self._mark("step_grads")
+        if self.world > 1:
+            dist.all_reduce(flat[f_gu:], group=self.pg)
+        self._mark("allreduce")
+        # gradient rows of the distinct ids -> owners (reverse of the row exchange)
+        grads_out = torch.empty(max(n_u, 1), SHARD_ROW, dtype=torch.float32, device=self.device)
+        check(lib.tlsan_shard_pack_grads(flat.data_ptr(), fp(f_gb), plan["order32"].data_ptr(), n_u,
+                                         grads_out.data_ptr(), st))
+        grads_in = exchange(grads_out[:n_u], plan["in_splits"], plan["out_splits"], self.pg, self.world)
+        self._g_emb.zero_()
+        self._g_b.zero_()
+        o = 0
+        for cnt in plan["out_splits"]:          # source ranks in rank order: fixed summation order
+            if cnt:
+                check(lib.tlsan_shard_accum_grads(grads_in.data_ptr() + 4 * SHARD_ROW * o,
+                                                  plan["local"].data_ptr() + 4 * o, cnt, self._g_emb.data_ptr(),
+                                                  self._g_b.data_ptr(), st))
+            o += cnt
+        self._mark("return_grads")
+        check(lib.tlsan_shard_apply_replicated(C.byref(dims), C.byref(self._params), fp(f_cate), fp(f_gu), fp(f_dgrad),
+                                               fp(f_sq), NSQ, lr, self.reg, self.clip, self._ws.data_ptr(),
+                                               self._ws.numel(), self._stats.data_ptr(), st))
+        scale = self._stats.data_ptr() + 4 * STAT["scale"]
+        check(lib.tlsan_sgd_dense(self.item_emb_shard.data_ptr(), self._g_emb.data_ptr(), self.n_local * 32, lr,
+                                  self.reg, scale, st))
+        check(lib.tlsan_sgd_dense(self.item_b_shard.data_ptr(), self._g_b.data_ptr(), self.n_local, lr, 0.0, scale, st))
+        self._mark("apply")
+        self.global_step += 1
+        return self._stats
+
+    def train(self, sess, batch, lr, add_summary=False):
+        """Model.train (model.py:208-234) on this rank's rows of the global batch."""
+        stats = self.train_staged(self.stage_batch(batch), float(lr))
+        if int(self._bad.item()):
+            raise _lib.TlsanError("an item id was routed to a rank that does not own it")
+        return float(stats[STAT["loss"]].item())
+
+    # ------------------------------------------------------------------ scoring
+    def score_staged(self, db, ncand=1):
+        cb, _ = self._fetch(db)
+        dims = self._dims(db.B, db.S)
+        logits = torch.empty(db.B, ncand, dtype=torch.float32, device=self.device)
+        if db.B >= 2048:                                       # same kernel selection as Model.score_staged
+            need = C.c_size_t()
+            check(self._lib.tlsan_score_workspace_bytes(C.byref(dims), C.byref(need)))
+            if self._score_ws is None or self._score_ws.numel() < need.value:
+                self._score_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+            check(self._lib.tlsan_score_ws(C.byref(dims), C.byref(self._params), C.byref(cb.c), ncand,
+                                           logits.data_ptr(), None, self._score_ws.data_ptr(),
+                                           self._score_ws.numel(), self._stream()))
+        else:
+            check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(cb.c), ncand,
+                                        logits.data_ptr(), None, self._stream()))
+        return logits
+
+    def eval_auc(self, sess, batch):
+        """Model.eval_auc (model.py:237-263) on this rank's rows."""
+        res = self.score_staged(self.stage_batch(batch, is_test=True), 2).cpu().numpy()
+        return np.mean(res[:, 0] - res[:, 1] > 0)
+
+    # ------------------------------------------------------------------ state
+    def load_full_state(self, sd):
+        """Take this rank's rows of a full (replicated-model) state dict -- tests and checkpoints."""
+        mine = torch.from_numpy(shard_ids(self.rank, self.world, self.NI, self.partition))
+        if self.n_local:
+            self.item_emb_shard[:self.n_local] = torch.as_tensor(np.asarray(sd["item_emb"]), dtype=torch.float32)[mine].to(self.device)
+            self.item_b_shard[:self.n_local] = torch.as_tensor(np.asarray(sd["item_b"]), dtype=torch.float32)[mine].to(self.device)
+        self.cate_emb.copy_(torch.as_tensor(np.asarray(sd["cate_emb"]), dtype=torch.float32))
+        self.user_emb.copy_(torch.as_tensor(np.asarray(sd["user_emb"]), dtype=torch.float32))
+        self.usert_emb.copy_(torch.as_tensor(np.asarray(sd["usert_emb"]), dtype=torch.float32))
+        dense = self.dense.detach().cpu().clone()
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            n = int(np.prod(shape)) if shape else 1
+            dense[off:off + n] = torch.as_tensor(np.asarray(sd[name]), dtype=torch.float32).reshape(-1)
+        self.dense.copy_(dense)
+
+    def gather_full_state(self):
+        """Reassemble the full state dict on every rank (all_gather of the shards)."""
+        sd = {}
+        mine = torch.from_numpy(shard_ids(self.rank, self.world, self.NI, self.partition)).to(self.device)
+        pad = -(-self.NI // self.world)
+        emb = torch.zeros(pad, 33, device=self.device)
+        ids = torch.full((pad,), -1, dtype=torch.int64, device=self.device)
+        emb[:self.n_local, :32] = self.item_emb_shard[:self.n_local]
+        emb[:self.n_local, 32] = self.item_b_shard[:self.n_local]
+        ids[:self.n_local] = mine
+        if self.world > 1:
+            embs = [torch.empty_like(emb) for _ in range(self.world)]
+            idss = [torch.empty_like(ids) for _ in range(self.world)]
+            dist.all_gather(embs, emb, group=self.pg)
+            dist.all_gather(idss, ids, group=self.pg)
+            emb, ids = torch.cat(embs), torch.cat(idss)
+        keep = ids >= 0
+        full = torch.zeros(self.NI, 33, device=self.device)
+        full[ids[keep]] = emb[keep]
+        sd["item_emb"] = full[:, :32].cpu()
+        sd["item_b"] = full[:, 32].cpu()
+        sd["user_emb"] = self.user_emb.detach().cpu().clone()
+        sd["usert_emb"] = self.usert_emb.detach().cpu().clone()
+        sd["cate_emb"] = self.cate_emb.detach().cpu().clone()
+        dense = self.dense.detach().cpu()
+        for name, (off, shape) in DENSE_LAYOUT.items():
+            n = int(np.prod(shape)) if shape else 1
+            sd[name] = dense[off:off + n].reshape(shape).clone()
+        return sd
