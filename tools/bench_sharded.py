@@ -49,7 +49,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    marks, per = m.profile, 7
+    marks, per = m.profile, 6
     names = [marks[i][0] for i in range(1, per)]
     ph = np.zeros(per - 1)
     for s_ in range(args.steps):
