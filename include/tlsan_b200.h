@@ -170,6 +170,14 @@ int tlsan_pack_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int6
                           const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* out,
                           int64_t out_words, int32_t validate, int32_t nthreads);
 
+/* tlsan_pack_batch_host + the host->device copy of the feed: packs into `pinned` (page-locked host memory) in
+ * three phases and issues cudaMemcpyAsync(dev + off, pinned + off) on `stream` as each phase completes, so the
+ * copy of one phase overlaps the packing of the next.  `pinned` may be reused once `stream` has passed the copies. */
+int tlsan_stage_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int64_t* i, const int64_t* i2,
+                           const float* y, const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t,
+                           const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* pinned, int32_t* dev,
+                           int64_t words, int32_t validate, int32_t nthreads, void* stream);
+
 /* Device-resident dataset.  CSR image, in HBM, of the samples built by
  * TLSAN/build_dataset.py:58-59,71: per sample r its user, its long-term history
  * pre_items / pre_time [pre_off[r], pre_off[r+1]) (pre_time = float32(1/n), input.py:36,45), its session

@@ -46,6 +46,35 @@ static int fused_impl() {
 }
 static bool use_mma() { return fused_impl() >= 1; }
 
+// The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
+// onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
+// events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+  static SideStream per_dev[64];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TLSAN_SORT_OVERLAP");
+    enabled = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.st) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s.st = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
+static bool g_prof_overlap = false;   // the recorded steps ran the sort on the side stream
+
 #define REQUIRE(cond, code, ...)      \
   do {                                \
     if (!(cond)) {                    \
@@ -178,12 +207,26 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t* sorted_vals = nullptr;
   tlsan_profile_mark(-1, st);
-  if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
-  tlsan_profile_mark(TLSAN_PHASE_SORT, st);
+  SideStream* side = use_mma() ? side_stream() : nullptr;
+  cudaEvent_t sorted = nullptr;
+  if (side) {
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, side->st))) return rc;
+    tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
+    sorted = side->join;
+    g_prof_overlap = true;
+  } else {
+    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
+    tlsan_profile_mark(TLSAN_PHASE_SORT, st);
+    g_prof_overlap = false;
+  }
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
-    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, st);
-  else if (fused_impl() == 1) rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, st);
+    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, sorted, st);
+  else if (fused_impl() == 1)
+    rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
   if (rc) return rc;
   if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;
@@ -253,8 +296,10 @@ int tlsan_profile_end(float* ms, int32_t* steps) {
   for (int s = 0; s < n; ++s) {
     TLSAN_CHECK_CUDA(cudaEventSynchronize(g_ev[(size_t)s * per + TLSAN_PHASE_COUNT]));
     for (int ph = 0; ph < TLSAN_PHASE_COUNT; ++ph) {
-      // FUSED_A / BWD_LONG share one mark pair per kernel, see tlsan_launch_fwd_bwd
-      TLSAN_CHECK_CUDA(cudaEventElapsedTime(&ms[s * TLSAN_PHASE_COUNT + ph], g_ev[(size_t)s * per + ph],
+      // a phase runs from the previous mark to its own; with the sort on the side stream the long-term
+      // forward starts at the step-start mark like the sort does (the two overlap)
+      const int begin = (ph == TLSAN_PHASE_LONG_FWD && g_prof_overlap) ? 0 : ph;
+      TLSAN_CHECK_CUDA(cudaEventElapsedTime(&ms[s * TLSAN_PHASE_COUNT + ph], g_ev[(size_t)s * per + begin],
                                             g_ev[(size_t)s * per + ph + 1]));
     }
   }

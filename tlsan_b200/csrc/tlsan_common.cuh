@@ -116,10 +116,11 @@ int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, c
 int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                            float* logits, float* ut, cudaStream_t st);
 int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
-                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st);
+                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaEvent_t sorted,
+                             cudaStream_t st);
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
-                               cudaStream_t st);
+                               cudaEvent_t sorted, cudaStream_t st);
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                           float* logits, float* ut, float* scratch, cudaStream_t st);
 int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,

@@ -387,7 +387,8 @@ static int launch_async(const FArgs& a, int* grid_out, cudaStream_t st) {
   return TLSAN_OK;
 }
 
-int tlsan_launch_long_fwd_mma(const FArgs& a, cudaStream_t st);
+int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
+int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
 
 // `hybrid` (default): per kernel, whichever formulation measured faster on B200 (profiles/):
@@ -396,7 +397,7 @@ int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
 // kernel (its per-sample dependent chain is otherwise exposed: 130 -> 113 us).
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
-                               cudaStream_t st) {
+                               cudaEvent_t sorted, cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
@@ -404,11 +405,12 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   int rc;
-  if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, st) : launch_async<1>(a, nullptr, st))) return rc;
+  if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st) : launch_async<1>(a, nullptr, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_a);
+  if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
   if ((rc = launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
   if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))

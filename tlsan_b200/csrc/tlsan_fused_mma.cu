@@ -20,6 +20,7 @@
 //   k_fwd_mma<2>     short FWA forward + logit + loss + backward of logit / short FWA (model.py:135-137,164-172,350-364)
 //   k_dense_bwd_mma  d o_long = dz Wd^T ; dWd = O^T dZ ; dbd
 //   k_bwd_long_mma   backward of the long FWA and of the time-aware position term (model.py:98-109)
+#include <stdlib.h>
 #include "tlsan_mma_common.cuh"
 
 // long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state.
@@ -101,6 +102,11 @@ __global__ void __launch_bounds__(MMA_THREADS, (MODE == 1 || MODE == 3) ? 3 : 2)
   if (TRAIN) { wst = load_fwa_t(a.dense, TLSAN_OFF_W1S, L.g, L.t); G.init(); }
   float* vec = sm.vec[warp];
   const int nwarps = gridDim.x * MMA_WARPS;
+  // per-warp staging of one round of long-term token rows.  MODE 1 (training) owns the whole dynamic smem and
+  // sizes it by L (a round holds min(32, ell) tokens): 16-row slots when L <= 16 leave shared memory for the
+  // radix-sort kernels that run beside it on the side stream.
+  float (*rowbuf)[64] = MODE == 1 ? reinterpret_cast<float (*)[64]>(smem_raw) + (size_t)warp * (a.L <= 16 ? 16 : 32)
+                                  : sm.rows[warp];
 
   for (int b = blockIdx.x * MMA_WARPS + warp; b < a.B; b += nwarps) {
     const int u = __ldg(a.u + b);
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(MMA_THREADS, (MODE == 1 || MODE == 3) ? 3 : 2)
       // ---- long-term FWA forward
       const int ell = __ldg(a.sl + b);
       Soft2 st;
-      long_forward(a, L, b, u, ell, gamma, wl, sm.rows[warp], st);
+      long_forward(a, L, b, u, ell, gamma, wl, rowbuf, st);
       const float o[2] = {st.den[0] > 0.f ? st.acc[0] / st.den[0] : 0.f, st.den[1] > 0.f ? st.acc[1] / st.den[1] : 0.f};
       if (MODE == 1) {
         float* sc = a.scratch + (size_t)b * (TLSAN_SCR * 64) + L.f0;
@@ -285,10 +291,10 @@ __global__ void __launch_bounds__(MMA_THREADS, (MODE == 1 || MODE == 3) ? 3 : 2)
 // ------------------------------------------------------------------ backward of the long-term FWA
 __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) {
   extern __shared__ __align__(16) unsigned char smem_b[];
-  float (*rowsb)[32][64] = reinterpret_cast<float (*)[32][64]>(smem_b);          // [warp][32][64]
   float (*red)[160] = reinterpret_cast<float (*)[160]>(smem_b);                   // reused after the loop
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
+  float (*rowsw)[64] = reinterpret_cast<float (*)[64]>(smem_b) + (size_t)warp * (a.L <= 16 ? 16 : 32);   // [warp][16|32][64]
   const float gamma = a.dense[TLSAN_OFF_GAMMA];
   const FwaW wl = load_fwa(a.dense, TLSAN_OFF_W1L, L.g, L.t);
   const FwaWT wlt = load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t);
@@ -310,13 +316,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_bwd_long_mma(const FArgs a) 
       const int cnt = min(32, ell - r0);
       float dtau_l = 0.f;                          // lane j collects d tau of token r0 + j
       const int inv_l = L.lane < cnt ? __ldg(a.inv + ((size_t)b << a.spsh) + r0 + L.lane) : 0;   // sorted ranks
-      stage_round_rows(a, me, cnt, L.lane, rowsb[warp]);
+      stage_round_rows(a, me, cnt, L.lane, rowsw);
       for (int j = 0; j < cnt; j += 2) {
         Pair cur;
         cur.okB = j + 1 < cnt;
         cur.tA = __shfl_sync(0xffffffffu, me.tau, j); cur.tB = __shfl_sync(0xffffffffu, me.tau, (j + 1) & 31);
-        cur.eA = *reinterpret_cast<const float2*>(&rowsb[warp][j][L.f0]);
-        cur.eB = cur.okB ? *reinterpret_cast<const float2*>(&rowsb[warp][j + 1][L.f0]) : make_float2(0.f, 0.f);
+        cur.eA = *reinterpret_cast<const float2*>(&rowsw[j][L.f0]);
+        cur.eB = cur.okB ? *reinterpret_cast<const float2*>(&rowsw[j + 1][L.f0]) : make_float2(0.f, 0.f);
         const int posA = __shfl_sync(0xffffffffu, inv_l, j), posB = __shfl_sync(0xffffffffu, inv_l, (j + 1) & 31);
         const bool okB = cur.okB;
         const float2 eA = cur.eA, eB = cur.eB;
@@ -568,6 +574,11 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
 FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b);
 
 
+int tlsan_overlap_ctas() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("TLSAN_OVERLAP_CTAS"); v = e ? atoi(e) : 2; if (v < 1 || v > 3) v = 2; }
+  return v;
+}
 static int mma_grid(int B, int ctas_per_sm) {
   const int need = (B + MMA_WARPS - 1) / MMA_WARPS;
   const int cap = tlsan_num_sms() * ctas_per_sm;
@@ -592,23 +603,26 @@ int tlsan_launch_dense_bwd(const float* dense, float* scratch, int B, float* par
   return TLSAN_OK;
 }
 
-static const int kSmemLongFwd = (int)(sizeof(float) * MMA_WARPS * (160 + 32 * 64));   // red + rows of SmemMma
-static const int kSmemBwdLong = (int)(sizeof(float) * MMA_WARPS * 32 * 64);
+static const int kSmemLongMax = (int)(sizeof(float) * MMA_WARPS * 32 * 64);
+// staging area of the long-term kernels: [warp][16 or 32 token rows][64]; never below the 8 x 160 floats the
+// backward reuses for its end-of-kernel reduction
+static int smem_long(int L) { return (int)(sizeof(float) * MMA_WARPS * (L <= 16 ? 16 : 32) * 64); }
 
 static int set_long_attrs() {
   static bool done = false;
   if (!done) {
-    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLongFwd));
-    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_long_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwdLong));
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLongMax));
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_long_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLongMax));
     done = true;
   }
   return TLSAN_OK;
 }
 
-int tlsan_launch_long_fwd_mma(const FArgs& a, cudaStream_t st) {
+// ctas_per_sm: 3 fills the register file; 2 leaves a third of it to the radix-sort kernels on the side stream
+int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st) {
   int rc = set_long_attrs();
   if (rc) return rc;
-  k_fwd_mma<1><<<mma_grid(a.B, 3), MMA_THREADS, kSmemLongFwd, st>>>(a, 1);
+  k_fwd_mma<1><<<mma_grid(a.B, ctas_per_sm), MMA_THREADS, smem_long(a.L), st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<long>");
   return TLSAN_OK;
 }
@@ -618,7 +632,7 @@ int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st) {
   if (rc) return rc;
   const int g = mma_grid(a.B, 2);
   *grid_b = g;
-  k_bwd_long_mma<<<g, MMA_THREADS, kSmemBwdLong, st>>>(a);
+  k_bwd_long_mma<<<g, MMA_THREADS, smem_long(a.L), st>>>(a);
   TLSAN_CHECK_LAUNCH("k_bwd_long_mma");
   return TLSAN_OK;
 }
@@ -644,7 +658,7 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
   FArgs a = tlsan_make_fargs(d, p, b);
   a.logits = logits; a.ut = ut; a.scratch = scratch;
   int rc;
-  if ((rc = tlsan_launch_long_fwd_mma(a, st))) return rc;
+  if ((rc = tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
   if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
   k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short score>");
@@ -652,7 +666,8 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
 }
 
 int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
-                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaStream_t st) {
+                             const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaEvent_t sorted,
+                             cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
@@ -661,13 +676,14 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   // forward: long FWA -> dense GEMM -> short FWA + loss + backward of logit / short FWA
   int rc;
-  if ((rc = tlsan_launch_long_fwd_mma(a, st))) return rc;
+  if ((rc = tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   const int g = mma_grid(d.B, 2);
   *grid_a = g; *grid_b = g;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
+  if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
   k_fwd_mma<2><<<g, MMA_THREADS, sizeof(float) * MMA_WARPS * 160, st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short>");
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);

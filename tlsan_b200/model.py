@@ -97,9 +97,11 @@ def _pack_offsets(B, L, S):
     return offs, o
 
 
-def pack_batch(lib, batch, dims, is_test, out, validate=True):
+def pack_batch(lib, batch, dims, is_test, out, validate=True, dev_ptr=None, stream=None):
     """Host-side feed (reference model.py:210-222): the 9-tuple -> packed int32 words in ``out``.
-    Out-of-range ids raise IndexError, like tf.gather on CPU (InvalidArgumentError)."""
+    Out-of-range ids raise IndexError, like tf.gather on CPU (InvalidArgumentError).
+    With ``dev_ptr`` the words are also copied to the device on ``stream``, phase by phase while the
+    rest is still being packed (tlsan_stage_batch_host; ``out`` must then be pinned memory)."""
     def i64(x):
         return np.ascontiguousarray(x, dtype=np.int64)
     B, S = dims.B, dims.S
@@ -114,8 +116,13 @@ def pack_batch(lib, batch, dims, is_test, out, validate=True):
     if hist_i.shape != (B, dims.L) or hist_t.shape != (B, dims.L) or hist_i_new.shape != (B, S):
         raise ValueError("batch arrays have inconsistent shapes")
     p = lambda a: None if a is None else a.ctypes.data
-    rc = lib.tlsan_pack_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
-                                   p(sl), p(sl_new), p(c), out.ctypes.data, out.size, 1 if validate else 0, 0)
+    if dev_ptr is None:
+        rc = lib.tlsan_pack_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
+                                       p(sl), p(sl_new), p(c), out.ctypes.data, out.size, 1 if validate else 0, 0)
+    else:
+        rc = lib.tlsan_stage_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
+                                        p(sl), p(sl_new), p(c), out.ctypes.data, dev_ptr, out.size,
+                                        1 if validate else 0, 0, stream)
     if rc == -1:
         raise IndexError(lib.tlsan_last_error().decode())
     check(rc)
@@ -238,11 +245,13 @@ class Model(object):
         offs, total = _pack_offsets(B, self.L, S)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = torch.empty(total, dtype=torch.int32).pin_memory()
-        host = self._stage_cache[key]
-        pack_batch(self._lib, batch, self._dims(B, S), is_test, host.numpy(), self.validate)
+            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        host, ev = self._stage_cache[key]
+        ev.synchronize()                      # the previous copy out of this pinned buffer has finished
         dev = torch.empty(total, dtype=torch.int32, device=self.device)
-        dev.copy_(host, non_blocking=True)
+        pack_batch(self._lib, batch, self._dims(B, S), is_test, host.numpy(), self.validate, dev.data_ptr(),
+                   self._stream())
+        ev.record(torch.cuda.current_stream(self.device))
         self.last_h2d_bytes = total * 4
         return DeviceBatch(dev, B, self.L, S, offs, is_test)
 

@@ -208,12 +208,13 @@ class ShardedModel(object):
         offs, total = _pack_offsets(B, self.L, S)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = torch.empty(total, dtype=torch.int32).pin_memory()
-        host = self._stage_cache[key]
+            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        host, ev = self._stage_cache[key]
+        ev.synchronize()
         gd = Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC, B_global=B, reserved=0)
-        pack_batch(self._lib, batch, gd, is_test, host.numpy(), self.validate)
         dev = torch.empty(total, dtype=torch.int32, device=self.device)
-        dev.copy_(host, non_blocking=True)
+        pack_batch(self._lib, batch, gd, is_test, host.numpy(), self.validate, dev.data_ptr(), self._stream())
+        ev.record(torch.cuda.current_stream(self.device))
         return DeviceBatch(dev, B, self.L, S, offs, is_test)
 
     def _id_fields(self, db):
