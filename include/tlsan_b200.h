@@ -160,6 +160,13 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
 int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut,
                      const int32_t* label, int32_t* rank, void* stream);
 
+/* The same ranks on the tcgen05 tensor cores: a [B,64]x[64,NI] 3xTF32 GEMM whose accumulator tiles
+ * stay in TMEM and are only counted, never stored (csrc/tlsan_rank_tc.cu).  The workspace holds the catalogue
+ * re-laid out as UMMA operand tiles (73 728 B per 128 items), rebuilt on every call from the current weights. */
+int tlsan_rank_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes);
+int tlsan_label_rank_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut, const int32_t* label,
+                        int32_t* rank, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host helper (no GPU work): pack the 9-tuple of TLSAN/input.py:54,107 (int64 ids, fp32 hist_t) into
  * ONE int32 staging buffer -- the int64->int32 feed cast of model.py:210-222 -- multi-threaded, with
  * the id range checks TF's CPU gather performs.  Segment order (each rounded up to 4 words):

@@ -272,6 +272,25 @@ int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
   return tlsan_launch_label_rank(*dims, *p, ut, label, rank, (cudaStream_t)stream);
 }
 
+int tlsan_rank_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(bytes != nullptr, TLSAN_E_NULL, "bytes is NULL");
+  *bytes = tlsan_rank_ws_bytes(*dims);
+  return TLSAN_OK;
+}
+
+int tlsan_label_rank_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut, const int32_t* label,
+                        int32_t* rank, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, false))) return rc;
+  REQUIRE(ut && label && rank && workspace, TLSAN_E_NULL, "NULL argument");
+  REQUIRE(aligned16(ut), TLSAN_E_ALIGN, "ut must be 16-B aligned");
+  REQUIRE(workspace_bytes >= tlsan_rank_ws_bytes(*dims), TLSAN_E_WORKSPACE, "workspace too small");
+  return tlsan_launch_label_rank_tc(*dims, *p, ut, label, rank, ws_base(workspace), (cudaStream_t)stream);
+}
+
 long long tlsan_launch_count(void) { return g_tlsan_launches; }
 
 int tlsan_profile_begin(int32_t max_steps) {

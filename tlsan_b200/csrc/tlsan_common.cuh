@@ -133,4 +133,7 @@ int tlsan_launch_apply_replicated(const tlsan_dims_t& d, const tlsan_params_t& p
                                   int n_item_sumsq, float lr, float reg, float clip, float* stats, cudaStream_t st);
 int tlsan_launch_label_rank(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
                             int32_t* rank, cudaStream_t st);
+size_t tlsan_rank_ws_bytes(const tlsan_dims_t& d);
+int tlsan_launch_label_rank_tc(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
+                               int32_t* rank, char* img, cudaStream_t st);
 int tlsan_num_sms();

@@ -407,7 +407,7 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&h)[4], ui
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     h[i] = to_tf32(x[i]);
-    l[i] = to_tf32(x[i] - __uint_as_float(h[i]));
+    l[i] = __float_as_uint(x[i] - __uint_as_float(h[i]));   // the tensor core drops the low 13 bits itself
   }
 }
 // acc += A(16x8) B(8x8), B fragment read from the hi/lo images at rows (k0+2t, k0+2t+1), column n0+g
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
       for (int nt = 0; nt < 8; ++nt) {
         const float b0 = sz[(s0 + t) * TILE_LD + nt * 8 + g], b1 = sz[(s0 + t + 4) * TILE_LD + nt * 8 + g];
         const uint32_t bh0 = to_tf32(b0), bh1 = to_tf32(b1);
-        const uint32_t bl0 = to_tf32(b0 - __uint_as_float(bh0)), bl1 = to_tf32(b1 - __uint_as_float(bh1));
+        const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0)), bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
         mma_tf32(accw[nt], l[0], l[2], l[1], l[3], bh0, bh1);
         mma_tf32(accw[nt], h[0], h[2], h[1], h[3], bl0, bl1);
         mma_tf32(accw[nt], h[0], h[2], h[1], h[3], bh0, bh1);

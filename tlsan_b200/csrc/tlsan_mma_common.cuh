@@ -42,7 +42,7 @@ __device__ __forceinline__ void mma3(float (&d)[4], const float (&x)[4], const B
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     h[i] = to_tf32(x[i]);
-    l[i] = to_tf32(x[i] - __uint_as_float(h[i]));
+    l[i] = __float_as_uint(x[i] - __uint_as_float(h[i]));   // low 13 bits are dropped by the tensor core: no LOP
   }
   // the two small terms chain on one accumulator, the big term runs beside them; packed final add
   float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -130,11 +130,15 @@ __device__ __forceinline__ void tile_bwd(const float (&x)[4], bool okB, const fl
   tile_maps(x, w, m1, m2);
   // softmax weight times d out: a * do, with (1/den) * do folded into one per-feature factor
   const float kf[2] = {inv[0] * dout[0], inv[1] * dout[1]};
+  // exp(m2 - mx) = ex2(m2 * log2e - mx * log2e): the second product is per sample (hoisted out of the tile loop)
+  const float nmx[2] = {-mx[0] * 1.4426950408889634f, -mx[1] * 1.4426950408889634f};
   float ado[4], dm2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = i & 1;
-    const float aw = exp_neg(m2[i] - mx[j]) * kf[j];
+    float ee;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ee) : "f"(fmaf(m2[i], 1.4426950408889634f, nmx[j])));
+    const float aw = ee * kf[j];
     ado[i] = (i < 2 || okB) ? aw : 0.f;
     dm2[i] = ado[i] * (x[i] - o[j]);
   }

@@ -204,6 +204,7 @@ class Model(object):
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
         self._ws = None
         self._score_ws = None
+        self._rank_ws = None
         self._flat = None
         self._stage_cache = {}
         self.last_h2d_bytes = 0
@@ -331,8 +332,17 @@ class Model(object):
         dims = self._dims(db.B, db.S)
         rank = torch.empty(db.B, dtype=torch.int32, device=self.device)
         label = db.buf[db.offs["i"]:db.offs["i"] + db.B]
-        check(self._lib.tlsan_label_rank(C.byref(dims), C.byref(self._params), ut.data_ptr(), label.data_ptr(),
-                                         rank.data_ptr(), self._stream()))
+        if os.environ.get("TLSAN_RANK_IMPL", "tc") == "ffma":     # CUDA-core formulation, kept for A/B timing
+            check(self._lib.tlsan_label_rank(C.byref(dims), C.byref(self._params), ut.data_ptr(), label.data_ptr(),
+                                             rank.data_ptr(), self._stream()))
+        else:
+            need = C.c_size_t()
+            check(self._lib.tlsan_rank_workspace_bytes(C.byref(dims), C.byref(need)))
+            if self._rank_ws is None or self._rank_ws.numel() < need.value:
+                self._rank_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+            check(self._lib.tlsan_label_rank_ws(C.byref(dims), C.byref(self._params), ut.data_ptr(), label.data_ptr(),
+                                                rank.data_ptr(), self._rank_ws.data_ptr(), self._rank_ws.numel(),
+                                                self._stream()))
         return rank.cpu().numpy()
 
     def _metric(self, n, which):
