@@ -192,8 +192,8 @@ static char* ws_base(void* workspace) {
   return reinterpret_cast<char*>(tlsan_align_up(reinterpret_cast<uintptr_t>(workspace), 256));
 }
 
-int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
-                     size_t workspace_bytes, float* flat, void* stream) {
+static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
+                           size_t workspace_bytes, float* flat, bool with_tsq, void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
@@ -216,10 +216,13 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
     sorted = side->join;
+    // ||W||^2 of the tables needs only the (still unchanged) weights: off the critical path too
+    if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, side->st))) return rc;
     g_prof_overlap = true;
   } else {
     if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, st);
+    if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, st))) return rc;
     g_prof_overlap = false;
   }
   int grid_a = 0, grid_b = 0, grid_c = 0;
@@ -229,14 +232,25 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
     rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
   if (rc) return rc;
-  if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;
-  rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+  if (side) {
+    // the fixed-order sum of the per-CTA partials and the segmented row reduce are independent: side by side
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, side->st))) return rc;
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
+    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+    TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  } else {
+    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;
+    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
+  }
   tlsan_profile_mark(TLSAN_PHASE_REDUCE, st);
   return rc;
 }
 
-int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
-                     float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+static int apply_flat_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
+                           float clip_norm, void* workspace, size_t workspace_bytes, float* stats, bool have_tsq,
+                           void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
@@ -247,9 +261,19 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
           w.total + 256);
   char* ws = ws_base(workspace);
   rc = tlsan_launch_apply(*dims, *p, w, ws, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, flat + w.f_dgrad, lr,
-                          reg, clip_norm, stats, (cudaStream_t)stream);
+                          reg, clip_norm, have_tsq, stats, (cudaStream_t)stream);
   tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
   return rc;
+}
+
+int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
+                     size_t workspace_bytes, float* flat, void* stream) {
+  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, false, stream);
+}
+
+int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
+                     float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, false, stream);
 }
 
 int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, float lr, float reg,
@@ -259,8 +283,9 @@ int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   REQUIRE(workspace != nullptr, TLSAN_E_NULL, "workspace is NULL");
   const TlsanWs w = tlsan_ws_layout(*dims);
   float* flat = reinterpret_cast<float*>(ws_base(workspace) + w.flat);
-  if ((rc = tlsan_step_grads(dims, p, b, workspace, workspace_bytes, flat, stream))) return rc;
-  return tlsan_apply_flat(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, stream);
+  // one fused step: the table norms are computed beside the forward kernels (weights change only in apply)
+  if ((rc = step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, true, stream))) return rc;
+  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
 }
 
 int tlsan_label_rank(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut, const int32_t* label,

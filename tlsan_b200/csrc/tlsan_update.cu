@@ -345,15 +345,31 @@ int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, i
   return TLSAN_OK;
 }
 
+static int tsq_grid() {
+  int ntsq = tlsan_num_sms() * 2;
+  return ntsq > TLSAN_MAX_GRID ? TLSAN_MAX_GRID : ntsq;
+}
+
+// ||W||^2 partials of the four regularised tables; depends on the weights only, so a fused train step
+// runs it on the side stream while the forward kernels run
+int tlsan_launch_table_sumsq(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
+                             cudaStream_t st) {
+  k_table_sumsq<<<tsq_grid(), 256, 0, st>>>(p.emb, p.usert, (long long)d.NI * 32, (long long)d.NC * 32,
+                                            (long long)d.NU * 32, (long long)d.NU * d.L,
+                                            reinterpret_cast<float*>(ws + w.tsq));
+  TLSAN_CHECK_LAUNCH("k_table_sumsq");
+  return TLSAN_OK;
+}
+
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                        const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
-                       float reg, float clip, float* stats, cudaStream_t st) {
+                       float reg, float clip, bool have_tsq, float* stats, cudaStream_t st) {
   float* tsq = reinterpret_cast<float*>(ws + w.tsq);
-  int ntsq = tlsan_num_sms() * 2;
-  if (ntsq > TLSAN_MAX_GRID) ntsq = TLSAN_MAX_GRID;
-  k_table_sumsq<<<ntsq, 256, 0, st>>>(p.emb, p.usert, (long long)d.NI * 32, (long long)d.NC * 32,
-                                      (long long)d.NU * 32, (long long)d.NU * d.L, tsq);
-  TLSAN_CHECK_LAUNCH("k_table_sumsq");
+  const int ntsq = tsq_grid();
+  if (!have_tsq) {
+    int rc = tlsan_launch_table_sumsq(d, p, w, ws, st);
+    if (rc) return rc;
+  }
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
   k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, nullptr, 0, invB, lr, reg, clip, p.dense, stats);
   TLSAN_CHECK_LAUNCH("k_finalize2");
