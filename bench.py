@@ -386,6 +386,29 @@ def main():
     barrier()
     ms_score = e0.elapsed_time(e1) / 10
 
+    # ---------------- full-catalogue ranking (eval_prec / eval_recall hot kernel, tcgen05 3xTF32 GEMM)
+    rb = min(B, 65536)
+    ut = torch.randn(rb, 64, device="cuda")
+    lab = torch.randint(0, NI, (rb,), dtype=torch.int32, device="cuda")
+    rk = torch.empty(rb, dtype=torch.int32, device="cuda")
+    rdims = model._dims(rb, 1)
+    need = C.c_size_t()
+    _lib.check(lib.tlsan_rank_workspace_bytes(C.byref(rdims), C.byref(need)))
+    rws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+
+    def rank_once():
+        _lib.check(lib.tlsan_label_rank_ws(C.byref(rdims), C.byref(model._params), ut.data_ptr(), lab.data_ptr(),
+                                           rk.data_ptr(), rws.data_ptr(), rws.numel(), None))
+    for _ in range(3):
+        rank_once()
+    barrier()
+    e0.record()
+    for _ in range(10):
+        rank_once()
+    e1.record()
+    barrier()
+    ms_rank = e0.elapsed_time(e1) / 10
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -442,6 +465,15 @@ def main():
                                      "assembly in the input.py layout) + train step, no host batcher", "steps": ds_steps},
         "eval": {"metric": "eval_seqs_per_s", "value": B * world / (ms_score * 1e-3), "unit": "seqs/s",
                  "candidates": 2},
+        "eval_rank": {"metric": "full_catalogue_rank_seqs_per_s", "value": rb * world / (ms_rank * 1e-3), "unit": "seqs/s",
+                      "what": "eval_prec/eval_recall hot kernel: [B,64]x[64,NI] 3xTF32 tcgen05 GEMM + count-only "
+                              "epilogue (k_build_catalogue + k_label_rank_tc), B=%d, NI=%d" % (rb, NI),
+                      "roofline": {"bound": "tensor", "achieved": 3 * 2.0 * rb * NI * 72 / (ms_rank * 1e-3) / 1e12,
+                                   "peak": float(peaks.get("bf16_tflops", 1590.0)) / 2.0, "unit": "TFLOP/s",
+                                   "frac": 3 * 2.0 * rb * NI * 72 / (ms_rank * 1e-3) / 1e12 /
+                                           (float(peaks.get("bf16_tflops", 1590.0)) / 2.0),
+                                   "note": "issued tf32 flops (3 terms, K padded 64->72); peak = measured bf16 "
+                                           "cuBLAS burst / 2 (tf32 runs at half the bf16 rate)"}},
         "final_loss": loss,
     }
     _emit(line)

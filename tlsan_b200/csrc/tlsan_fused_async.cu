@@ -408,9 +408,9 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st) : launch_async<1>(a, nullptr, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
-  tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
+  tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
   if ((rc = launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
   if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))

@@ -679,11 +679,11 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
   if ((rc = tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
-  tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);
   const int g = mma_grid(d.B, 2);
   *grid_a = g; *grid_b = g;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
+  tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
   k_fwd_mma<2><<<g, MMA_THREADS, sizeof(float) * MMA_WARPS * 160, st>>>(a, 1);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short>");
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
