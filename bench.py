@@ -2,7 +2,10 @@
 """bench.py -- TLSAN train-step throughput on B200 (contract: see the task statement / DESIGN.md).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--batch B] [--Ls L] [--no-cpu-baseline]
+                    [--batch B] [--Ls L] [--no-cpu-baseline] [--workload electronics|movies] [--strong]
+
+--workload movies = BASELINE.json configs[2] (Movies-TV shape: NU 35 896, NI 28 589, NC 15); --strong keeps the
+GLOBAL batch at --batch and gives every rank batch/N rows (strong scaling); the default is weak scaling.
 
 Workload (BASELINE.json configs[1]): "TLSAN Electronics-shape synthetic (40k users, 22k items,
 673 cates) fp32": NU 39 991, NI 22 048, NC 673, generators of SURVEY.md section 8d config 2
@@ -31,6 +34,9 @@ sys.path.insert(0, ROOT)
 
 NU, NI, NC = 39991, 22048, 673
 N_SAMPLES = 561100
+WORKLOADS = {"electronics": ("TLSAN Electronics-shape synthetic", 39991, 22048, 673),
+             "movies": ("TLSAN Movies-TV-shape synthetic", 35896, 28589, 15)}
+WL_NAME = WORKLOADS["electronics"][0]
 # Digital-Music empirical laws: P(min(len,10) = k), k = 1..10 ; short length pmf
 P_LONG = np.array([7.0, 6.9, 6.7, 6.5, 6.3, 5.9, 5.2, 4.5, 3.9, 47.1]) / 100.0
 P_SHORT_HEAD = np.array([.8724, .0886, .0223, .0085, .0040])
@@ -215,8 +221,8 @@ def run_reference(args, rank):
 
 
 def workload_config(args, B):
-    return {"workload": "TLSAN Electronics-shape synthetic (NU 39991, NI 22048, NC 673), train step "
-                        "(fwd+bwd+L2+clip+SGD)", "per_gpu_batch": B, "global_batch": B * args.gpus,
+    return {"workload": "%s (NU %d, NI %d, NC %d), train step (fwd+bwd+L2+clip+SGD)" % (WL_NAME, NU, NI, NC),
+            "per_gpu_batch": B, "global_batch": B * args.gpus,
             "Ls": args.Ls, "short_max": S_MAX, "lr": 1.0, "optimizer": "sgd", "parallelism": "dp%d" % args.gpus,
             "l2_policy": "several distinct device-resident batches cycled; per-step working set "
                          "(gradient rows + tables + batch) exceeds the 126 MB L2"}
@@ -255,8 +261,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no e2e / scoring / cpu legs")
+    ap.add_argument("--workload", default="electronics", choices=sorted(WORKLOADS))
+    ap.add_argument("--strong", action="store_true", help="fixed GLOBAL batch: every rank gets batch / N rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global NU, NI, NC, WL_NAME
+    WL_NAME, NU, NI, NC = WORKLOADS[args.workload]
+    if args.strong:
+        args.batch = max(1, args.batch // max(args.gpus, 1))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -455,7 +467,8 @@ def main():
     line = {
         "metric": "train_samples_per_s", "value": args.steps * B * world / (ms * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, B),
         "e2e": {"value": e2e_steps * B * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps},

@@ -65,7 +65,7 @@ typedef struct {
   int32_t S;        /* width of hist_i_new = max short length in batch (input.py:33,37) */
   int32_t NI, NU, NC;
   int32_t B_global; /* denominator of reduce_mean (model.py:171); = B on one GPU */
-  int32_t reserved;
+  int32_t reserved; /* flags; bit 0: tlsan_step_grads skips the table norms (row-sharded callers compute their own) */
 } tlsan_dims_t;
 
 /* Trainable state, model.py:56-81.  `emb` is ONE table: rows [0,NI) = item_emb,
@@ -147,7 +147,10 @@ int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
  *   segmented reduce into ONE flat fp32 buffer `flat` of tlsan_flat_count() floats
  *   (sparse-part table gradients, dense gradients, sum-of-squares and loss partials),
  *   which the caller all-reduces (sum) across ranks;
- * tlsan_apply_flat: L2 term + clip + SGD from the reduced buffer (identical on every rank). */
+ * tlsan_apply_flat: L2 term + clip + SGD from the reduced buffer (identical on every rank).  It must follow
+ *   tlsan_step_grads on the SAME workspace with the weights unchanged in between: the sums of squares of the
+ *   tables (l2_loss, model.py:164-169) are computed by tlsan_step_grads beside its forward kernels and read
+ *   back from the workspace here. */
 int tlsan_flat_count(const tlsan_dims_t* dims, int64_t* count);
 int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
                      void* workspace, size_t workspace_bytes, float* flat, void* stream);

@@ -268,12 +268,14 @@ static int apply_flat_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
 
 int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
                      size_t workspace_bytes, float* flat, void* stream) {
-  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, false, stream);
+  // the table norms go into the workspace here (beside the forward kernels): tlsan_apply_flat, which must
+  // follow on the same workspace with the weights unchanged, reads them instead of recomputing
+  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, dims && !(dims->reserved & 1), stream);
 }
 
 int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
                      float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
-  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, false, stream);
+  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
 }
 
 int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, float lr, float reg,

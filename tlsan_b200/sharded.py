@@ -186,7 +186,7 @@ class ShardedModel(object):
 
     def _dims(self, B, S, B_global=None):
         return Dims(B=B, L=self.L, S=S, NI=self.cap, NU=self.NU, NC=self.NC,
-                    B_global=int(B_global if B_global is not None else B), reserved=0)
+                    B_global=int(B_global if B_global is not None else B), reserved=1)   # norms: see train_staged
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
