@@ -225,7 +225,9 @@ def workload_config(args, B):
             "per_gpu_batch": B, "global_batch": B * args.gpus,
             "Ls": args.Ls, "short_max": S_MAX, "lr": 1.0, "optimizer": "sgd", "parallelism": "dp%d" % args.gpus,
             "l2_policy": "several distinct device-resident batches cycled; per-step working set "
-                         "(gradient rows + tables + batch) exceeds the 126 MB L2"}
+                         "(gradient rows + tables + batch) exceeds the 126 MB L2",
+            "pipeline": "off" if getattr(args, "no_pipeline", False) else
+                        "occurrence sort of batch k+1 enqueued behind the backward kernels of step k"}
 
 
 _REAL_STDOUT = None
@@ -261,6 +263,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no e2e / scoring / cpu legs")
+    ap.add_argument("--no-pipeline", action="store_true", help="do not presort the next batch behind the current step")
     ap.add_argument("--workload", default="electronics", choices=sorted(WORKLOADS))
     ap.add_argument("--strong", action="store_true", help="fixed GLOBAL batch: every rank gets batch / N rows")
     args = ap.parse_args()
@@ -308,8 +311,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timed region
+    nres = len(dev_batches)
+    pipe = not args.no_pipeline          # name the next batch: its occurrence sort runs behind this step's backward
     for w in range(args.warmup):
-        model.train_staged(dev_batches[w % len(dev_batches)], 1.0)
+        model.train_staged(dev_batches[w % nres], 1.0, next_db=dev_batches[(w + 1) % nres] if pipe else None)
     barrier()
     launches0 = lib.tlsan_launch_count()
     _lib.check(lib.tlsan_profile_begin(args.steps))
@@ -319,7 +324,8 @@ def main():
         clocks.mark_begin()
     e0.record()
     for k in range(args.steps):
-        model.train_staged(dev_batches[k % len(dev_batches)], 1.0)
+        model.train_staged(dev_batches[(args.warmup + k) % nres], 1.0,
+                           next_db=dev_batches[(args.warmup + k + 1) % nres] if pipe else None)
     e1.record()
     barrier()
     if clocks:
@@ -371,13 +377,18 @@ def main():
     dds = DeviceDataset(csr, is_test=False)
     perm = torch.randperm(len(dds), device="cuda", dtype=torch.int32)
     nb = len(dds) // B
+    def ds_batch(k):
+        return dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max")
     for k in range(3):
-        model.train_staged(dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max"), 1.0)
+        model.train_staged(ds_batch(k), 1.0)
     barrier()
     ds_steps = max(3, min(args.steps, 50))
     e0.record()
-    for k in range(ds_steps):
-        model.train_staged(dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max"), 1.0)
+    cur = ds_batch(0)
+    for k in range(ds_steps):            # batch k+1 is assembled (and, pipelined, sorted) while step k runs
+        nxt = ds_batch(k + 1)
+        model.train_staged(cur, 1.0, next_db=nxt if pipe else None)
+        cur = nxt
     e1.record()
     barrier()
     t_ds = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -437,7 +448,7 @@ def main():
     ph = phase[:nrec.value].mean(axis=0)
     phases_ms = {n: float(v) for n, v in zip(_lib.PHASES, ph)}
     per_batch = [algorithmic_bytes(b, L) for b in host_batches]
-    used = [per_batch[k % len(per_batch)] for k in range(args.steps)]
+    used = [per_batch[(args.warmup + k) % len(per_batch)] for k in range(args.steps)]
     mean_bytes = {k: float(np.mean([u[k] for u in used])) for k in used[0]}
     train_bytes = mean_bytes["train"] + 2 * table_bytes(L) + 2 * 4 * 4449
     # dominant kernel = the longest of the per-sample gather kernels (each phase below is ONE kernel)

@@ -65,7 +65,7 @@ typedef struct {
   int32_t S;        /* width of hist_i_new = max short length in batch (input.py:33,37) */
   int32_t NI, NU, NC;
   int32_t B_global; /* denominator of reduce_mean (model.py:171); = B on one GPU */
-  int32_t reserved; /* flags; bit 0: tlsan_step_grads skips the table norms (row-sharded callers compute their own) */
+  int32_t reserved; /* flags; bit 0: tlsan_step_grads skips the table norms (row-sharded callers compute their own); bit 1: this batch was presorted into this workspace by the previous *_pipelined call */
 } tlsan_dims_t;
 
 /* Trainable state, model.py:56-81.  `emb` is ONE table: rows [0,NI) = item_emb,
@@ -157,6 +157,23 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
 int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat,
                      float lr, float reg, float clip_norm, void* workspace, size_t workspace_bytes,
                      float* stats, void* stream);
+
+/* Pipelined variants: `next` (optional) names the batch of the FOLLOWING step and that step's own workspace.  Its
+ * occurrence sort is enqueued behind the backward kernels of this step, where it runs beside the reduce, the
+ * all-reduce and the update; the following call passes the same batch / workspace with dims->reserved bit 1 set
+ * and starts without a sort.  Results are identical to the plain entry points. */
+typedef struct {
+  const tlsan_dims_t* dims;
+  const tlsan_batch_t* batch;
+  void* workspace;
+  size_t workspace_bytes;
+} tlsan_next_t;
+int tlsan_train_step_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                               const tlsan_next_t* next, float lr, float reg, float clip_norm, void* workspace,
+                               size_t workspace_bytes, float* stats, void* stream);
+int tlsan_step_grads_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                               const tlsan_next_t* next, void* workspace, size_t workspace_bytes, float* flat,
+                               void* stream);
 
 /* Full-catalogue ranking for Model.eval_prec / eval_recall (model.py:140-156,265-299):
  * rank[b] = #items scored above label[b] under u_t . all_emb^T + item_b with top_k tie order. */

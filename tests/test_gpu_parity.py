@@ -163,6 +163,34 @@ def test_train_step_is_deterministic(dm):
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
+def test_pipelined_steps_equal_plain_steps(dm):
+    """tlsan_train_step_pipelined: presorting batch k+1 behind step k (other workspace, side stream) must not
+    change a bit -- different batch shapes per step, and a step whose announced successor is NOT the batch
+    that follows (the presorted result is dropped and the step sorts itself)."""
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    sizes = [300, 64, 512, 300, 7, 300]
+    batches, lo = [], 0
+    for n in sizes:
+        batches.append(O.collate_train(dm.train_set[lo:lo + n], 10)); lo += n
+    outs = []
+    for mode in ("plain", "pipelined", "mispredicted"):
+        model = model_from_params(params, dm.icl, cfg)
+        dbs = [model.stage_batch(b) for b in batches]
+        for k, db in enumerate(dbs):
+            nxt = None
+            if mode == "pipelined" and k + 1 < len(dbs):
+                nxt = dbs[k + 1]
+            if mode == "mispredicted":
+                nxt = dbs[(k + 2) % len(dbs)]
+            model.train_staged(db, 1.0, next_db=nxt)
+        torch.cuda.synchronize()
+        outs.append({k: v.numpy().copy() for k, v in model.state_dict().items()})
+    for other in outs[1:]:
+        for k in outs[0]:
+            assert np.array_equal(outs[0][k], other[k]), k
+
+
 def test_gather_concat_bit_exact():
     from tlsan_b200 import _lib
     rng = np.random.default_rng(3)

@@ -23,6 +23,11 @@ class Batch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("u", "i", "i2", "y", "hist_i", "hist_i_new", "hist_t", "sl", "sl_new", "c")]
 
 
+class Next(C.Structure):
+    _fields_ = [("dims", C.POINTER(Dims)), ("batch", C.POINTER(Batch)), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
 class Dataset(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("uid", "pre_off", "pre_items", "pre_time", "new_off", "new_items", "cand",
                                           "second_i", "second_f", "ucate")] + [("n", C.c_int64)]
@@ -48,6 +53,11 @@ _SIGS = {
     "tlsan_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),
     "tlsan_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_float, C.c_float,
                                    C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "tlsan_train_step_pipelined": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.POINTER(Next),
+                                             C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
+                                             C.c_void_p]),
+    "tlsan_step_grads_pipelined": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.POINTER(Next),
+                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "tlsan_flat_count": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_int64)]),
     "tlsan_step_grads": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Batch), C.c_void_p, C.c_size_t,
                                    C.c_void_p, C.c_void_p]),

@@ -49,7 +49,7 @@ static bool use_mma() { return fused_impl() >= 1; }
 // The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
 // onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
 // events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
-struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr; };
 static SideStream* side_stream() {
   static SideStream per_dev[64];
   static int enabled = -1;
@@ -65,6 +65,8 @@ static SideStream* side_stream() {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, lo) != cudaSuccess ||   // presort: fills gaps
+        cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
       s.st = nullptr;
@@ -74,6 +76,22 @@ static SideStream* side_stream() {
   return &s;
 }
 static bool g_prof_overlap = false;   // the recorded steps ran the sort on the side stream
+
+// Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
+// one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
+struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr; bool valid = false; };
+static Presort g_presort[8];
+static Presort* presort_slot(char* ws, bool create) {
+  for (auto& e : g_presort) if (e.ws == ws) return &e;
+  if (!create) return nullptr;
+  for (auto& e : g_presort)
+    if (!e.valid) {
+      if (!e.ev && cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      e.ws = ws;
+      return &e;
+    }
+  return nullptr;
+}
 
 #define REQUIRE(cond, code, ...)      \
   do {                                \
@@ -193,7 +211,7 @@ static char* ws_base(void* workspace) {
 }
 
 static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
-                           size_t workspace_bytes, float* flat, bool with_tsq, void* stream) {
+                           size_t workspace_bytes, float* flat, bool with_tsq, const tlsan_next_t* next, void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
@@ -209,13 +227,29 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   tlsan_profile_mark(-1, st);
   SideStream* side = use_mma() ? side_stream() : nullptr;
   cudaEvent_t sorted = nullptr;
-  if (side) {
+  int long_ctas = 3;
+  const bool presorted = (dims->reserved & 2) != 0;
+  if (presorted) {
+    Presort* ps = presort_slot(ws, false);
+    REQUIRE(side && ps && ps->valid, TLSAN_E_UNSUPPORTED, "batch was not presorted into this workspace");
+    ps->valid = false;
+    sorted = ps->ev;
+    sorted_vals = tlsan_sorted_vals(w, ws);
+    tlsan_profile_mark(TLSAN_PHASE_SORT, st);
+    if (with_tsq) {
+      TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
+      TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+      if ((rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, side->st))) return rc;
+    }
+    g_prof_overlap = false;
+  } else if (side) {
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
     if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, side->st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
     sorted = side->join;
+    long_ctas = tlsan_overlap_ctas();
     // ||W||^2 of the tables needs only the (still unchanged) weights: off the critical path too
     if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, side->st))) return rc;
     g_prof_overlap = true;
@@ -227,11 +261,30 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   }
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
-    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, sorted, st);
+    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, sorted,
+                                    long_ctas, st);
   else if (fused_impl() == 1)
-    rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, st);
+    rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, long_ctas, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
   if (rc) return rc;
+  if (next && side) {
+    // sort of the next batch: behind the backward kernels of this step, beside its reduce / all-reduce / update
+    REQUIRE(next->dims && next->batch && next->workspace, TLSAN_E_NULL, "next has a NULL field");
+    if ((rc = check_dims(next->dims))) return rc;
+    if ((rc = check_batch(next->batch, true, 1))) return rc;
+    const TlsanWs wn = tlsan_ws_layout(*next->dims);
+    REQUIRE(next->workspace_bytes >= wn.total + 256, TLSAN_E_WORKSPACE, "next workspace too small");
+    char* wsn = ws_base(next->workspace);
+    REQUIRE(wsn != ws, TLSAN_E_UNSUPPORTED, "the next batch needs its own workspace");
+    Presort* ps = presort_slot(wsn, true);
+    REQUIRE(ps != nullptr, TLSAN_E_UNSUPPORTED, "too many presorted workspaces in flight");
+    const int32_t* unused = nullptr;
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+    TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
+    if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, side->st2))) return rc;
+    TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev, side->st2));
+    ps->valid = true;
+  }
   if (side) {
     // the fixed-order sum of the per-CTA partials and the segmented row reduce are independent: side by side
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
@@ -270,11 +323,29 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
                      size_t workspace_bytes, float* flat, void* stream) {
   // the table norms go into the workspace here (beside the forward kernels): tlsan_apply_flat, which must
   // follow on the same workspace with the weights unchanged, reads them instead of recomputing
-  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, dims && !(dims->reserved & 1), stream);
+  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, dims && !(dims->reserved & 1), nullptr, stream);
 }
 
 int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
                      float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
+}
+
+int tlsan_step_grads_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                               const tlsan_next_t* next, void* workspace, size_t workspace_bytes, float* flat,
+                               void* stream) {
+  return step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, dims && !(dims->reserved & 1), next, stream);
+}
+
+int tlsan_train_step_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
+                               const tlsan_next_t* next, float lr, float reg, float clip_norm, void* workspace,
+                               size_t workspace_bytes, float* stats, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(workspace != nullptr, TLSAN_E_NULL, "workspace is NULL");
+  const TlsanWs w = tlsan_ws_layout(*dims);
+  float* flat = reinterpret_cast<float*>(ws_base(workspace) + w.flat);
+  if ((rc = step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, true, next, stream))) return rc;
   return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
 }
 
@@ -286,7 +357,7 @@ int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
   const TlsanWs w = tlsan_ws_layout(*dims);
   float* flat = reinterpret_cast<float*>(ws_base(workspace) + w.flat);
   // one fused step: the table norms are computed beside the forward kernels (weights change only in apply)
-  if ((rc = step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, true, stream))) return rc;
+  if ((rc = step_grads_impl(dims, p, b, workspace, workspace_bytes, flat, true, nullptr, stream))) return rc;
   return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
 }
 

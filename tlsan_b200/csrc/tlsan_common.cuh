@@ -111,16 +111,18 @@ int tlsan_launch_bucket(const int32_t* dd, const float* lut, float* out, int32_t
                         cudaStream_t st);
 int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
                       char* ws, const int32_t** sorted_vals, cudaStream_t st);
+const int32_t* tlsan_sorted_vals(const TlsanWs& w, char* ws);
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st);
 int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                            float* logits, float* ut, cudaStream_t st);
 int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                              const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaEvent_t sorted,
-                             cudaStream_t st);
+                             int long_ctas, cudaStream_t st);
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
-                               cudaEvent_t sorted, cudaStream_t st);
+                               cudaEvent_t sorted, int long_ctas, cudaStream_t st);
+int tlsan_overlap_ctas();
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                           float* logits, float* ut, float* scratch, cudaStream_t st);
 int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, int grid_c, float* dgrad,

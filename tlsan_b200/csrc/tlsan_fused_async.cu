@@ -397,7 +397,7 @@ int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
 // kernel (its per-sample dependent chain is otherwise exposed: 130 -> 113 us).
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
-                               cudaEvent_t sorted, cudaStream_t st) {
+                               cudaEvent_t sorted, int long_ctas, cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
@@ -405,7 +405,7 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   int rc;
-  if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st) : launch_async<1>(a, nullptr, st))) return rc;
+  if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   a.part = reinterpret_cast<float*>(ws + w.part_a);

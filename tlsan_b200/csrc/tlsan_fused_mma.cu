@@ -667,7 +667,7 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
 
 int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                              const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaEvent_t sorted,
-                             cudaStream_t st) {
+                             int long_ctas, cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
@@ -676,7 +676,7 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   // forward: long FWA -> dense GEMM -> short FWA + loss + backward of logit / short FWA
   int rc;
-  if ((rc = tlsan_launch_long_fwd_mma(a, sorted ? tlsan_overlap_ctas() : 3, st))) return rc;
+  if ((rc = tlsan_launch_long_fwd_mma(a, long_ctas, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   const int g = mma_grid(d.B, 2);

@@ -163,6 +163,14 @@ __global__ void k_seg_bounds(const int* __restrict__ keys, const int* __restrict
   for (int r = prev + 1; r <= cur; ++r) seg_off[r] = i;
 }
 
+// which ping-pong buffer holds the sorted occurrence ids after the last pass (pass k writes b, a, b, ...)
+const int32_t* tlsan_sorted_vals(const TlsanWs& w, char* ws) {
+  int bits = 1;
+  while ((1ll << bits) < (long long)w.NR) ++bits;
+  const int passes = (bits + 7) / 8;
+  return reinterpret_cast<const int32_t*>(ws + ((passes & 1) ? w.vals_b : w.vals_a));
+}
+
 int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
                       char* ws, const int32_t** sorted_vals, cudaStream_t st) {
   int* keys_a = reinterpret_cast<int*>(ws + w.keys_a);

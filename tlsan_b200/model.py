@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OFF, STAT, Batch, Dims, Params, check
+from ._lib import OFF, STAT, Batch, Dims, Next, Params, check
 
 _L = "all/long_term/num_blocks0_0/long_term_layer/feature_wise_attention1/"
 _S = "all/short_term/num_blocks1_0/short_term_layer/feature_wise_attention2/"
@@ -202,7 +202,9 @@ class Model(object):
                               cate_items=self.cate_items.data_ptr())
 
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
-        self._ws = None
+        self._ws = [None, None]
+        self._ws_slot = 0
+        self._presorted = None      # (batch buffer address, workspace slot) sorted ahead by the previous step
         self._score_ws = None
         self._rank_ws = None
         self._flat = None
@@ -222,19 +224,22 @@ class Model(object):
         self.eval_writer = None
 
     # ------------------------------------------------------------------ plumbing
-    def _dims(self, B, S, B_global=None):
+    def _dims(self, B, S, B_global=None, flags=0):
         return Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC,
-                    B_global=int(B_global if B_global is not None else B), reserved=0)
+                    B_global=int(B_global if B_global is not None else B), reserved=flags)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _workspace(self, dims):
+    def _workspace(self, dims, slot=0):
+        """Step workspace; two slots so that a pipelined step can presort the next batch into the other one."""
         need = C.c_size_t()
         check(self._lib.tlsan_workspace_bytes(C.byref(dims), C.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
-        return self._ws
+        if self._ws[slot] is None or self._ws[slot].numel() < need.value:
+            self._ws[slot] = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+            if self._presorted is not None and self._presorted[4] == slot:
+                self._presorted = None
+        return self._ws[slot]
 
     def stage_batch(self, batch, is_test=False):
         """Pack the input.py 9-tuple into pinned memory (tlsan_pack_batch_host: multi-threaded
@@ -257,27 +262,47 @@ class Model(object):
         return DeviceBatch(dev, B, self.L, S, offs, is_test)
 
     # ------------------------------------------------------------------ training
-    def train_staged(self, db, lr, global_batch=None):
+    def train_staged(self, db, lr, global_batch=None, next_db=None):
         """One optimiser step on a device-resident batch; returns the device stats tensor
-        (index with ``tlsan_b200._lib.STAT``) without synchronising."""
+        (index with ``tlsan_b200._lib.STAT``) without synchronising.  ``next_db`` (optional) is the batch the
+        NEXT call will train on: its occurrence sort is then enqueued behind this step's backward kernels
+        (tlsan_*_pipelined), off the next step's critical path.  Results do not depend on it."""
         Bg = global_batch if global_batch is not None else db.B * self.world
-        dims = self._dims(db.B, db.S, Bg)
-        ws = self._workspace(dims)
+        slot = self._ws_slot
+        flags = 0
+        if self._presorted is not None:
+            if self._presorted == (db.buf.data_ptr(), db.B, db.S, Bg, self._presorted[4]):
+                slot, flags = self._presorted[4], 2
+            self._presorted = None
+        dims = self._dims(db.B, db.S, Bg, flags)
+        ws = self._workspace(dims, slot)
         st = self._stream()
+        nxt = None
+        if next_db is not None:
+            nBg = next_db.B * self.world if global_batch is None else global_batch
+            ndims = self._dims(next_db.B, next_db.S, nBg)
+            nws = self._workspace(ndims, 1 - slot)
+            nxt = Next(dims=C.pointer(ndims), batch=C.pointer(next_db.c), workspace=nws.data_ptr(),
+                       workspace_bytes=nws.numel())
+        nref = C.byref(nxt) if nxt is not None else None
         if self.world == 1:
-            check(self._lib.tlsan_train_step(C.byref(dims), C.byref(self._params), C.byref(db.c), lr, self.reg,
-                                             self.clip, ws.data_ptr(), ws.numel(), self._stats.data_ptr(), st))
+            check(self._lib.tlsan_train_step_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref, lr,
+                                                       self.reg, self.clip, ws.data_ptr(), ws.numel(),
+                                                       self._stats.data_ptr(), st))
         else:
             n = C.c_int64()
             check(self._lib.tlsan_flat_count(C.byref(dims), C.byref(n)))
             if self._flat is None or self._flat.numel() != n.value:
                 self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
-            check(self._lib.tlsan_step_grads(C.byref(dims), C.byref(self._params), C.byref(db.c), ws.data_ptr(),
-                                             ws.numel(), self._flat.data_ptr(), st))
+            check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
+                                                       ws.data_ptr(), ws.numel(), self._flat.data_ptr(), st))
             torch.distributed.all_reduce(self._flat, group=self.pg)
             check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
                                              self.reg, self.clip, ws.data_ptr(), ws.numel(),
                                              self._stats.data_ptr(), st))
+        if next_db is not None:
+            self._presorted = (next_db.buf.data_ptr(), next_db.B, next_db.S, nBg, 1 - slot)
+            self._ws_slot = 1 - slot
         self.global_step.value += 1
         return self._stats
 
