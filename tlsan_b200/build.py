@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("TLSAN_NVCC_EXTRA", "").split()          # e.g. -DTLSAN_DEBUG_DWD for kernel debugging
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))

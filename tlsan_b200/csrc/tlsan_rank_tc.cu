@@ -19,7 +19,7 @@
 //   * the label's own score comes from the SAME instruction sequence (a first tile whose "items" are the 128
 //     labels; user m reads the diagonal), so s_bj == s_b,lab holds exactly at j = lab and ties break by index
 //     like tf.nn.top_k.
-#include "tlsan_common.cuh"
+#include "tlsan_tc.cuh"
 
 #define RK_M 128
 #define RK_N 128
@@ -31,73 +31,6 @@
 #define RK_THREADS 192
 #define RK_TMEM_COLS 256
 #define RK_SMEM (3 * RK_TILE + 256)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// shared-memory matrix descriptor: K-major, no swizzle; core matrix = 8 rows x 16 B stored contiguously,
-// next 8-row group +128 B (SBO), next k-chunk +RK_N*16 B (LBO); version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((RK_N * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-         (1ull << 46);
-}
-// instruction descriptor, kind::tf32: D fp32, A/B tf32 K-major, M = 128, N = 128
-#define RK_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RK_N >> 3) << 17) | ((uint32_t)(RK_M >> 4) << 24))
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(RK_IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // k-chunk c (4 floats) of the augmented catalogue row of item j: [item_emb[j] | cate_emb[icl[j]] | item_b[j], 0...]
 __device__ __forceinline__ float4 catalogue_chunk(int NI, const float* __restrict__ emb, const float* __restrict__ item_b,
@@ -203,7 +136,8 @@ __global__ void __launch_bounds__(RK_THREADS, 1) k_label_rank_tc(int B, int NI, 
       const uint32_t pa = term == 1 ? a_lo : a_hi, pb = term == 2 ? b_lo : b_hi;
 #pragma unroll
       for (int ks = 0; ks < RK_K / 8; ++ks)
-        umma_tf32(d_tmem, umma_desc(pa + ks * RK_KSTEP_BYTES), umma_desc(pb + ks * RK_KSTEP_BYTES),
+        umma_tf32(d_tmem, umma_desc(pa + ks * RK_KSTEP_BYTES, RK_N * 16, 128),
+                  umma_desc(pb + ks * RK_KSTEP_BYTES, RK_N * 16, 128), umma_idesc_tf32(RK_M, RK_N, 0, 0),
                   (term | ks) ? 1u : 0u);
     }
   };
