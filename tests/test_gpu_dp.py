@@ -1,5 +1,6 @@
-"""Data-parallel train step on 2 GPUs (NCCL): every rank trains on its contiguous row block,
-all-reduces the flat gradient buffer, applies the update; the weights must equal (up to fp32
+"""Data-parallel train step on 2 GPUs: every rank trains on its contiguous row block, the gradients are summed
+and the update applied either by the fused NVLink peer-memory exchange (tlsan_dp_exchange, "p2p") or by NCCL
+all-reduce + tlsan_apply_flat ("nccl"); the weights must equal (up to fp32
 reduction order) those of one GPU training on the whole batch, and be identical across ranks."""
 import os
 import socket
@@ -11,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, mode, q):
     import torch.distributed as dist
     from oracle import tlsan_oracle as O
     from tests.util import load_digital_music, model_from_params
@@ -23,7 +24,7 @@ def _worker(rank, world, port, q):
     dm = load_digital_music()
     cfg = O.default_config(*dm.counts)
     params = O.randomize_params(O.init_params(cfg, seed=1234), seed=7)
-    model = model_from_params(params, dm.icl, cfg, process_group=dist.group.WORLD)
+    model = model_from_params(params, dm.icl, cfg, process_group=dist.group.WORLD, dp_mode=mode)
     losses = []
     for step in range(3):
         batch = O.collate_train(dm.train_set[step * 301:(step + 1) * 301], 10)      # odd size: uneven shards
@@ -50,14 +51,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_data_parallel_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_data_parallel_matches_single_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
     out = dict()

@@ -63,6 +63,13 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p]),
     "tlsan_apply_flat": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_float, C.c_float, C.c_float,
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "tlsan_dp_arena_bytes": (C.c_int, [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_size_t)]),
+    "tlsan_dp_arena_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "tlsan_dp_arena_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "tlsan_dp_arena_release": (C.c_int, [C.c_void_p, C.c_int32]),
+    "tlsan_dp_exchange": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
+                                    C.c_void_p, C.c_void_p]),
     "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "tlsan_rank_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),

@@ -349,6 +349,65 @@ int tlsan_train_step_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p
   return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
 }
 
+int tlsan_dp_arena_bytes(const tlsan_dims_t* dims, int32_t world, size_t* bytes) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  REQUIRE(bytes != nullptr, TLSAN_E_NULL, "bytes is NULL");
+  REQUIRE(world >= 1 && world <= 16, TLSAN_E_DIMS, "world must be in [1,16] (got %d)", world);
+  *bytes = tlsan_dp_arena_bytes_impl(*dims, world);
+  return TLSAN_OK;
+}
+
+int tlsan_dp_arena_create(size_t bytes, void** ptr, char* handle64) {
+  REQUIRE(ptr && handle64 && bytes > 0, TLSAN_E_NULL, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  TLSAN_CHECK_CUDA(cudaMalloc(ptr, bytes));
+  TLSAN_CHECK_CUDA(cudaMemset(*ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  TLSAN_CHECK_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return TLSAN_OK;
+}
+
+int tlsan_dp_arena_open(const char* handle64, void** ptr) {
+  REQUIRE(ptr && handle64, TLSAN_E_NULL, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  TLSAN_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return TLSAN_OK;
+}
+
+int tlsan_dp_arena_release(void* ptr, int32_t owned) {
+  if (!ptr) return TLSAN_OK;
+  if (owned) TLSAN_CHECK_CUDA(cudaFree(ptr));
+  else TLSAN_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return TLSAN_OK;
+}
+
+int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, void* const* arenas,
+                      int32_t rank, int32_t world, int32_t epoch, float lr, float reg, float clip_norm,
+                      void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims))) return rc;
+  if ((rc = check_params(p, true))) return rc;
+  REQUIRE(flat && arenas && workspace && stats, TLSAN_E_NULL, "NULL argument");
+  REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, TLSAN_E_DIMS, "bad rank / world (%d / %d)", rank, world);
+  REQUIRE(epoch >= 1 && clip_norm > 0.f, TLSAN_E_DIMS, "epoch must be >= 1 and clip_norm > 0");
+  for (int i = 0; i < world; ++i) REQUIRE(arenas[i] != nullptr, TLSAN_E_NULL, "arena %d is NULL", i);
+  // the weights must be ONE buffer in the arena layout: emb | usert | item_b | dense
+  const long long NR = (long long)dims->NI + dims->NC + dims->NU;
+  const long long off_usert = NR * 32, off_itemb = off_usert + ((long long)dims->NU * dims->L + 3) / 4 * 4,
+                  off_dense = off_itemb + ((long long)dims->NI + 3) / 4 * 4;
+  REQUIRE(p->usert == p->emb + off_usert && p->item_b == p->emb + off_itemb && p->dense == p->emb + off_dense,
+          TLSAN_E_UNSUPPORTED, "tlsan_dp_exchange needs emb | usert | item_b | dense in one buffer (see header)");
+  const TlsanWs w = tlsan_ws_layout(*dims);
+  REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small");
+  rc = tlsan_launch_dp_exchange(*dims, *p, w, ws_base(workspace), flat, reinterpret_cast<float* const*>(arenas), rank,
+                                world, epoch, lr, reg, clip_norm, stats, (cudaStream_t)stream);
+  tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
+  return rc;
+}
+
 int tlsan_train_step(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, float lr, float reg,
                      float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
   int rc;

@@ -143,7 +143,8 @@ class Model(object):
         if config.get("optimizer", "sgd") != "sgd":
             raise ValueError("only the reference default optimizer 'sgd' is implemented (train.py:40)")
 
-    def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True):
+    def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True,
+                 dp_mode=None):
         self.config = config
         self._check_config(config)
         self._lib = _lib.lib()                                  # raises if the CUDA library is missing
@@ -159,6 +160,14 @@ class Model(object):
         self.validate = validate
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        # data-parallel exchange: "p2p" = fused reduce-scatter / update / all-gather over NVLink peer memory
+        # (tlsan_dp_exchange), "nccl" = all_reduce + tlsan_apply_flat
+        self.dp_mode = dp_mode or os.environ.get("TLSAN_DP_MODE", "p2p")
+        if self.dp_mode not in ("p2p", "nccl"):
+            raise ValueError("dp_mode must be 'p2p' or 'nccl'")
+        self._arenas = None
+        self._dp_epoch = 0
 
         icl = np.ascontiguousarray(np.asarray(item_cate_list, dtype=np.int32))
         if icl.shape != (self.NI,) or icl.min() < 0 or icl.max() >= self.NC:
@@ -183,19 +192,29 @@ class Model(object):
         emb[:self.NI] = glorot(self.NI, 32)
         emb[self.NI + self.NC:] = glorot(self.NU, 32)
         emb[self.NI:self.NI + self.NC] = glorot(self.NC, 32)
-        self.emb = emb.to(dev)
+        # all trainable state in ONE device buffer, emb | usert | item_b | dense (each padded to 16 B): the layout
+        # the NVLink data-parallel exchange sums and updates slice by slice (tlsan_dp_exchange)
+        up4 = lambda n: (n + 3) // 4 * 4
+        o_usert = NR * 32
+        o_itemb = o_usert + up4(self.NU * self.L)
+        o_dense = o_itemb + up4(self.NI)
+        self._wflat = torch.zeros(o_dense + _lib.DENSE_PAD, device=dev)
+        self.emb = self._wflat[:o_usert].view(NR, 32)
+        self.emb.copy_(emb)
         self.item_emb = self.emb[:self.NI]
         self.cate_emb = self.emb[self.NI:self.NI + self.NC]
         self.user_emb = self.emb[self.NI + self.NC:]
-        self.item_b = torch.zeros(self.NI, device=dev)
-        self.usert_emb = torch.full((self.NU, self.L), -1.0, device=dev)
+        self.item_b = self._wflat[o_itemb:o_itemb + self.NI]
+        self.usert_emb = self._wflat[o_usert:o_usert + self.NU * self.L].view(self.NU, self.L)
+        self.usert_emb.fill_(-1.0)
         dense = torch.zeros(_lib.DENSE_PAD)
         for name, (off, shape) in DENSE_LAYOUT.items():
             if name == "gamma_parameter":
                 dense[off] = 1.0
             elif len(shape) == 2:
                 dense[off:off + shape[0] * shape[1]] = glorot(*shape).reshape(-1)
-        self.dense = dense.to(dev)
+        self.dense = self._wflat[o_dense:]
+        self.dense.copy_(dense)
         self._params = Params(emb=self.emb.data_ptr(), usert=self.usert_emb.data_ptr(),
                               item_b=self.item_b.data_ptr(), dense=self.dense.data_ptr(),
                               icl=self.icl.data_ptr(), cate_off=self.cate_off.data_ptr(),
@@ -296,15 +315,45 @@ class Model(object):
                 self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
             check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
                                                        ws.data_ptr(), ws.numel(), self._flat.data_ptr(), st))
-            torch.distributed.all_reduce(self._flat, group=self.pg)
-            check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
-                                             self.reg, self.clip, ws.data_ptr(), ws.numel(),
-                                             self._stats.data_ptr(), st))
+            if self.dp_mode == "p2p" and self.world <= 16:
+                arenas = self._dp_arenas()
+                self._dp_epoch += 1
+                check(self._lib.tlsan_dp_exchange(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), arenas,
+                                                  self.rank, self.world, self._dp_epoch, lr, self.reg, self.clip,
+                                                  ws.data_ptr(), ws.numel(), self._stats.data_ptr(), st))
+            else:
+                torch.distributed.all_reduce(self._flat, group=self.pg)
+                check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
+                                                 self.reg, self.clip, ws.data_ptr(), ws.numel(),
+                                                 self._stats.data_ptr(), st))
         if next_db is not None:
             self._presorted = (next_db.buf.data_ptr(), next_db.B, next_db.S, nBg, 1 - slot)
             self._ws_slot = 1 - slot
         self.global_step.value += 1
         return self._stats
+
+    def _dp_arenas(self):
+        """IPC-shared exchange arenas of all ranks (created once): every rank cudaMallocs one, the 64-byte IPC
+        handles travel through torch.distributed, peers map them (NVLink peer memory)."""
+        if self._arenas is None:
+            dims = self._dims(1, 1)
+            need = C.c_size_t()
+            check(self._lib.tlsan_dp_arena_bytes(C.byref(dims), self.world, C.byref(need)))
+            mine, handle = C.c_void_p(), C.create_string_buffer(64)
+            check(self._lib.tlsan_dp_arena_create(need.value, C.byref(mine), handle))
+            handles = [None] * self.world
+            torch.distributed.all_gather_object(handles, bytes(handle.raw), group=self.pg)
+            ptrs = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs[r] = mine.value
+                else:
+                    peer = C.c_void_p()
+                    check(self._lib.tlsan_dp_arena_open(h, C.byref(peer)))
+                    ptrs[r] = peer.value
+            torch.distributed.barrier(group=self.pg)
+            self._arenas = ptrs
+        return self._arenas
 
     def train(self, sess, batch, lr, add_summary=False):
         """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op]."""
