@@ -159,23 +159,23 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
                      float* stats, void* stream);
 
 /* Data-parallel exchange over NVLink peer memory, in place of NCCL all-reduce + tlsan_apply_flat: a
- * fused reduce-scatter + optimiser step + all-gather.  Every rank packs the gradients of tlsan_step_grads in the
- * LAYOUT OF THE WEIGHTS into an arena that its peers map through CUDA IPC; rank r sums slice r of all arenas out of
- * peer memory (fixed rank order: deterministic, identical on every rank), applies L2 + clip + SGD to that slice,
- * publishes it, and every rank pulls the other slices; ranks meet at two release / acquire flags in the arenas.
- * The weights must be ONE device buffer: emb [(NI+NC+NU)*32] | usert [NU*L, padded to 4] | item_b [NI, padded to 4]
- * | dense [TLSAN_DENSE_PAD], with params->usert / item_b / dense pointing into it.
+ * fused reduce-scatter + optimiser step + all-gather.  Every rank owns an ARENA that its peers map through CUDA
+ * IPC and passes it to tlsan_step_grads as the `flat` gradient buffer; rank r then sums slice r of the weight index
+ * space out of all arenas (peer memory, fixed rank order: deterministic, identical on every rank), applies
+ * L2 + clip + SGD to that slice, publishes it, and every rank pulls the other slices; ranks meet at two
+ * release / acquire flags in the arenas.  The tables must be ONE device buffer: emb [(NI+NC+NU)*32] |
+ * usert [NU*L, padded to 4] | item_b [NI, padded to 4], with params->usert / item_b pointing into it.
  *   tlsan_dp_arena_bytes / _create / _open / _release : arena size for (dims, world); cudaMalloc + IPC handle
  *       (64 bytes, to be exchanged by the host, e.g. torch.distributed.all_gather_object); map a peer's arena.
- *   tlsan_dp_exchange : arenas[world] = the mapped arenas in rank order (arenas[rank] = the own one); epoch = 1, 2, ...
- *       (one more every call, the same on every rank); must follow tlsan_step_grads on the same workspace. */
+ *   tlsan_dp_exchange : arenas[world] = the mapped arenas in rank order; arenas[rank] = the own one = the buffer
+ *       tlsan_step_grads just wrote; epoch = 1, 2, ... (one more every call, the same on every rank). */
 int tlsan_dp_arena_bytes(const tlsan_dims_t* dims, int32_t world, size_t* bytes);
 int tlsan_dp_arena_create(size_t bytes, void** ptr, char* handle64);
 int tlsan_dp_arena_open(const char* handle64, void** ptr);
 int tlsan_dp_arena_release(void* ptr, int32_t owned);
-int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, void* const* arenas,
-                      int32_t rank, int32_t world, int32_t epoch, float lr, float reg, float clip_norm,
-                      void* workspace, size_t workspace_bytes, float* stats, void* stream);
+int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, void* const* arenas, int32_t rank,
+                      int32_t world, int32_t epoch, float lr, float reg, float clip_norm, void* workspace,
+                      size_t workspace_bytes, float* stats, void* stream);
 
 /* Pipelined variants: `next` (optional) names the batch of the FOLLOWING step and that step's own workspace.  Its
  * occurrence sort is enqueued behind the backward kernels of this step, where it runs beside the reduce, the

@@ -67,7 +67,7 @@ _SIGS = {
     "tlsan_dp_arena_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "tlsan_dp_arena_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "tlsan_dp_arena_release": (C.c_int, [C.c_void_p, C.c_int32]),
-    "tlsan_dp_exchange": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
+    "tlsan_dp_exchange": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.POINTER(C.c_void_p), C.c_int32,
                                     C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
                                     C.c_void_p, C.c_void_p]),
     "tlsan_label_rank": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -384,26 +384,25 @@ int tlsan_dp_arena_release(void* ptr, int32_t owned) {
   return TLSAN_OK;
 }
 
-int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, void* const* arenas,
-                      int32_t rank, int32_t world, int32_t epoch, float lr, float reg, float clip_norm,
-                      void* workspace, size_t workspace_bytes, float* stats, void* stream) {
+int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, void* const* arenas, int32_t rank,
+                      int32_t world, int32_t epoch, float lr, float reg, float clip_norm, void* workspace,
+                      size_t workspace_bytes, float* stats, void* stream) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
-  REQUIRE(flat && arenas && workspace && stats, TLSAN_E_NULL, "NULL argument");
+  REQUIRE(arenas && workspace && stats, TLSAN_E_NULL, "NULL argument");
   REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, TLSAN_E_DIMS, "bad rank / world (%d / %d)", rank, world);
   REQUIRE(epoch >= 1 && clip_norm > 0.f, TLSAN_E_DIMS, "epoch must be >= 1 and clip_norm > 0");
   for (int i = 0; i < world; ++i) REQUIRE(arenas[i] != nullptr, TLSAN_E_NULL, "arena %d is NULL", i);
-  // the weights must be ONE buffer in the arena layout: emb | usert | item_b | dense
+  // the tables must be ONE buffer: emb | usert | item_b (each padded to 16 B)
   const long long NR = (long long)dims->NI + dims->NC + dims->NU;
-  const long long off_usert = NR * 32, off_itemb = off_usert + ((long long)dims->NU * dims->L + 3) / 4 * 4,
-                  off_dense = off_itemb + ((long long)dims->NI + 3) / 4 * 4;
-  REQUIRE(p->usert == p->emb + off_usert && p->item_b == p->emb + off_itemb && p->dense == p->emb + off_dense,
-          TLSAN_E_UNSUPPORTED, "tlsan_dp_exchange needs emb | usert | item_b | dense in one buffer (see header)");
+  const long long off_usert = NR * 32, off_itemb = off_usert + ((long long)dims->NU * dims->L + 3) / 4 * 4;
+  REQUIRE(p->usert == p->emb + off_usert && p->item_b == p->emb + off_itemb, TLSAN_E_UNSUPPORTED,
+          "tlsan_dp_exchange needs emb | usert | item_b in one buffer (see header)");
   const TlsanWs w = tlsan_ws_layout(*dims);
   REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small");
-  rc = tlsan_launch_dp_exchange(*dims, *p, w, ws_base(workspace), flat, reinterpret_cast<float* const*>(arenas), rank,
-                                world, epoch, lr, reg, clip_norm, stats, (cudaStream_t)stream);
+  rc = tlsan_launch_dp_exchange(*dims, *p, w, ws_base(workspace), reinterpret_cast<float* const*>(arenas), rank, world,
+                                epoch, lr, reg, clip_norm, stats, (cudaStream_t)stream);
   tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
   return rc;
 }

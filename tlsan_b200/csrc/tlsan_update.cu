@@ -386,30 +386,30 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
 }
 
 // ------------------------------------------------------------------ data-parallel exchange over NVLink peer memory
-// One fused reduce-scatter + optimiser step + all-gather in place of NCCL all-reduce + apply:
-//   every rank packs its local gradients in the LAYOUT OF THE WEIGHTS (`wflat` = emb | usert | item_b | dense)
-//   into an IPC-shared arena and raises flag 1; rank r then sums slice r of all ranks' arenas straight out of
-//   peer memory (fixed rank order: deterministic and identical everywhere), applies L2 + clip + SGD to that
-//   slice of its own weights, publishes the new values in its arena and raises flag 2; finally every rank
-//   pulls the other slices.  The 4 449 small parameters and the statistics are reduced redundantly by every
-//   rank (18 KB per peer), so the clip scale is known before the slices are touched.
-// arena = [Gw: n_w floats + 8 tail | wnew: chunk floats | 64 ints flags]
-struct DpLayout { long long off_usert, off_itemb, off_dense, n_tab, n_w, chunk; };
+// One fused reduce-scatter + optimiser step + all-gather in place of NCCL all-reduce + apply.
+// Every rank lets tlsan_step_grads write its flat gradient buffer INTO an IPC-shared arena; after folding the
+// category gradient into the (otherwise unused) item half of the category rows it raises flag 1.  Rank r then
+// sums, for slice r of the WEIGHT index space (emb | usert | item_b), the matching gradient words of all ranks
+// straight out of peer memory (fixed rank order: deterministic and identical everywhere), applies L2 + clip + SGD
+// to that slice of its own weights, publishes the new values in its arena and raises flag 2; finally every rank
+// pulls the other slices.  The 4 449 small parameters and the statistics are reduced redundantly by every rank
+// (18 KB per peer), so the clip scale is known before the slices are touched.
+// arena = [flat: flat_count floats | wnew: chunk floats | 64 ints: flag1, flag2, ..., err at [8], counters at [16..]]
+struct DpLayout { long long off_usert, off_itemb, n_tab, chunk, flat_count; };
 static DpLayout dp_layout(const tlsan_dims_t& d, int world) {
   DpLayout y;
   const long long NR = (long long)d.NI + d.NC + d.NU;
   y.off_usert = NR * 32;
   y.off_itemb = y.off_usert + ((long long)d.NU * d.L + 3) / 4 * 4;
-  y.off_dense = y.off_itemb + ((long long)d.NI + 3) / 4 * 4;
-  y.n_tab = y.off_dense;
-  y.n_w = y.off_dense + TLSAN_DENSE_PAD;
+  y.n_tab = y.off_itemb + ((long long)d.NI + 3) / 4 * 4;
   const long long q = (y.n_tab / 4 + world - 1) / world;        // float4 units per rank
   y.chunk = q * 4;
+  y.flat_count = (long long)tlsan_ws_layout(d).flat_count;
   return y;
 }
 size_t tlsan_dp_arena_bytes_impl(const tlsan_dims_t& d, int world) {
   const DpLayout y = dp_layout(d, world);
-  return (size_t)(y.n_w + 8 + y.chunk) * 4 + 256;
+  return (size_t)(y.flat_count + y.chunk) * 4 + 256;
 }
 
 __device__ __forceinline__ float4 ld_peer4(const float* p) {      // peer memory: never through the (incoherent) L1
@@ -427,46 +427,20 @@ __device__ __forceinline__ int ld_flag(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-
-struct DpPeers { float* arena[16]; };
-
-// local gradients -> weight layout (item / user / usert / item_b / dense + loss and norm partials); the category
-// rows are written by k_reduce_cate (tlsan_shard.cu) straight into Gw
-__global__ void __launch_bounds__(256) k_dp_pack(int NI, int NC, int NU, int L, int PU, DpLayout y,
-                                                 const float* __restrict__ g_i, const float* __restrict__ g_b,
-                                                 const float* __restrict__ g_u, const float* __restrict__ dgrad,
-                                                 float* __restrict__ Gw) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long v_item = (long long)NI * 8, v_user = (long long)NU * 8;
-  const long long n_ut = (long long)NU * L;
-  const long long total = v_item + v_user + n_ut + NI + TLSAN_DENSE_PAD + 8;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    if (e < v_item) {
-      reinterpret_cast<float4*>(Gw)[e] = *reinterpret_cast<const float4*>(g_i + (e >> 3) * 64 + (e & 7) * 4);
-    } else if (e < v_item + v_user) {
-      const long long x = e - v_item;
-      reinterpret_cast<float4*>(Gw + (size_t)(NI + NC) * 32)[x] =
-          *reinterpret_cast<const float4*>(g_u + (x >> 3) * PU + (x & 7) * 4);
-    } else if (e < v_item + v_user + n_ut) {
-      const long long x = e - v_item - v_user;
-      const long long u = x / L;
-      Gw[y.off_usert + x] = g_u[u * PU + 32 + (x - u * L)];
-    } else if (e < v_item + v_user + n_ut + NI) {
-      const long long x = e - v_item - v_user - n_ut;
-      Gw[y.off_itemb + x] = g_b[x];
-    } else {
-      const long long x = e - v_item - v_user - n_ut - NI;
-      if (x < TLSAN_DENSE_PAD) Gw[y.off_dense + x] = x < TLSAN_DENSE_COUNT ? dgrad[x] : 0.f;
-      else if (x == TLSAN_DENSE_PAD) Gw[y.n_w] = dgrad[TLSAN_PART_LOSS];
-      else if (x == TLSAN_DENSE_PAD + 1) Gw[y.n_w + 1] = dgrad[TLSAN_PART_SUMSQ];
+// the last CTA of a grid to get here publishes `epoch` in `flag` (release at system scope)
+__device__ __forceinline__ void dp_signal_when_grid_done(int* counter, int* flag, int epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(counter, 1) == (int)gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
     }
   }
 }
 
-__global__ void k_dp_signal(int* flag, int epoch) {
-  __threadfence_system();
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-}
+struct DpPeers { float* arena[16]; };
 
 // spin until every peer's flag `which` has reached `epoch` (bounded: a dead peer must not hang the GPU)
 __device__ __forceinline__ void dp_wait(const DpPeers& peers, long long flag_off, int which, int world, int epoch,
@@ -482,61 +456,11 @@ __device__ __forceinline__ void dp_wait(const DpPeers& peers, long long flag_off
   __syncthreads();
 }
 
-// dense gradients + loss / norm partials summed over ranks (fixed order) into the partial-row layout k_finalize2 reads
-__global__ void __launch_bounds__(1024) k_dp_dense_sum(DpPeers peers, DpLayout y, int world, int epoch,
-                                                       float* __restrict__ dtot, int* __restrict__ err) {
-  const long long flag_off = y.n_w + 8 + y.chunk;
-  dp_wait(peers, flag_off, 0, world, epoch, err);
-  for (int e = threadIdx.x; e < TLSAN_DENSE_PAD + 2; e += 1024) {
-    const long long src = e < TLSAN_DENSE_PAD ? y.off_dense + e : y.n_w + (e - TLSAN_DENSE_PAD);
-    float s = 0.f;
-    for (int p = 0; p < world; ++p) s += ld_peer1(peers.arena[p] + src);
-    const int dst = e < TLSAN_DENSE_PAD ? e : (e == TLSAN_DENSE_PAD ? TLSAN_PART_LOSS : TLSAN_PART_SUMSQ);
-    if (e < TLSAN_DENSE_COUNT || e >= TLSAN_DENSE_PAD) dtot[dst] = s;
-  }
-}
-
-// slice `rank` of the table part of wflat: sum over ranks, update, publish
-__global__ void __launch_bounds__(256) k_dp_apply_slice(DpPeers peers, DpLayout y, int rank, int world,
-                                                        float* __restrict__ wflat, float lr, float reg,
-                                                        const float* __restrict__ stats) {
-  const float scale = stats[TLSAN_STAT_SCALE];
-  const long long lo = (long long)rank * y.chunk, hi = min(lo + y.chunk, y.n_tab);
-  float* wnew = peers.arena[rank] + y.n_w + 8;
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += stride) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < world; ++p) {
-      const float4 v = ld_peer4(peers.arena[p] + e);
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
-    }
-    const float r = e < y.off_itemb ? reg : 0.f;               // item_b carries no L2 term (model.py:164-169)
-    float4 w = *reinterpret_cast<float4*>(wflat + e);
-    w.x -= lr * ((g.x + r * w.x) * scale); w.y -= lr * ((g.y + r * w.y) * scale);
-    w.z -= lr * ((g.z + r * w.z) * scale); w.w -= lr * ((g.w + r * w.w) * scale);
-    *reinterpret_cast<float4*>(wflat + e) = w;
-    *reinterpret_cast<float4*>(wnew + (e - lo)) = w;
-  }
-}
-
-// the other ranks' updated slices -> local weights
-__global__ void __launch_bounds__(256) k_dp_gather(DpPeers peers, DpLayout y, int rank, int world, int epoch,
-                                                   float* __restrict__ wflat, int* __restrict__ err) {
-  const long long flag_off = y.n_w + 8 + y.chunk;
-  dp_wait(peers, flag_off, 1, world, epoch, err);
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (int p = 0; p < world; ++p) {
-    if (p == rank) continue;
-    const long long lo = (long long)p * y.chunk, hi = min(lo + y.chunk, y.n_tab);
-    const float* src = peers.arena[p] + y.n_w + 8;
-    for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += stride)
-      *reinterpret_cast<float4*>(wflat + e) = ld_peer4(src + (e - lo));
-  }
-}
-
-__global__ void __launch_bounds__(256) k_reduce_cate_w(int NI, const float* __restrict__ g_i,
-                                                       const int* __restrict__ cate_off,
-                                                       const int* __restrict__ cate_items, float* __restrict__ out) {
+// category gradient of category k (item-row cate halves in CSR order + the direct u_cate row) -> item half of flat
+// row NI + k, i.e. where the weight-indexed exchange expects the gradient of emb row NI + k; then flag 1
+__global__ void __launch_bounds__(256) k_dp_reduce_cate(int NI, float* __restrict__ g_i, const int* __restrict__ cate_off,
+                                                        const int* __restrict__ cate_items, int* __restrict__ flags,
+                                                        int epoch) {
   __shared__ float sh[8][32];
   const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lo = cate_off[k], hi = cate_off[k + 1];
@@ -548,38 +472,125 @@ __global__ void __launch_bounds__(256) k_reduce_cate_w(int NI, const float* __re
     float g = g_i[(size_t)(NI + k) * 64 + 32 + lane];
 #pragma unroll
     for (int w = 0; w < 8; ++w) g += sh[w][lane];
-    out[(size_t)k * 32 + lane] = g;
+    g_i[(size_t)(NI + k) * 64 + lane] = g;
+  }
+  dp_signal_when_grid_done(flags + 16, flags + 0, epoch);
+}
+
+// dense gradients + loss / norm partials summed over ranks (fixed order) into the partial-row layout k_finalize2 reads
+__global__ void __launch_bounds__(1024) k_dp_dense_sum(DpPeers peers, DpLayout y, long long f_dgrad, int world, int epoch,
+                                                       float* __restrict__ dtot, int* __restrict__ err) {
+  dp_wait(peers, y.flat_count + y.chunk, 0, world, epoch, err);
+  for (int e = threadIdx.x; e < TLSAN_PART; e += 1024) {
+    if (e < TLSAN_DENSE_COUNT || e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ) {
+      float v[16];                       // every peer's word in flight together, then the fixed-order sum
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < world) v[p] = ld_peer1(peers.arena[p] + f_dgrad + e);
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < world) s += v[p];
+      dtot[e] = s;
+    }
   }
 }
 
+// gradient words (one float4 of the weight index space) of one rank, read from its flat buffer in peer memory
+__device__ __forceinline__ float4 dp_grad4(const float* __restrict__ flat, long long e, int NIC, int NU, int L, int PU,
+                                           long long f_gb, long long f_gu, const DpLayout& y) {
+  if (e < (long long)NIC * 32) return ld_peer4(flat + (e >> 5) * 64 + (e & 31));            // item and category rows
+  if (e < y.off_usert) {                                                                       // user rows
+    const long long x = e - (long long)NIC * 32;
+    return ld_peer4(flat + f_gu + (x >> 5) * PU + (x & 31));
+  }
+  if (e < y.off_itemb) {                                                                       // usert_emb [NU][L]
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long x = e - y.off_usert + i;
+      const long long u = x / L;
+      v[i] = u < NU ? ld_peer1(flat + f_gu + u * PU + 32 + (x - u * L)) : 0.f;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  }
+  return ld_peer4(flat + f_gb + (e - y.off_itemb));                                            // item_b
+}
+
+// slice `rank` of the table part of wflat: sum over ranks, update, publish; then flag 2
+__global__ void __launch_bounds__(256) k_dp_apply_slice(DpPeers peers, DpLayout y, int rank, int world, int NIC, int NU,
+                                                        int L, int PU, long long f_gb, long long f_gu,
+                                                        float* __restrict__ wflat, float lr, float reg,
+                                                        const float* __restrict__ stats, int epoch) {
+  const float scale = stats[TLSAN_STAT_SCALE];
+  const long long lo = (long long)rank * y.chunk, hi = min(lo + y.chunk, y.n_tab);
+  float* wnew = peers.arena[rank] + y.flat_count;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += stride) {
+    // all ranks' words in flight together (a peer read is ~1-2 us: never one after the other), then a fixed-order sum
+    float4 v[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+      if (p < world) v[p] = dp_grad4(peers.arena[p], e, NIC, NU, L, PU, f_gb, f_gu, y);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+      if (p < world) { g.x += v[p].x; g.y += v[p].y; g.z += v[p].z; g.w += v[p].w; }
+    const float r = e < y.off_itemb ? reg : 0.f;               // item_b carries no L2 term (model.py:164-169)
+    float4 w = *reinterpret_cast<float4*>(wflat + e);
+    w.x -= lr * ((g.x + r * w.x) * scale); w.y -= lr * ((g.y + r * w.y) * scale);
+    w.z -= lr * ((g.z + r * w.z) * scale); w.w -= lr * ((g.w + r * w.w) * scale);
+    *reinterpret_cast<float4*>(wflat + e) = w;
+    *reinterpret_cast<float4*>(wnew + (e - lo)) = w;
+  }
+  int* flags = reinterpret_cast<int*>(peers.arena[rank] + y.flat_count + y.chunk);
+  dp_signal_when_grid_done(flags + 17, flags + 1, epoch);
+}
+
+// the other ranks' updated slices -> local weights
+__global__ void __launch_bounds__(256) k_dp_gather(DpPeers peers, DpLayout y, int rank, int world, int epoch,
+                                                   float* __restrict__ wflat, int* __restrict__ err) {
+  dp_wait(peers, y.flat_count + y.chunk, 1, world, epoch, err);
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) continue;
+    const long long lo = (long long)p * y.chunk, hi = min(lo + y.chunk, y.n_tab);
+    const float* src = peers.arena[p] + y.flat_count;
+    for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e + i * stride < hi) v[i] = ld_peer4(src + (e + i * stride - lo));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e + i * stride < hi) *reinterpret_cast<float4*>(wflat + e + i * stride) = v[i];
+    }
+  }
+}
+
+// `arenas[rank]` must be the buffer tlsan_step_grads wrote its flat gradients to
 int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
-                             const float* flat, float* const* arenas, int rank, int world, int epoch, float lr,
-                             float reg, float clip, float* stats, cudaStream_t st) {
+                             float* const* arenas, int rank, int world, int epoch, float lr, float reg, float clip,
+                             float* stats, cudaStream_t st) {
   const DpLayout y = dp_layout(d, world);
   DpPeers peers;
   for (int i = 0; i < 16; ++i) peers.arena[i] = i < world ? arenas[i] : nullptr;
-  float* Gw = arenas[rank];
-  int* flags = reinterpret_cast<int*>(Gw + y.n_w + 8 + y.chunk);
+  float* flat = arenas[rank];
+  int* flags = reinterpret_cast<int*>(flat + y.flat_count + y.chunk);
   int* err = flags + 8;
-  const float* g_i = flat + w.f_gi; const float* g_b = flat + w.f_gb; const float* g_u = flat + w.f_gu;
-  const float* dgrad = flat + w.f_dgrad;
-  k_reduce_cate_w<<<d.NC, 256, 0, st>>>(d.NI, g_i, p.cate_off, p.cate_items, Gw + (size_t)d.NI * 32);
-  TLSAN_CHECK_LAUNCH("k_reduce_cate_w");
-  k_dp_pack<<<tlsan_num_sms() * 4, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, w.PU, y, g_i, g_b, g_u, dgrad, Gw);
-  TLSAN_CHECK_LAUNCH("k_dp_pack");
-  k_dp_signal<<<1, 1, 0, st>>>(flags + 0, epoch);
-  TLSAN_CHECK_LAUNCH("k_dp_signal");
+  k_dp_reduce_cate<<<d.NC, 256, 0, st>>>(d.NI, flat + w.f_gi, p.cate_off, p.cate_items, flags, epoch);
+  TLSAN_CHECK_LAUNCH("k_dp_reduce_cate");
   float* dtot = reinterpret_cast<float*>(ws + w.part_a);          // the per-CTA partials are consumed by now
-  k_dp_dense_sum<<<1, 1024, 0, st>>>(peers, y, world, epoch, dtot, err);
+  k_dp_dense_sum<<<1, 1024, 0, st>>>(peers, y, (long long)w.f_dgrad, world, epoch, dtot, err);
   TLSAN_CHECK_LAUNCH("k_dp_dense_sum");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
   k_finalize2<<<1, 1024, 0, st>>>(dtot, reinterpret_cast<float*>(ws + w.tsq), tsq_grid(), nullptr, 0, invB, lr, reg,
                                   clip, p.dense, stats);
   TLSAN_CHECK_LAUNCH("k_finalize2");
-  k_dp_apply_slice<<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, p.emb, lr, reg, stats);
+  k_dp_apply_slice<<<tlsan_num_sms() * 4, 256, 0, st>>>(peers, y, rank, world, d.NI + d.NC, d.NU, d.L, w.PU,
+                                                        (long long)w.f_gb, (long long)w.f_gu, p.emb, lr, reg, stats,
+                                                        epoch);
   TLSAN_CHECK_LAUNCH("k_dp_apply_slice");
-  k_dp_signal<<<1, 1, 0, st>>>(flags + 1, epoch);
-  TLSAN_CHECK_LAUNCH("k_dp_signal");
   k_dp_gather<<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, epoch, p.emb, err);
   TLSAN_CHECK_LAUNCH("k_dp_gather");
   return TLSAN_OK;

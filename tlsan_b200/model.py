@@ -161,9 +161,10 @@ class Model(object):
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
-        # data-parallel exchange: "p2p" = fused reduce-scatter / update / all-gather over NVLink peer memory
-        # (tlsan_dp_exchange), "nccl" = all_reduce + tlsan_apply_flat
-        self.dp_mode = dp_mode or os.environ.get("TLSAN_DP_MODE", "p2p")
+        # data-parallel exchange: "nccl" = all_reduce (NVLS in-switch reduction on NVSwitch) + tlsan_apply_flat
+        # [default: measured faster at 2 and 8 GPUs]; "p2p" = fused reduce-scatter / update / all-gather over
+        # NVLink peer memory (tlsan_dp_exchange)
+        self.dp_mode = dp_mode or os.environ.get("TLSAN_DP_MODE", "nccl")
         if self.dp_mode not in ("p2p", "nccl"):
             raise ValueError("dp_mode must be 'p2p' or 'nccl'")
         self._arenas = None
@@ -309,19 +310,21 @@ class Model(object):
                                                        self.reg, self.clip, ws.data_ptr(), ws.numel(),
                                                        self._stats.data_ptr(), st))
         else:
-            n = C.c_int64()
-            check(self._lib.tlsan_flat_count(C.byref(dims), C.byref(n)))
-            if self._flat is None or self._flat.numel() != n.value:
-                self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
-            check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
-                                                       ws.data_ptr(), ws.numel(), self._flat.data_ptr(), st))
             if self.dp_mode == "p2p" and self.world <= 16:
-                arenas = self._dp_arenas()
+                arenas = self._dp_arenas()                     # this rank's arena doubles as the flat gradient buffer
+                check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
+                                                           ws.data_ptr(), ws.numel(), arenas[self.rank], st))
                 self._dp_epoch += 1
-                check(self._lib.tlsan_dp_exchange(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), arenas,
-                                                  self.rank, self.world, self._dp_epoch, lr, self.reg, self.clip,
-                                                  ws.data_ptr(), ws.numel(), self._stats.data_ptr(), st))
+                check(self._lib.tlsan_dp_exchange(C.byref(dims), C.byref(self._params), arenas, self.rank, self.world,
+                                                  self._dp_epoch, lr, self.reg, self.clip, ws.data_ptr(), ws.numel(),
+                                                  self._stats.data_ptr(), st))
             else:
+                n = C.c_int64()
+                check(self._lib.tlsan_flat_count(C.byref(dims), C.byref(n)))
+                if self._flat is None or self._flat.numel() != n.value:
+                    self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
+                check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
+                                                           ws.data_ptr(), ws.numel(), self._flat.data_ptr(), st))
                 torch.distributed.all_reduce(self._flat, group=self.pg)
                 check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
                                                  self.reg, self.clip, ws.data_ptr(), ws.numel(),
