@@ -216,9 +216,13 @@ int tlsan_pack_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int6
                           const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* out,
                           int64_t out_words, int32_t validate, int32_t nthreads);
 
-/* tlsan_pack_batch_host + the host->device copy of the feed: packs into `pinned` (page-locked host memory) in
- * three phases and issues cudaMemcpyAsync(dev + off, pinned + off) on `stream` as each phase completes, so the
- * copy of one phase overlaps the packing of the next.  `pinned` may be reused once `stream` has passed the copies. */
+/* The feed of Model.train / eval_auc (model.py:210-222,239-261) end to end: pack into `pinned` (page-locked host
+ * memory) with a persistent thread pool, copy to `dev` on `stream` phase by phase while the rest is still being
+ * packed, and leave the packed batch layout of tlsan_pack_batch_host at the front of `dev`.  The session matrix
+ * hist_i_new [B][S] is almost all padding, so it travels ragged (offsets + valid items, in a tail region behind the
+ * packed layout) and k_expand_sessions rebuilds the zero-padded matrix in HBM.  `pinned` and `dev` must hold
+ * tlsan_stage_words(dims) int32 words; `pinned` may be reused once `stream` has passed the copies. */
+int tlsan_stage_words(const tlsan_dims_t* dims, int64_t* words);
 int tlsan_stage_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int64_t* i, const int64_t* i2,
                            const float* y, const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t,
                            const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* pinned, int32_t* dev,

@@ -245,6 +245,12 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   } else if (side) {
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+    if (Presort* stale = presort_slot(ws, false)) {
+      // a presort announced for this workspace was not consumed (the caller trained on another batch): its
+      // kernels may still be writing the sort buffers we are about to reuse
+      if (stale->valid) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev, 0));
+      stale->valid = false;
+    }
     if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, side->st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));

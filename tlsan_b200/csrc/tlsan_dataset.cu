@@ -63,3 +63,23 @@ extern "C" int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int3
   TLSAN_CHECK_LAUNCH("k_collate");
   return TLSAN_OK;
 }
+
+// hist_i_new [B][S] from its ragged transfer form (tlsan_stage_batch_host): row b holds items[off[b] .. off[b]+sl_new[b])
+// then zeros -- exactly the zero padding of DataInput.__next__ (TLSAN/input.py:50-51)
+__global__ void k_expand_sessions(const int* __restrict__ sl_new, const int* __restrict__ off,
+                                  const int* __restrict__ items, int* __restrict__ out, int B, int S) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)B * S) return;
+  const int b = (int)(g / S), j = (int)(g - (long long)b * S);
+  int sn = sl_new[b];
+  sn = sn < 0 ? 0 : (sn > S ? S : sn);
+  out[g] = j < sn ? items[off[b] + j] : 0;
+}
+
+int tlsan_launch_expand_sessions(const int32_t* sl_new, const int32_t* off, const int32_t* items, int32_t* hist_i_new,
+                                 int B, int S, cudaStream_t st) {
+  const long long n = (long long)B * S;
+  k_expand_sessions<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sl_new, off, items, hist_i_new, B, S);
+  TLSAN_CHECK_LAUNCH("k_expand_sessions");
+  return TLSAN_OK;
+}

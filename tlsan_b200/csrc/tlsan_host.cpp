@@ -6,9 +6,12 @@
 #include <string.h>
 #include <thread>
 #include <vector>
+#include <cuda_runtime.h>
 #include "../../include/tlsan_b200.h"
 
 void tlsan_set_error(const char* fmt, ...);
+int tlsan_launch_expand_sessions(const int32_t* sl_new, const int32_t* off, const int32_t* items, int32_t* hist_i_new,
+                                 int B, int S, cudaStream_t st);
 
 namespace {
 // Range check without 64-bit min/max (which baseline x86-64 cannot vectorise): OR-accumulate
@@ -178,7 +181,130 @@ int pack_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const i
   }
   return TLSAN_OK;
 }
+
+// ---- compact staging: the session matrix hist_i_new [B][S] is almost all padding (S = longest session of the batch,
+// 87 % of the sessions hold one item), so it travels ragged -- offsets [B] + the valid items -- and a kernel rebuilds
+// the padded matrix in HBM.  Staging layout = the packed batch layout followed by [offsets up4(B) | items up4(B*S)].
+int stage_compact_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const int64_t* i2, const float* y,
+                       const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t, const int64_t* sl,
+                       const int64_t* sl_new, const int64_t* c, int32_t* out, int32_t* dev, int64_t words,
+                       int32_t validate, int32_t nthreads, cudaStream_t st) {
+  if (!d || !u || !i || !hist_i || !hist_i_new || !hist_t || !sl || !sl_new || !c || !out || !dev || (!i2 && !y)) {
+    tlsan_set_error("tlsan_stage_batch_host: NULL argument");
+    return TLSAN_E_NULL;
+  }
+  const Layout Y = layout_of(d);
+  const int64_t B = Y.B, L = Y.L, S = Y.S;
+  const int64_t o_off = Y.total, o_rag = o_off + up4(B), need = o_rag + up4(B * S);
+  if (words < need) {
+    tlsan_set_error("tlsan_stage_batch_host: buffers hold %lld words, need %lld (tlsan_stage_words)", (long long)words,
+                    (long long)need);
+    return TLSAN_E_WORKSPACE;
+  }
+  int T = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+  if (T < 1) T = 1;
+  if (T > 8) T = 8;
+  if (B * (2 * L + S) < 200000) T = 1;
+  struct PerThread { Chk u, i, s2, c, sl, sn, hi, hn; int64_t nnew = 0; bool sl_low = false; };
+  std::vector<PerThread> pt(T);
+  std::atomic<int> phase_done[4];
+  for (auto& a : phase_done) a.store(0, std::memory_order_relaxed);
+  cudaError_t cerr = cudaSuccess;
+  int64_t total_new = 0;
+  auto copy_words = [&](int64_t lo, int64_t hi) {
+    if (hi > lo && cerr == cudaSuccess)
+      cerr = cudaMemcpyAsync(dev + lo, out + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, st);
+  };
+  auto arrive = [&](int ph) { phase_done[ph].fetch_add(1, std::memory_order_release); };
+  auto wait_all = [&](int ph) {
+    while (phase_done[ph].load(std::memory_order_acquire) < T) std::this_thread::yield();
+  };
+  const std::function<void(int)> work = [&](int t) {
+    PerThread& P = pt[t];
+    const int64_t r0 = B * t / T, r1 = B * (t + 1) / T, n = r1 - r0;
+    // phase 0: the per-row scalars of this thread's rows + the number of session items they hold
+    cvt(u + r0, out + Y.o_u + r0, n, d->NU, P.u); cvt(i + r0, out + Y.o_i + r0, n, d->NI, P.i);
+    cvt(c + r0, out + Y.o_c + r0, n, d->NC, P.c); cvt(sl + r0, out + Y.o_sl + r0, n, (int32_t)L + 1, P.sl);
+    cvt(sl_new + r0, out + Y.o_sn + r0, n, (int32_t)S + 1, P.sn);
+    if (i2) cvt(i2 + r0, out + Y.o_2 + r0, n, d->NI, P.s2);
+    else memcpy(out + Y.o_2 + r0, y + r0, (size_t)n * 4);
+    int64_t cnt = 0;
+    for (int64_t b = r0; b < r1; ++b) {
+      P.sl_low |= sl[b] < 1;
+      const int64_t sn = sl_new[b] < 0 ? 0 : (sl_new[b] > S ? S : sl_new[b]);
+      cnt += sn;
+    }
+    P.nnew = cnt;
+    arrive(0);
+    wait_all(0);
+    int64_t off = 0;
+    for (int q = 0; q < t; ++q) off += pt[q].nnew;
+    // phase 1: offsets + the valid session items of this thread's rows
+    for (int64_t b = r0; b < r1; ++b) {
+      const int64_t sn = sl_new[b] < 0 ? 0 : (sl_new[b] > S ? S : sl_new[b]);
+      out[o_off + b] = (int32_t)off;
+      cvt(hist_i_new + b * S, out + o_rag + off, sn, d->NI, P.hn);
+      off += sn;
+    }
+    arrive(1);
+    if (t == 0) {
+      wait_all(1);
+      for (int q = 0; q < T; ++q) total_new += pt[q].nnew;
+      copy_words(0, Y.o_hi);                      // scalars
+      copy_words(o_off, o_off + B);               // session offsets
+      copy_words(o_rag, o_rag + total_new);       // session items
+    }
+    const int64_t n1 = B * L, a1 = n1 * t / T, b1 = n1 * (t + 1) / T;
+    memcpy(out + Y.o_ht + a1, hist_t + a1, (size_t)(b1 - a1) * 4);
+    arrive(2);
+    if (t == 0) { wait_all(2); copy_words(Y.o_ht, Y.total); }
+    cvt(hist_i + a1, out + Y.o_hi + a1, b1 - a1, d->NI, P.hi);
+    arrive(3);
+    if (t == 0) { wait_all(3); copy_words(Y.o_hi, Y.o_hn); }
+  };
+  {
+    std::lock_guard<std::mutex> lk(pool().call_mu);
+    pool().run(T, work);
+  }
+  if (cerr != cudaSuccess) {
+    tlsan_set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cerr));
+    return TLSAN_E_CUDA;
+  }
+  // hist_i_new [B][S] <- (sl_new, offsets, items), zero padded like input.py:50-51
+  int rc = tlsan_launch_expand_sessions(dev + Y.o_sn, dev + o_off, dev + o_rag, dev + Y.o_hn, (int)B, (int)S, st);
+  if (rc) return rc;
+  if (validate) {
+    PerThread A;
+    for (int t = 0; t < T; ++t) {
+      Chk* dst[] = {&A.u, &A.i, &A.s2, &A.c, &A.sl, &A.sn, &A.hi, &A.hn};
+      const Chk* src[] = {&pt[t].u, &pt[t].i, &pt[t].s2, &pt[t].c, &pt[t].sl, &pt[t].sn, &pt[t].hi, &pt[t].hn};
+      for (int k = 0; k < 8; ++k) { dst[k]->hi64 |= src[k]->hi64; dst[k]->neg |= src[k]->neg; dst[k]->used |= src[k]->used; }
+      A.sl_low |= pt[t].sl_low;
+    }
+    struct { const char* name; bool bad; int64_t lo, hi; } chk[] = {
+        {"u", bad(A.u), 0, d->NU}, {"i", bad(A.i), 0, d->NI}, {"c", bad(A.c), 0, d->NC},
+        {"hist_i", bad(A.hi), 0, d->NI}, {"hist_i_new", bad(A.hn), 0, d->NI},
+        {"sl", bad(A.sl) || A.sl_low, 1, L + 1}, {"sl_new", bad(A.sn), 0, S + 1}, {"second", bad(A.s2), 0, d->NI}};
+    for (auto& k : chk) {
+      if (k.bad) {
+        tlsan_set_error("batch field %s out of range [%lld, %lld)", k.name, (long long)k.lo, (long long)k.hi);
+        return TLSAN_E_DIMS;
+      }
+    }
+  }
+  return TLSAN_OK;
+}
 }  // namespace
+
+extern "C" int tlsan_stage_words(const tlsan_dims_t* d, int64_t* words) {
+  if (!d || !words) {
+    tlsan_set_error("tlsan_stage_words: NULL argument");
+    return TLSAN_E_NULL;
+  }
+  const Layout Y = layout_of(d);
+  *words = Y.total + up4(Y.B) + up4(Y.B * Y.S);
+  return TLSAN_OK;
+}
 
 extern "C" int tlsan_pack_batch_host(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const int64_t* i2,
                                      const float* y, const int64_t* hist_i, const int64_t* hist_i_new,
@@ -193,10 +319,6 @@ extern "C" int tlsan_stage_batch_host(const tlsan_dims_t* d, const int64_t* u, c
                                       const float* hist_t, const int64_t* sl, const int64_t* sl_new, const int64_t* c,
                                       int32_t* pinned, int32_t* dev, int64_t words, int32_t validate,
                                       int32_t nthreads, void* stream) {
-  if (!dev) {
-    tlsan_set_error("tlsan_stage_batch_host: dev is NULL");
-    return TLSAN_E_NULL;
-  }
-  return pack_impl(d, u, i, i2, y, hist_i, hist_i_new, hist_t, sl, sl_new, c, pinned, words, validate, nthreads, dev,
-                   (cudaStream_t)stream);
+  return stage_compact_impl(d, u, i, i2, y, hist_i, hist_i_new, hist_t, sl, sl_new, c, pinned, dev, words, validate,
+                            nthreads, (cudaStream_t)stream);
 }

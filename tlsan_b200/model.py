@@ -269,16 +269,21 @@ class Model(object):
         if np.shape(batch[3])[1] != self.L:
             raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (np.shape(batch[3])[1], self.L))
         offs, total = _pack_offsets(B, self.L, S)
+        dims = self._dims(B, S)
+        words = C.c_int64()
+        check(self._lib.tlsan_stage_words(C.byref(dims), C.byref(words)))    # packed layout + ragged session tail
+        words = int(words.value)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            self._stage_cache[key] = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.cuda.Event())
         host, ev = self._stage_cache[key]
         ev.synchronize()                      # the previous copy out of this pinned buffer has finished
-        dev = torch.empty(total, dtype=torch.int32, device=self.device)
-        pack_batch(self._lib, batch, self._dims(B, S), is_test, host.numpy(), self.validate, dev.data_ptr(),
-                   self._stream())
+        dev = torch.empty(words, dtype=torch.int32, device=self.device)
+        pack_batch(self._lib, batch, dims, is_test, host.numpy(), self.validate, dev.data_ptr(), self._stream())
         ev.record(torch.cuda.current_stream(self.device))
-        self.last_h2d_bytes = total * 4
+        # bytes that actually crossed PCIe: everything but the padded session matrix, plus its ragged form
+        n_new = int(np.clip(np.asarray(batch[7], dtype=np.int64), 0, S).sum())
+        self.last_h2d_bytes = 4 * (total - (B * S + 3) // 4 * 4 + B + n_new)
         return DeviceBatch(dev, B, self.L, S, offs, is_test)
 
     # ------------------------------------------------------------------ training

@@ -206,13 +206,16 @@ class ShardedModel(object):
         if np.shape(batch[3])[1] != self.L:
             raise ValueError("hist_i has %d columns but the model was built with Ls=%d" % (np.shape(batch[3])[1], self.L))
         offs, total = _pack_offsets(B, self.L, S)
+        gd = Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC, B_global=B, reserved=0)
+        words = C.c_int64()
+        check(self._lib.tlsan_stage_words(C.byref(gd), C.byref(words)))
+        words = int(words.value)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = (torch.empty(total, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            self._stage_cache[key] = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.cuda.Event())
         host, ev = self._stage_cache[key]
         ev.synchronize()
-        gd = Dims(B=B, L=self.L, S=S, NI=self.NI, NU=self.NU, NC=self.NC, B_global=B, reserved=0)
-        dev = torch.empty(total, dtype=torch.int32, device=self.device)
+        dev = torch.empty(words, dtype=torch.int32, device=self.device)
         pack_batch(self._lib, batch, gd, is_test, host.numpy(), self.validate, dev.data_ptr(), self._stream())
         ev.record(torch.cuda.current_stream(self.device))
         return DeviceBatch(dev, B, self.L, S, offs, is_test)
