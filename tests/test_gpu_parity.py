@@ -191,6 +191,38 @@ def test_pipelined_steps_equal_plain_steps(dm):
             assert np.array_equal(outs[0][k], other[k]), k
 
 
+def test_pipelined_steps_random_predictions_and_many_models(dm):
+    """Stress of the presort machinery: 40 steps whose announced successor is right, wrong or absent at random must
+    equal 40 plain steps bit for bit; and more models than the library has presort slots, each abandoning an
+    announced presort, must not exhaust them."""
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(5, 400, 40)
+    batches, lo = [], 0
+    for n in sizes:
+        batches.append(O.collate_train(dm.train_set[lo:lo + int(n)], 10)); lo += int(n)
+    outs = []
+    for mode in ("plain", "random"):
+        model = model_from_params(params, dm.icl, cfg)
+        dbs = [model.stage_batch(b) for b in batches]
+        for k, db in enumerate(dbs):
+            nxt = None
+            if mode == "random":
+                r = rng.integers(0, 3)
+                nxt = dbs[(k + 1) % len(dbs)] if r == 0 else (dbs[int(rng.integers(0, len(dbs)))] if r == 1 else None)
+            model.train_staged(db, 1.0, next_db=nxt)
+        torch.cuda.synchronize()
+        outs.append({k: v.numpy().copy() for k, v in model.state_dict().items()})
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    for _ in range(40):
+        m = model_from_params(params, dm.icl, cfg)
+        d0, d1 = m.stage_batch(batches[0]), m.stage_batch(batches[1])
+        m.train_staged(d0, 1.0, next_db=d1)          # presort announced, model dropped
+    torch.cuda.synchronize()
+
+
 def test_gather_concat_bit_exact():
     from tlsan_b200 import _lib
     rng = np.random.default_rng(3)

@@ -80,7 +80,7 @@ static bool g_prof_overlap = false;   // the recorded steps ran the sort on the 
 // Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
 // one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
 struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr; bool valid = false; };
-static Presort g_presort[8];
+static Presort g_presort[32];
 static Presort* presort_slot(char* ws, bool create) {
   for (auto& e : g_presort) if (e.ws == ws) return &e;
   if (!create) return nullptr;
@@ -88,6 +88,14 @@ static Presort* presort_slot(char* ws, bool create) {
     if (!e.valid) {
       if (!e.ev && cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
       e.ws = ws;
+      return &e;
+    }
+  // every slot holds an announced-but-never-consumed presort (callers that dropped their model): one whose
+  // kernels have finished can no longer race with anything and may be recycled
+  for (auto& e : g_presort)
+    if (cudaEventQuery(e.ev) == cudaSuccess) {
+      e.ws = ws;
+      e.valid = false;
       return &e;
     }
   return nullptr;

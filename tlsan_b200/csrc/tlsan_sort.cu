@@ -14,7 +14,7 @@
 
 // key of occurrence id `g` straight from the batch (pass 1 never materialises the key array)
 struct KeySrc {
-  int B, L, S, spsh, NI, NC;
+  int B, L, S, spsh, NI, NC, NR;
   const int *u, *cand, *c, *sl, *sl_new, *hist_i, *hist_i_new;
 };
 __device__ __forceinline__ int occ_key(const KeySrc& k, long long g) {
@@ -25,6 +25,9 @@ __device__ __forceinline__ int occ_key(const KeySrc& k, long long g) {
   else if (j == k.L + k.S) key = __ldg(k.cand + b);
   else if (j == k.L + k.S + 1) key = k.NI + __ldg(k.c + b);
   else if (j == k.L + k.S + 2) key = k.NI + k.NC + __ldg(k.u + b);
+  // ids are range-checked when a batch is staged; a batch buffer that was freed and reused while a presort
+  // announced for it was still queued must not turn into out-of-range segment writes either
+  if ((unsigned)key >= (unsigned)k.NR) key = TLSAN_INVALID_KEY;
   return key;
 }
 
@@ -182,7 +185,7 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
   int* seg_off = reinterpret_cast<int*>(ws + w.seg_off);
   const long long nocc = w.nocc;
   KeySrc src;
-  src.B = d.B; src.L = d.L; src.S = d.S; src.spsh = w.SPSH; src.NI = d.NI; src.NC = d.NC;
+  src.B = d.B; src.L = d.L; src.S = d.S; src.spsh = w.SPSH; src.NI = d.NI; src.NC = d.NC; src.NR = w.NR;
   src.u = b.u; src.cand = b.i; src.c = b.c; src.sl = b.sl; src.sl_new = b.sl_new;
   src.hist_i = b.hist_i; src.hist_i_new = b.hist_i_new;
   int bits = 1;

@@ -256,6 +256,8 @@ class Model(object):
         need = C.c_size_t()
         check(self._lib.tlsan_workspace_bytes(C.byref(dims), C.byref(need)))
         if self._ws[slot] is None or self._ws[slot].numel() < need.value:
+            if self._ws[slot] is not None:
+                torch.cuda.synchronize(self.device)      # the library's side streams may still be using the old one
             self._ws[slot] = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
             if self._presorted is not None and self._presorted[4] == slot:
                 self._presorted = None
@@ -339,6 +341,14 @@ class Model(object):
             self._ws_slot = 1 - slot
         self.global_step.value += 1
         return self._stats
+
+    def __del__(self):
+        # kernels on the library's side streams (sort, table norms, a presort of the next batch) may still be reading
+        # this model's buffers; the caching allocator only orders frees against the current stream
+        try:
+            torch.cuda.synchronize(self.device)
+        except Exception:
+            pass
 
     def _dp_arenas(self):
         """IPC-shared exchange arenas of all ranks (created once): every rank cudaMallocs one, the 64-byte IPC
