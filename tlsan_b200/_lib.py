@@ -1,5 +1,6 @@
 """ctypes binding of include/tlsan_b200.h.  No CPU fallback: if the CUDA library is missing
 or fails to load, importing the compute entry points raises."""
+import atexit
 import ctypes as C
 import os
 
@@ -104,6 +105,18 @@ PHASE_KERNEL = {"long_fwd": "k_fwd_mma<1>", "short": "k_async<2>", "bwd_long": "
                 "dense_fwd": "k_dense_fwd_mma", "dense_bwd": "k_dense_bwd_mma", "reduce": "k_row_reduce"}
 
 
+def _drain():
+    """At interpreter exit: let the kernels still queued on the library's side streams (a presort announced for a
+    batch nobody trained on, table norms) finish before torch tears its allocations down under them."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            for d in range(torch.cuda.device_count()):
+                torch.cuda.synchronize(d)
+    except Exception:
+        pass
+
+
 def lib():
     """Load tlsan_b200/libtlsan_b200.so (built by tlsan_b200.build / __graft_entry__.build)."""
     global _lib
@@ -118,6 +131,7 @@ def lib():
         if h.tlsan_abi_version() != 1:
             raise TlsanError("ABI version mismatch")
         _lib = h
+        atexit.register(_drain)
     return _lib
 
 

@@ -254,7 +254,11 @@ class Model(object):
     def _workspace(self, dims, slot=0):
         """Step workspace; two slots so that a pipelined step can presort the next batch into the other one."""
         need = C.c_size_t()
-        check(self._lib.tlsan_workspace_bytes(C.byref(dims), C.byref(need)))
+        # sized for the session width rounded up to 8 columns: S is the longest session of the batch (input.py:33)
+        # and wobbles from batch to batch; a reallocation costs a device synchronisation and a cudaMalloc
+        roomy = Dims(B=dims.B, L=dims.L, S=(dims.S + 7) // 8 * 8, NI=dims.NI, NU=dims.NU, NC=dims.NC,
+                     B_global=dims.B_global, reserved=0)
+        check(self._lib.tlsan_workspace_bytes(C.byref(roomy), C.byref(need)))
         if self._ws[slot] is None or self._ws[slot].numel() < need.value:
             if self._ws[slot] is not None:
                 torch.cuda.synchronize(self.device)      # the library's side streams may still be using the old one
