@@ -4,14 +4,19 @@
  * `class Model` (TLSAN/model.py:13-313) fed by the 9-tuple of TLSAN/input.py:54,107.  Every
  * entry point below names the reference call it replaces.  Conventions:
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
- *     (params, batch, workspace, outputs); nothing is allocated or freed behind the ABI;
- *   - every call is asynchronous on the `cudaStream_t` passed as `void* stream`;
+ *     (params, batch, workspace, outputs) unless a function says host; nothing is allocated or freed behind
+ *     the ABI except the IPC arenas of tlsan_dp_arena_* (explicit create / release);
+ *   - every call is asynchronous on the `cudaStream_t` passed as `void* stream`.  A train step also uses two
+ *     internal streams per device (the occurrence sort and the table norms run beside the forward kernels, a
+ *     pipelined step sorts the next batch behind the backward kernels); they fork from and join `stream` with
+ *     events, so the caller sees ordinary stream semantics -- but buffers handed to a step must stay allocated
+ *     until `stream` has passed it (and a batch announced as `next` until the step that consumes it);
  *   - return 0 on success, a negative TLSAN_E_* code otherwise; `tlsan_last_error()` returns
  *     a thread-local description; no C++ exception crosses the ABI;
  *   - indices are int32, values fp32; embedding rows are 128 B and must be 16-B aligned.
- * The small attention weights are mirrored into one __constant__ bank per process: calls
- * that read them upload in-stream first, so concurrent use from two streams must be
- * serialised by the caller.
+ * The small attention weights are mirrored into one __constant__ bank per process (CUDA-core variant only) and the
+ * internal streams / presort registry are per process: concurrent train steps from two host threads on one device
+ * must be serialised by the caller.
  */
 #ifndef TLSAN_B200_H
 #define TLSAN_B200_H
