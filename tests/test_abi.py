@@ -61,6 +61,18 @@ def test_argument_validation_without_gpu(lib):
         _lib.check(-2)
 
 
+def test_stage_words_cover_the_packed_layout_and_the_ragged_tail(lib):
+    """tlsan_stage_words = packed batch layout (model._pack_offsets) + session offsets + worst-case session items."""
+    from tlsan_b200.model import _pack_offsets
+    up4 = lambda n: (n + 3) // 4 * 4
+    for B, L, S in ((1, 1, 1), (7, 10, 3), (65536, 10, 18), (333, 90, 41)):
+        d = _lib.Dims(B=B, L=L, S=S, NI=100, NU=50, NC=5, B_global=B, reserved=0)
+        w = C.c_int64()
+        assert lib.tlsan_stage_words(C.byref(d), C.byref(w)) == 0
+        _, total = _pack_offsets(B, L, S)
+        assert w.value == total + up4(B) + up4(B * S)
+
+
 def test_model_refuses_to_run_without_cuda():
     import torch
     if torch.cuda.is_available():
