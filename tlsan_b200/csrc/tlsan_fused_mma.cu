@@ -627,7 +627,11 @@ int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st) 
   return TLSAN_OK;
 }
 
+bool tlsan_bwd_long_diet_selected();                                   // tlsan_fused_diet.cu (experimental, default off)
+int tlsan_launch_bwd_long_diet(const FArgs& a, int* grid_b, cudaStream_t st);
+
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st) {
+  if (tlsan_bwd_long_diet_selected()) return tlsan_launch_bwd_long_diet(a, grid_b, st);
   int rc = set_long_attrs();
   if (rc) return rc;
   const int g = mma_grid(a.B, 2);
