@@ -53,6 +53,7 @@ struct TlsanWs {
   int64_t nocc;
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
+  size_t row_cnt, row_fill;   // per-row occurrence counters of the (experimental) counting sort
   size_t rows_i, rows_u, gscal, scratch;
   size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
@@ -95,6 +96,8 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.f_dgrad = w.f_gu + (size_t)d.NU * w.PU;
   w.flat_count = w.f_dgrad + TLSAN_PART;
   w.flat = take(w.flat_count * 4);
+  w.row_cnt = take((size_t)(w.NR + 2) * 4);    // appended last: every other offset is as measured in round 1
+  w.row_fill = take((size_t)(w.NR + 2) * 4);
   w.total = o;
   return w;
 }
