@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TLSAN_ABI_VERSION 1
+#define TLSAN_ABI_VERSION 2   /* 2: tlsan_batch_t.hist_d, TLSAN_STAT_DP_ERR */
 
 /* fixed architecture of the path (TLSAN/train.py:26-35 defaults; hidden_units must equal
  * item+cate embedding size, model.py:100-109) */
@@ -98,6 +98,10 @@ typedef struct {
   const int32_t* sl;         /* batch[6] */
   const int32_t* sl_new;     /* batch[7] */
   const int32_t* c;          /* batch[8]  u_cate */
+  const int32_t* hist_d;     /* optional (may be NULL): RAW day gaps d[B][L] = cur_day - day + 1, 0 = padding.  When set,
+                              * the long-term kernels bucket while they gather -- n = sum_j [d >= 2^j] = min(12,
+                              * floor(log2 d)), weight float32(1/n), exactly proc_time_emb (build_dataset.py:16-21) +
+                              * the float32 store of input.py:36,45 -- and hist_t is ignored (it may alias hist_d). */
 } tlsan_batch_t;
 
 /* scalars a train step leaves on the device (index into `stats`) */
@@ -107,6 +111,7 @@ enum {
   TLSAN_STAT_NORM = 2,     /* global norm used by clip_by_global_norm, model.py:201 */
   TLSAN_STAT_SCALE = 3,    /* clip multiplier */
   TLSAN_STAT_L2 = 4,       /* l2_norm, model.py:164-169 */
+  TLSAN_STAT_DP_ERR = 5,   /* tlsan_dp_exchange: 1 = a wait on a peer rank timed out; that step's update was SKIPPED */
   TLSAN_STAT_COUNT = 8
 };
 
@@ -173,7 +178,10 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
  *   tlsan_dp_arena_bytes / _create / _open / _release : arena size for (dims, world); cudaMalloc + IPC handle
  *       (64 bytes, to be exchanged by the host, e.g. torch.distributed.all_gather_object); map a peer's arena.
  *   tlsan_dp_exchange : arenas[world] = the mapped arenas in rank order; arenas[rank] = the own one = the buffer
- *       tlsan_step_grads just wrote; epoch = 1, 2, ... (one more every call, the same on every rank). */
+ *       tlsan_step_grads just wrote; epoch = 1, 2, ... (one more every call, the same on every rank).
+ *       A rank waits for its peers with a bounded spin (TLSAN_DP_TIMEOUT_S seconds, default 30): on a timeout the
+ *       kernels of that step leave the weights untouched and stats[TLSAN_STAT_DP_ERR] is set (sticky) -- the
+ *       caller must poll it (tlsan_b200.Model does, every dp_check_every steps) and stop: replicas have diverged. */
 int tlsan_dp_arena_bytes(const tlsan_dims_t* dims, int32_t world, size_t* bytes);
 int tlsan_dp_arena_create(size_t bytes, void** ptr, char* handle64);
 int tlsan_dp_arena_open(const char* handle64, void** ptr);
@@ -185,7 +193,9 @@ int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, void* c
 /* Pipelined variants: `next` (optional) names the batch of the FOLLOWING step and that step's own workspace.  Its
  * occurrence sort is enqueued behind the backward kernels of this step, where it runs beside the reduce, the
  * all-reduce and the update; the following call passes the same batch / workspace with dims->reserved bit 1 set
- * and starts without a sort.  Results are identical to the plain entry points. */
+ * and starts without a sort.  If no valid presort exists for that workspace (side streams disabled with
+ * TLSAN_SORT_OVERLAP=0, or the announcement was dropped) the step simply sorts in place.  Results are identical
+ * to the plain entry points. */
 typedef struct {
   const tlsan_dims_t* dims;
   const tlsan_batch_t* batch;

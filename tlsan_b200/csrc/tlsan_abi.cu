@@ -35,12 +35,15 @@ void tlsan_profile_mark(int phase_done, cudaStream_t st) {
 //   ffma  = CUDA-core maps, 4 samples per warp      (tlsan_fwd_bwd.cu)
 //   mma   = 3xTF32 mma tiles, synchronous gathers   (tlsan_fused_mma.cu)
 //   async = mma tiles + cp.async sample pipeline     (tlsan_fused_async.cu)
-//   (unset) hybrid = per kernel the faster of mma / async, see tlsan_launch_fwd_bwd_async   [default]
+//   hybrid = per kernel the faster of mma / async     (the round-1 default)
+//   (unset) pf = long-term kernels with a metadata pre-pass + in-warp prefetch pipeline (tlsan_fused_pf.cu),
+//           cp.async pipeline for the short-term kernel                                              [default]
 static int fused_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TLSAN_FUSED_IMPL");
-    v = (e && strcmp(e, "ffma") == 0) ? 0 : (e && strcmp(e, "mma") == 0) ? 1 : (e && strcmp(e, "async") == 0) ? 2 : 3;
+    v = (e && strcmp(e, "ffma") == 0) ? 0 : (e && strcmp(e, "mma") == 0) ? 1 : (e && strcmp(e, "async") == 0) ? 2
+        : (e && strcmp(e, "hybrid") == 0) ? 3 : 4;
   }
   return v;
 }
@@ -136,6 +139,8 @@ static int check_batch(const tlsan_batch_t* b, bool train, int ncand) {
           "batch has a NULL field");
   if (train) REQUIRE(b->y != nullptr, TLSAN_E_NULL, "batch.y (labels) is NULL");
   if (ncand > 1) REQUIRE(b->i2 != nullptr, TLSAN_E_NULL, "batch.i2 is NULL but ncand == 2");
+  REQUIRE(b->hist_d == nullptr || fused_impl() == 1 || fused_impl() >= 3, TLSAN_E_UNSUPPORTED,
+          "raw day gaps (batch.hist_d) need the mma / hybrid / pf kernels (TLSAN_FUSED_IMPL)");
   return TLSAN_OK;
 }
 
@@ -174,11 +179,16 @@ int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_b
   return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
 }
 
+// scratch [B][TLSAN_SCR][64] + per-token metadata [B][L] x 16 B, each 256-B aligned
+static size_t score_ws_bytes(const tlsan_dims_t* d) {
+  return tlsan_align_up((size_t)d->B * TLSAN_SCR * 64 * sizeof(float), 256) + (size_t)d->B * d->L * 16 + 512;
+}
+
 int tlsan_score_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   REQUIRE(bytes != nullptr, TLSAN_E_NULL, "bytes is NULL");
-  *bytes = (size_t)dims->B * TLSAN_SCR * 64 * sizeof(float) + 256;
+  *bytes = score_ws_bytes(dims);
   return TLSAN_OK;
 }
 
@@ -191,8 +201,7 @@ int tlsan_score_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsa
   if ((rc = check_batch(b, false, ncand))) return rc;
   REQUIRE(logits != nullptr && workspace != nullptr, TLSAN_E_NULL, "logits/workspace is NULL");
   REQUIRE(ut == nullptr || aligned16(ut), TLSAN_E_ALIGN, "ut must be 16-B aligned");
-  REQUIRE(workspace_bytes >= (size_t)dims->B * TLSAN_SCR * 64 * sizeof(float) + 256, TLSAN_E_WORKSPACE,
-          "workspace too small");
+  REQUIRE(workspace_bytes >= score_ws_bytes(dims), TLSAN_E_WORKSPACE, "workspace too small");
   float* scratch = reinterpret_cast<float*>(tlsan_align_up(reinterpret_cast<uintptr_t>(workspace), 256));
   if (!use_mma()) return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
   return tlsan_launch_score_ws(*dims, *p, *b, ncand, logits, ut, scratch, (cudaStream_t)stream);
@@ -236,10 +245,11 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   SideStream* side = use_mma() ? side_stream() : nullptr;
   cudaEvent_t sorted = nullptr;
   int long_ctas = 3;
-  const bool presorted = (dims->reserved & 2) != 0;
+  // bit 1 = "the previous *_pipelined call announced this batch": honoured only if that call really enqueued the
+  // presort (it does not when the side streams are off); otherwise the step sorts in place like a plain one
+  Presort* ps = (dims->reserved & 2) && side ? presort_slot(ws, false) : nullptr;
+  const bool presorted = ps && ps->valid;
   if (presorted) {
-    Presort* ps = presort_slot(ws, false);
-    REQUIRE(side && ps && ps->valid, TLSAN_E_UNSUPPORTED, "batch was not presorted into this workspace");
     ps->valid = false;
     sorted = ps->ev;
     sorted_vals = tlsan_sorted_vals(w, ws);
@@ -275,7 +285,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   }
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
-    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() == 3, sorted,
+    rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() - 2, sorted,
                                     long_ctas, st);
   else if (fused_impl() == 1)
     rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, long_ctas, st);

@@ -53,8 +53,7 @@ struct TlsanWs {
   int64_t nocc;
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
-  size_t row_cnt, row_fill;   // per-row occurrence counters of the (experimental) counting sort
-  size_t rows_i, rows_u, gscal, scratch;
+  size_t rows_i, rows_u, gscal, scratch, meta;
   size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
   size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
@@ -86,6 +85,7 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.rows_u = take((size_t)d.B * w.PU * 4);
   w.gscal = take((size_t)d.B * 4);
   w.scratch = take((size_t)d.B * TLSAN_SCR * 64 * 4);
+  w.meta = take((size_t)d.B * d.L * 16);       // resolved per-token metadata of the long-term sequence (k_long_meta)
   w.part_a = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_c = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
@@ -96,8 +96,6 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.f_dgrad = w.f_gu + (size_t)d.NU * w.PU;
   w.flat_count = w.f_dgrad + TLSAN_PART;
   w.flat = take(w.flat_count * 4);
-  w.row_cnt = take((size_t)(w.NR + 2) * 4);    // appended last: every other offset is as measured in round 1
-  w.row_fill = take((size_t)(w.NR + 2) * 4);
   w.total = o;
   return w;
 }
@@ -123,7 +121,7 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
                              const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, cudaEvent_t sorted,
                              int long_ctas, cudaStream_t st);
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
-                               const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
+                               const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
                                cudaEvent_t sorted, int long_ctas, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,

@@ -12,6 +12,7 @@ struct FArgs {
   const int* icl;
   const int *u, *i, *i2, *c, *sl, *sl_new, *hist_i, *hist_i_new;
   const float *y, *hist_t;
+  const int* hist_d;   // raw day gaps (tlsan_batch_t.hist_d) or NULL
   // outputs
   float* logits;   // score: [B][ncand]
   float* ut;       // score: optional [B][64]

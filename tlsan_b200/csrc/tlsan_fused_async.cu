@@ -390,14 +390,21 @@ static int launch_async(const FArgs& a, int* grid_out, cudaStream_t st) {
 int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
+int tlsan_launch_long_meta(const FArgs& a, void* meta, cudaStream_t st);                          // tlsan_fused_pf.cu
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st);
+int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st);
 
 // `hybrid` (default): per kernel, whichever formulation measured faster on B200 (profiles/):
 // synchronous gathers for the two long-term kernels (24 / 16 resident warps already hide the
 // latency; the async pipeline only adds instructions there), cp.async pipeline for the short-term
 // kernel (its per-sample dependent chain is otherwise exposed: 130 -> 113 us).
+// `pf` (default since round 2): the long-term kernels are those of tlsan_fused_pf.cu (metadata pre-pass + in-warp
+// prefetch pipeline); forward and backward must be the same variant (the saved softmax maximum is in the log2
+// domain there).  variant: 0 = async everywhere, 1 = hybrid, 2 = pf.
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
-                               const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, bool hybrid,
+                               const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
                                cudaEvent_t sorted, int long_ctas, cudaStream_t st) {
+  const bool hybrid = variant == 1;
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
   a.inv = reinterpret_cast<const int*>(ws + w.inv); a.spsh = w.SPSH;
@@ -405,7 +412,11 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.gscal = reinterpret_cast<float*>(ws + w.gscal);
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   int rc;
-  if ((rc = hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st))) return rc;
+  void* meta = ws + w.meta;
+  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, st))) return rc;
+  if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, long_ctas, st)
+                         : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
+    return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
@@ -417,7 +428,9 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
-  if ((rc = hybrid ? tlsan_launch_bwd_long_mma(a, grid_b, st) : launch_async<3>(a, grid_b, st))) return rc;
+  if ((rc = variant == 2 ? tlsan_launch_bwd_long_pf(a, meta, grid_b, st)
+                         : hybrid ? tlsan_launch_bwd_long_mma(a, grid_b, st) : launch_async<3>(a, grid_b, st)))
+    return rc;
   tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
   return TLSAN_OK;
 }

@@ -21,6 +21,7 @@
 //   k_dense_bwd_mma  d o_long = dz Wd^T ; dWd = O^T dZ ; dbd
 //   k_bwd_long_mma   backward of the long FWA and of the time-aware position term (model.py:98-109)
 #include <stdlib.h>
+#include <string.h>
 #include "tlsan_mma_common.cuh"
 
 // long-term FWA forward of one sample (model.py:98-109, 334-345) -> softmax state.
@@ -627,11 +628,7 @@ int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st) 
   return TLSAN_OK;
 }
 
-bool tlsan_bwd_long_diet_selected();                                   // tlsan_fused_diet.cu (experimental, default off)
-int tlsan_launch_bwd_long_diet(const FArgs& a, int* grid_b, cudaStream_t st);
-
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st) {
-  if (tlsan_bwd_long_diet_selected()) return tlsan_launch_bwd_long_diet(a, grid_b, st);
   int rc = set_long_attrs();
   if (rc) return rc;
   const int g = mma_grid(a.B, 2);
@@ -656,13 +653,20 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
   return TLSAN_OK;
 }
 
+int tlsan_launch_long_meta(const FArgs& a, void* meta, cudaStream_t st);                          // tlsan_fused_pf.cu
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st);
+
 // scoring with a caller-provided scratch [B][TLSAN_SCR][64]: long FWA -> batched dense GEMM -> short FWA + logits
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                           float* logits, float* ut, float* scratch, cudaStream_t st) {
   FArgs a = tlsan_make_fargs(d, p, b);
   a.logits = logits; a.ut = ut; a.scratch = scratch;
   int rc;
-  if ((rc = tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
+  static int use_ws = -1;
+  if (use_ws < 0) { const char* e = getenv("TLSAN_FUSED_IMPL"); use_ws = (e && *e && strcmp(e, "pf") != 0) ? 0 : 1; }
+  void* meta = reinterpret_cast<char*>(scratch) + tlsan_align_up((size_t)d.B * TLSAN_SCR * 64 * sizeof(float), 256);
+  if (use_ws && (rc = tlsan_launch_long_meta(a, meta, st))) return rc;
+  if ((rc = use_ws ? tlsan_launch_long_fwd_pf(a, meta, 3, st) : tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
   if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
   k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short score>");

@@ -1,0 +1,445 @@
+// Long-term kernels with a resolved-metadata pre-pass and an in-warp prefetch pipeline (default path of the train
+// step and of large-batch scoring since round 2).
+//
+// Same math and lane layout as tlsan_fused_mma.cu (one warp = one sample, 16-row 3xTF32 mma tiles).  What changed is
+// how a sample's data reaches the warp.  The round-1 kernels walked, per sample, a chain of dependent loads
+//        u, sl  ->  hist_i / hist_t / usert[u]  ->  icl[id]  ->  token rows (item row | cate row)
+// and a quarter to a third of their stall samples sat on it (profiles/r01_ncu_full_summary.txt: long_scoreboard).
+//   * k_long_meta resolves the chain ONCE per step for every token: meta[b][t] = {item row, category row,
+//     P[u,t] * hist_t, hist_t} (16 B, coalesced) -- the time-gap bucketing of raw day gaps (build_dataset.py:16-21) happens
+//     here too, while gathering;
+//   * k_pf_long keeps, per warp, two shared-memory buffers of one ROUND (up to 16 tokens of one sample) each and a
+//     three-slot ring of round metadata, and runs a two-deep pipeline entirely on cp.async (no prefetch registers):
+//     while round n is computed from buffer n % 2, the rows of round n+1 are in flight (16 lanes x 16 B per token,
+//     addresses from metadata that landed a round ago) and the metadata of round n+2 is being copied.  No load a
+//     tile depends on is issued less than one round of compute earlier.
+// Work is assigned statically (sample b -> warp b mod #warps): every per-warp partial sum is accumulated in a fixed
+// order, results are bit-identical from run to run.
+//
+// Tile-level changes against tlsan_mma_common.cuh:
+//   * log2(e) is folded into W2 / b2 once per kernel: the softmax works in the log2 domain (no multiply per exp);
+//   * forward: up to FOUR tokens (two independent mma chains) per iteration and ONE running-max update for all of
+//     them (5 ex2 per 4 tokens and feature instead of 8), which also halves the dependent FMNMX / FFMA chain;
+//   * backward: the tile of tlsan_mma_common.cuh with the log2-domain exponent.  (A variant that fed the weight-
+//     gradient outer products from LDS.128 broadcasts instead of quad shuffles and reduced d tau through shared
+//     memory was measured and dropped: +25 % instructions after register allocation, profiles/experiments/.)
+//
+//   k_long_meta   per-token metadata of the long-term sequence                    (model.py:84-86,98-99,109)
+//   k_pf_long<1>  long-term FWA forward -> o_long + softmax statistics (scratch)  (model.py:98-109,334-345)
+//   k_pf_long<3>  backward of the long-term FWA and of the time-aware position term
+#include <stdlib.h>
+#include "tlsan_mma_common.cuh"
+
+#define PF_R 16                          // tokens per round
+#define PF_WARPS 8
+#define PF_THREADS (32 * PF_WARPS)
+#define LOG2E 1.4426950408889634f
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-warp shared-memory geometry (bytes); RW = rows per buffer = min(16, L rounded up to 2)
+struct PfGeo {
+  int rw, o_tau, o_stats, buf, o_ring, ring, per_warp, total;
+};
+static PfGeo pf_geo(int L, bool bwd) {
+  PfGeo g;
+  g.rw = L >= PF_R ? PF_R : (L + 1) / 2 * 2;
+  int o = g.rw * 256;
+  g.o_tau = o; o += 64;                                         // tau of the round's tokens
+  g.o_stats = o; if (bwd) o += 1024;                            // do_long | o_long | max | 1/den of the sample
+  g.buf = o;
+  o = 2 * g.buf;
+  g.o_ring = o;                                                 // 3 x { int4 meta[16] ; int pos[16] }
+  g.ring = 16 * 16 + 16 * 4;
+  o += 3 * g.ring;
+  g.per_warp = (o + 127) / 128 * 128;
+  g.total = g.per_warp * PF_WARPS;
+  if (bwd && g.total < (int)(PF_WARPS * 160 * 4)) g.total = PF_WARPS * 160 * 4;   // end-of-kernel reduction staging
+  return g;
+}
+
+struct PfArgs {
+  FArgs a;
+  const int4* meta;         // [B][L] {item row, category row, P*hist_t, hist_t}
+  PfGeo g;
+};
+
+__device__ __forceinline__ void cp16_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp4_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// forward weights with log2(e) folded into the second map: m2' = m2 * log2(e)
+__device__ __forceinline__ FwaW load_fwa_log2(const float* __restrict__ dense, int base, int g, int t) {
+  FwaW w;
+  w.W1 = load_b(dense + base, g, t);
+  w.W2 = make_b(dense[base + 72 + (2 * t) * 8 + g] * LOG2E, dense[base + 72 + (2 * t + 1) * 8 + g] * LOG2E);
+  w.b1[0] = dense[base + 64 + 2 * t]; w.b1[1] = dense[base + 64 + 2 * t + 1];
+  w.b2[0] = dense[base + 136 + 2 * t] * LOG2E; w.b2[1] = dense[base + 136 + 2 * t + 1] * LOG2E;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pre-pass: one thread per (sample, history slot)
+__global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.B * a.L) return;
+  const int b = (int)(idx / a.L), t = (int)(idx - (long long)b * a.L);
+  int4 m = make_int4(0, 0, 0, 0);
+  if (t < __ldg(a.sl + b)) {
+    const int id = __ldg(a.hist_i + idx);
+    const float ht = a.hist_d ? bucket_weight(__ldg(a.hist_d + idx)) : __ldg(a.hist_t + idx);   // bucketing fused
+    const float pt = __ldg(a.usert + (size_t)__ldg(a.u + b) * a.L + t) * ht;                   // model.py:99
+    m = make_int4(id, a.NI + __ldg(a.icl + id), __float_as_int(pt), __float_as_int(ht));
+  }
+  meta[idx] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// online softmax over the sequence axis in the log2 domain, for the lane's two features
+struct SoftL2 {
+  float mx[2], den[2], acc[2];
+  __device__ __forceinline__ void init() {
+    mx[0] = mx[1] = -INFINITY; den[0] = den[1] = 0.f; acc[0] = acc[1] = 0.f;
+  }
+  // two tokens (second may be masked: m = -inf, x = 0)
+  __device__ __forceinline__ void push2(const float (&m)[4], const float (&x)[4]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float nm = fmax3(mx[j], m[j], m[2 + j]);
+      const float sc = ex2f(mx[j] - nm), e0 = ex2f(m[j] - nm), e1 = ex2f(m[2 + j] - nm);
+      den[j] = fmaf(den[j], sc, e0 + e1);
+      acc[j] = fmaf(acc[j], sc, fmaf(e0, x[j], e1 * x[2 + j]));
+      mx[j] = nm;
+    }
+  }
+  // four tokens
+  __device__ __forceinline__ void push4(const float (&ma)[4], const float (&xa)[4], const float (&mb)[4],
+                                        const float (&xb)[4]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float nm = fmaxf(fmax3(mx[j], ma[j], ma[2 + j]), fmaxf(mb[j], mb[2 + j]));
+      const float sc = ex2f(mx[j] - nm);
+      const float e0 = ex2f(ma[j] - nm), e1 = ex2f(ma[2 + j] - nm), e2 = ex2f(mb[j] - nm), e3 = ex2f(mb[2 + j] - nm);
+      den[j] = fmaf(den[j], sc, (e0 + e1) + (e2 + e3));
+      acc[j] = fmaf(acc[j], sc, fmaf(e0, xa[j], e1 * xa[2 + j]) + fmaf(e2, xb[j], e3 * xb[2 + j]));
+      mx[j] = nm;
+    }
+  }
+};
+
+// backward of one tile: tile_bwd of tlsan_mma_common.cuh with the softmax exponent in the log2 domain
+// (w.W2 / w.b2 carry log2(e); wt holds the UNscaled transposed maps for d pre / d x)
+__device__ __forceinline__ void tile_bwd_l2(const float (&x)[4], bool okB, const float (&o)[2], const float (&kf)[2],
+                                            const float (&nmx)[2], const FwaW& w, const FwaWT& wt, int lane,
+                                            float (&dx)[4], FwaGrad& G) {
+  float m1[4], m2[4];
+  tile_maps(x, w, m1, m2);
+  float ado[4], dm2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = i & 1;
+    const float aw = ex2f(m2[i] + nmx[j]) * kf[j];             // softmax weight * d out
+    ado[i] = (i < 2 || okB) ? aw : 0.f;
+    dm2[i] = ado[i] * (x[i] - o[j]);
+  }
+  G.b2[0] += dm2[0] + dm2[2]; G.b2[1] += dm2[1] + dm2[3];
+  float dpre[4] = {0.f, 0.f, 0.f, 0.f};
+  mma3(dpre, dm2, wt.W2T);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dpre[i] = m1[i] > 0.f ? dpre[i] : 0.f;
+  G.b1[0] += dpre[0] + dpre[2]; G.b1[1] += dpre[1] + dpre[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dx[i] = ado[i];
+  mma3(dx, dpre, wt.W1T);
+  const int qbase = lane & ~3;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float2 dmb[2] = {make_float2(dm2[2 * r], dm2[2 * r]), make_float2(dm2[2 * r + 1], dm2[2 * r + 1])};
+    const float2 dpb[2] = {make_float2(dpre[2 * r], dpre[2 * r]), make_float2(dpre[2 * r + 1], dpre[2 * r + 1])};
+#pragma unroll
+    for (int tq = 0; tq < 4; ++tq) {
+      const float2 mk = make_float2(__shfl_sync(0xffffffffu, m1[2 * r], qbase + tq),
+                                    __shfl_sync(0xffffffffu, m1[2 * r + 1], qbase + tq));
+      const float2 xk = make_float2(__shfl_sync(0xffffffffu, x[2 * r], qbase + tq),
+                                    __shfl_sync(0xffffffffu, x[2 * r + 1], qbase + tq));
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        G.W2p[tq][jj] = __ffma2_rn(mk, dmb[jj], G.W2p[tq][jj]);
+        G.W1p[tq][jj] = __ffma2_rn(xk, dpb[jj], G.W1p[tq][jj]);
+      }
+    }
+  }
+}
+
+// fixed-order reduction of a warp's weight-gradient accumulators into red[0..143]
+__device__ __forceinline__ void pf_reduce_grads(const FwaGrad& G, const LaneGeo& L, float* __restrict__ red) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float r1 = G.w1(k, jj), r2 = G.w2(k, jj);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (L.g == 0) { red[k * 8 + 2 * L.t + jj] = r1; red[72 + k * 8 + 2 * L.t + jj] = r2; }
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    float r1 = G.b1[jj], r2 = G.b2[jj];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (L.g == 0) { red[64 + 2 * L.t + jj] = r1; red[136 + 2 * L.t + jj] = r2; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the warp's sequence of rounds: (sample b, first token r0, length ell); b >= B marks the end
+struct PfIter { int b, r0, ell; };
+
+template <int KIND>
+__global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const PfArgs A) {
+  constexpr bool BWD = KIND == 3;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FArgs& a = A.a;
+  const PfGeo& g = A.g;
+  LaneGeo L; L.init();
+  const int warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * PF_WARPS;
+  const int h = L.lane >> 4, c16 = L.lane & 15;
+  unsigned char* mine = smem + (size_t)warp * g.per_warp;
+  const FwaW wl = load_fwa_log2(a.dense, TLSAN_OFF_W1L, L.g, L.t);
+
+  const float gamma = a.dense[TLSAN_OFF_GAMMA];
+  auto ell_of = [&](int b) { return b < a.B ? __ldg(a.sl + b) : -1; };
+  auto ring = [&](int n) { return mine + g.o_ring + (n % 3) * g.ring; };
+  // copy the metadata of a round into ring slot `dst`: lane t < 16 serves token r0 + t
+  auto issue_meta = [&](const PfIter& it, unsigned char* dst) {
+    const int tok = it.r0 + c16;
+    if (h == 0 && tok < it.ell) {
+      cp16_s(smem_addr(dst) + c16 * 16, A.meta + (size_t)it.b * a.L + tok);
+      if (BWD) cp4_s(smem_addr(dst) + 256 + c16 * 4, a.inv + ((size_t)it.b << a.spsh) + tok);
+    }
+  };
+  // start the copies of a round into `buf` (its metadata has landed in ring slot `src`): tau, the token rows,
+  // (backward) the sample's record
+  auto issue_round = [&](const PfIter& it, const unsigned char* src, unsigned char* buf) {
+    const int cnt = min(PF_R, max(it.ell - it.r0, 0));
+    int4 m = make_int4(0, 0, 0, 0);
+    if (c16 < cnt) m = reinterpret_cast<const int4*>(src)[c16];
+    if (h == 0) reinterpret_cast<float*>(buf + g.o_tau)[c16] = gamma * __int_as_float(m.z);   // tau   (model.py:109)
+    // 16 lanes x 16 B per token (chunks 0-7 item row, 8-15 category row); two tokens per instruction
+    const uint32_t dst = smem_addr(buf) + h * 256 + c16 * 16;
+    const int col = (c16 & 7) * 4;
+    for (int tt = 0; tt < cnt; tt += 2) {
+      const int idt = __shfl_sync(0xffffffffu, m.x, tt + h), crt = __shfl_sync(0xffffffffu, m.y, tt + h);
+      if (tt + h < cnt) cp16_s(dst + tt * 256, a.emb + (size_t)(c16 < 8 ? idt : crt) * 32 + col);
+    }
+    if (BWD && it.r0 == 0 && it.ell >= 0) {                    // do_long | o_long | max | 1/den of the sample
+      const float* sc = a.scratch + (size_t)it.b * (TLSAN_SCR * 64);
+      cp16_s(smem_addr(buf + g.o_stats) + L.lane * 16, sc + L.lane * 4);
+      cp16_s(smem_addr(buf + g.o_stats) + 512 + L.lane * 16, sc + 128 + L.lane * 4);
+    }
+  };
+  auto advance = [&](const PfIter& it, int ell_next) {
+    PfIter n;
+    if (it.r0 + PF_R < it.ell) { n.b = it.b; n.r0 = it.r0 + PF_R; n.ell = it.ell; }
+    else { n.b = it.b + nw; n.r0 = 0; n.ell = ell_next; }
+    return n;
+  };
+
+  // ---- pipeline prologue: metadata of rounds 0 and 1, then the rows of round 0
+  PfIter it0, it1, it2;
+  it0.b = blockIdx.x * PF_WARPS + warp; it0.r0 = 0; it0.ell = ell_of(it0.b);
+  int eN = ell_of(it0.b + nw);                                  // length of the sample after the newest iterator's
+  it1 = advance(it0, eN);
+  if (it1.r0 == 0) eN = ell_of(it1.b + nw);
+  issue_meta(it0, ring(0));
+  issue_meta(it1, ring(1));
+  cp_commit();
+  cp_wait_group<0>();
+  __syncwarp();
+  issue_round(it0, ring(0), mine);
+  cp_commit();
+
+  // per-kernel state
+  SoftL2 st; st.init();
+  const FwaWT wlt = BWD ? load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t) : FwaWT();
+  FwaGrad G;
+  if (BWD) G.init();
+  float ggamma = 0.f, sq_acc = 0.f;
+  float o[2] = {0.f, 0.f}, kf[2] = {0.f, 0.f}, nmx[2] = {0.f, 0.f};
+
+  for (int n = 0; it0.b < a.B; ++n) {
+    unsigned char* buf = mine + (size_t)(n & 1) * g.buf;
+    cp_wait_group<0>();                                         // rows of round n + metadata of round n+1 (a round old)
+    __syncwarp();
+    // ---- next round's rows, the metadata of the round after it
+    issue_round(it1, ring(n + 1), mine + (size_t)((n + 1) & 1) * g.buf);
+    it2 = advance(it1, eN);
+    if (it2.r0 == 0) eN = ell_of(it2.b + nw);
+    issue_meta(it2, ring(n + 2));
+    cp_commit();
+
+    // ---- compute round n
+    const int cnt = min(PF_R, max(it0.ell - it0.r0, 0));
+    const float (*rows)[64] = reinterpret_cast<const float (*)[64]>(buf);
+    const float* tau = reinterpret_cast<const float*>(buf + g.o_tau);
+    if (!BWD) {
+      int j = 0;
+      for (; j + 2 < cnt; j += 4) {                            // 3 or 4 tokens: two independent tiles
+        const float4 t4 = *reinterpret_cast<const float4*>(tau + j);
+        const bool ok3 = j + 3 < cnt;
+        const float2 e0 = *reinterpret_cast<const float2*>(&rows[j][L.f0]);
+        const float2 e1 = *reinterpret_cast<const float2*>(&rows[j + 1][L.f0]);
+        const float2 e2 = *reinterpret_cast<const float2*>(&rows[j + 2][L.f0]);
+        const float2 e3 = ok3 ? *reinterpret_cast<const float2*>(&rows[j + 3][L.f0]) : make_float2(0.f, 0.f);
+        const float xa[4] = {e0.x * t4.x, e0.y * t4.x, e1.x * t4.y, e1.y * t4.y};
+        const float xb[4] = {e2.x * t4.z, e2.y * t4.z, ok3 ? e3.x * t4.w : 0.f, ok3 ? e3.y * t4.w : 0.f};
+        float m1a[4], m2a[4], m1b[4], m2b[4];
+        tile_maps(xa, wl, m1a, m2a);
+        tile_maps(xb, wl, m1b, m2b);
+        if (!ok3) { m2b[2] = -INFINITY; m2b[3] = -INFINITY; }
+        st.push4(m2a, xa, m2b, xb);
+      }
+      if (j < cnt) {                                           // 1 or 2 tokens
+        const bool okB = j + 1 < cnt;
+        const float tA = tau[j], tB = okB ? tau[j + 1] : 0.f;
+        const float2 eA = *reinterpret_cast<const float2*>(&rows[j][L.f0]);
+        const float2 eB = okB ? *reinterpret_cast<const float2*>(&rows[j + 1][L.f0]) : make_float2(0.f, 0.f);
+        const float x[4] = {eA.x * tA, eA.y * tA, eB.x * tB, eB.y * tB};
+        float m1t[4], m2t[4];
+        tile_maps(x, wl, m1t, m2t);
+        if (!okB) { m2t[2] = -INFINITY; m2t[3] = -INFINITY; }
+        st.push2(m2t, x);
+      }
+      if (it0.r0 + PF_R >= it0.ell) {                          // last round of the sample
+        float* sc = a.scratch + (size_t)it0.b * (TLSAN_SCR * 64) + L.f0;
+        const float i0 = st.den[0] > 0.f ? 1.f / st.den[0] : 0.f, i1 = st.den[1] > 0.f ? 1.f / st.den[1] : 0.f;
+        st2(sc + 64, st.acc[0] * i0, st.acc[1] * i1);          // o_long
+        st2(sc + 128, st.mx[0], st.mx[1]);                      // running max (log2 domain)
+        st2(sc + 192, i0, i1);                                  // 1 / denominator
+        st.init();
+      }
+    } else {
+      if (it0.r0 == 0) {
+        const float* sc = reinterpret_cast<const float*>(buf + g.o_stats) + L.f0;
+        const float2 dol2 = *reinterpret_cast<const float2*>(sc);
+        const float2 o2 = *reinterpret_cast<const float2*>(sc + 64);
+        const float2 mx2 = *reinterpret_cast<const float2*>(sc + 128);
+        const float2 inv2 = *reinterpret_cast<const float2*>(sc + 192);
+        o[0] = o2.x; o[1] = o2.y;
+        kf[0] = inv2.x * dol2.x; kf[1] = inv2.y * dol2.y;       // (1/den) * d out
+        nmx[0] = -mx2.x; nmx[1] = -mx2.y;
+      }
+      const unsigned char* mr = ring(n);                        // this round's metadata: {id, crow, P*hist_t, hist_t}, rank
+      const int* pos = reinterpret_cast<const int*>(mr + 256);
+      float* ru = a.rows_u + (size_t)it0.b * a.PU + 32;
+      float dtau_l = 0.f;                                       // lane j collects d tau of token r0 + j
+      for (int j = 0; j < cnt; j += 2) {
+        const bool okB = j + 1 < cnt;
+        const float tA = tau[j], tB = okB ? tau[j + 1] : 0.f;
+        const float2 eA = *reinterpret_cast<const float2*>(&rows[j][L.f0]);
+        const float2 eB = okB ? *reinterpret_cast<const float2*>(&rows[j + 1][L.f0]) : make_float2(0.f, 0.f);
+        const float x[4] = {eA.x * tA, eA.y * tA, eB.x * tB, eB.y * tB};
+        float dx[4];
+        tile_bwd_l2(x, okB, o, kf, nmx, wl, wlt, L.lane, dx, G);
+        // gradient of the gathered slices (tau * dX) and of tau (<dX, e>)
+        const float rA0 = dx[0] * tA, rA1 = dx[1] * tA;
+        sq_acc = fmaf(rA0, rA0, sq_acc); sq_acc = fmaf(rA1, rA1, sq_acc);
+        st2(a.rows_i + (size_t)pos[j] * 64 + L.f0, rA0, rA1);
+        const float dtA = warp_sum_f(fmaf(dx[0], eA.x, dx[1] * eA.y));
+        if (L.lane == j) dtau_l = dtA;
+        if (okB) {
+          const float rB0 = dx[2] * tB, rB1 = dx[3] * tB;
+          sq_acc = fmaf(rB0, rB0, sq_acc); sq_acc = fmaf(rB1, rB1, sq_acc);
+          st2(a.rows_i + (size_t)pos[j + 1] * 64 + L.f0, rB0, rB1);
+          const float dtB = warp_sum_f(fmaf(dx[2], eB.x, dx[3] * eB.y));
+          if (L.lane == j + 1) dtau_l = dtB;
+        }
+      }
+      if (L.lane < cnt) {
+        const int4 m = reinterpret_cast<const int4*>(mr)[L.lane];
+        ggamma = fmaf(dtau_l, __int_as_float(m.z), ggamma);    // d gamma += d tau * P[u,t] hist_t
+        const float dp = dtau_l * gamma * __int_as_float(m.w); // d usert_emb[u, t] = d tau * gamma * hist_t
+        sq_acc = fmaf(dp, dp, sq_acc);
+        ru[it0.r0 + L.lane] = dp;
+      }
+      if (it0.r0 + PF_R >= it0.ell)
+        for (int tt = max(it0.ell, 0) + L.lane; tt < a.PU - 32; tt += 32) ru[tt] = 0.f;
+    }
+    __syncwarp();                                               // buffer n % 2 / ring slot n % 3 may be overwritten
+    it0 = it1; it1 = it2;
+  }
+  cp_wait_group<0>();
+  if (!BWD) return;
+
+  // ---- per-CTA partial sums, fixed order: butterfly over g -> warps 0..7 -> global
+  __syncthreads();                                              // the buffers are dead: reuse them
+  float (*red)[160] = reinterpret_cast<float (*)[160]>(smem);
+  pf_reduce_grads(G, L, red[warp]);
+  {
+    const float r1 = warp_sum_f(ggamma), r2 = warp_sum_f(sq_acc);
+    if (L.lane == 0) { red[warp][144] = r1; red[warp][145] = r2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 146) {
+    float r = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < PF_WARPS; ++wv) r += red[wv][threadIdx.x];
+    const int dst = threadIdx.x < 144 ? TLSAN_OFF_W1L + threadIdx.x
+                                      : (threadIdx.x == 144 ? TLSAN_OFF_GAMMA : TLSAN_PART_SUMSQ);
+    a.part[(size_t)blockIdx.x * TLSAN_PART + dst] = r;
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+size_t tlsan_long_meta_bytes(int B, int L) { return (size_t)B * L * sizeof(int4); }
+
+int tlsan_launch_long_meta(const FArgs& a, void* meta, cudaStream_t st) {
+  const long long n = (long long)a.B * a.L;
+  k_long_meta<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<int4*>(meta));
+  TLSAN_CHECK_LAUNCH("k_long_meta");
+  return TLSAN_OK;
+}
+
+template <int KIND>
+static int launch_pf_long(const FArgs& a, const void* meta, int ctas_per_sm, int* grid_out, cudaStream_t st) {
+  PfArgs A;
+  A.a = a; A.meta = reinterpret_cast<const int4*>(meta); A.g = pf_geo(a.L, KIND == 3);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_long<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set = true;
+  }
+  const int need = (a.B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * ctas_per_sm;
+  const int gr = need < cap ? need : cap;
+  if (grid_out) *grid_out = gr;
+  k_pf_long<KIND><<<gr, PF_THREADS, A.g.total, st>>>(A);
+  TLSAN_CHECK_LAUNCH(KIND == 1 ? "k_pf_long<fwd>" : "k_pf_long<bwd>");
+  return TLSAN_OK;
+}
+
+// ctas_per_sm (forward): 3 fills the SM; 2 leaves room for the radix-sort kernels running beside it on the side stream
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st) {
+  return launch_pf_long<1>(a, meta, ctas_per_sm, nullptr, st);
+}
+int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st) {
+  return launch_pf_long<3>(a, meta, 2, grid_b, st);
+}

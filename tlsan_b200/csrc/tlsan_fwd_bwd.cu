@@ -583,7 +583,7 @@ FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tls
   a.invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
   a.emb = p.emb; a.usert = p.usert; a.item_b = p.item_b; a.dense = p.dense; a.icl = p.icl;
   a.u = b.u; a.i = b.i; a.i2 = b.i2; a.c = b.c; a.sl = b.sl; a.sl_new = b.sl_new;
-  a.hist_i = b.hist_i; a.hist_i_new = b.hist_i_new; a.y = b.y; a.hist_t = b.hist_t;
+  a.hist_i = b.hist_i; a.hist_i_new = b.hist_i_new; a.y = b.y; a.hist_t = b.hist_t; a.hist_d = b.hist_d;
   a.logits = nullptr; a.ut = nullptr; a.rows_i = nullptr; a.rows_u = nullptr; a.gscal = nullptr;
   a.scratch = nullptr; a.part = nullptr; a.inv = nullptr; a.spsh = 0;
   return a;

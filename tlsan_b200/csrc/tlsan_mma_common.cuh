@@ -191,13 +191,26 @@ struct LaneGeo {
   }
 };
 
+// float32(1/n), n = 0..12, exactly as the reference computes it: float64 1/n (build_dataset.py:20) rounded to
+// float32 by the store into the batch array (input.py:36,45); n = 0 (d < 2, unreachable) -> 0
+static __constant__ float c_bucket_w[13] = {0.f, (float)(1.0 / 1.0), (float)(1.0 / 2.0), (float)(1.0 / 3.0),
+                                            (float)(1.0 / 4.0), (float)(1.0 / 5.0), (float)(1.0 / 6.0),
+                                            (float)(1.0 / 7.0), (float)(1.0 / 8.0), (float)(1.0 / 9.0),
+                                            (float)(1.0 / 10.0), (float)(1.0 / 11.0), (float)(1.0 / 12.0)};
+// n = sum_j [d >= 2^j], j = 1..12  (build_dataset.py:16-21)  =  min(12, floor(log2 d)) for d >= 2
+__device__ __forceinline__ float bucket_weight(int d) {
+  const int n = d >= 2 ? min(12, 31 - __clz(d)) : 0;
+  return c_bucket_w[n];
+}
+
 // ---- token meta of up to 32 tokens, one per lane (coalesced), broadcast by shuffle
 struct LongMeta { int id, crow; float tau, pt, ht; };
 __device__ __forceinline__ LongMeta load_long_meta(const FArgs& a, int b, int u, int tt, int ell, float gamma) {
   LongMeta m;
   const bool ok = tt < ell;
   m.id = ok ? __ldg(a.hist_i + (size_t)b * a.L + tt) : 0;
-  m.ht = ok ? __ldg(a.hist_t + (size_t)b * a.L + tt) : 0.f;
+  if (a.hist_d) m.ht = ok ? bucket_weight(__ldg(a.hist_d + (size_t)b * a.L + tt)) : 0.f;   // bucketing fused into the gather
+  else m.ht = ok ? __ldg(a.hist_t + (size_t)b * a.L + tt) : 0.f;
   const float pu = ok ? __ldg(a.usert + (size_t)u * a.L + tt) : 0.f;
   m.pt = pu * m.ht;                  // P[u,t] * hist_t    (model.py:99)
   m.tau = gamma * m.pt;              // gamma * (...)      (model.py:109)

@@ -168,118 +168,12 @@ __global__ void k_seg_bounds(const int* __restrict__ keys, const int* __restrict
   for (int r = prev + 1; r <= cur; ++r) seg_off[r] = i;
 }
 
-static bool sort_count_selected() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TLSAN_SORT_IMPL"); v = (e && strcmp(e, "count") == 0) ? 1 : 0; }
-  return v == 1;
-}
-
 // which ping-pong buffer holds the sorted occurrence ids after the last pass (pass k writes b, a, b, ...)
 const int32_t* tlsan_sorted_vals(const TlsanWs& w, char* ws) {
-  if (sort_count_selected() && w.NR <= 262144) return reinterpret_cast<const int32_t*>(ws + w.vals_a);
   int bits = 1;
   while ((1ll << bits) < (long long)w.NR) ++bits;
   const int passes = (bits + 7) / 8;
   return reinterpret_cast<const int32_t*>(ws + ((passes & 1) ? w.vals_b : w.vals_a));
-}
-
-// ------------------------------------------------------------------ EXPERIMENTAL counting sort (default off)
-// TLSAN_SORT_IMPL=count -- written at the end of round 1 after the GPU budget was spent: it compiles but has NEVER
-// RUN.  The row key has only ~16 significant bits, so grouping needs no radix passes:
-//   k_count_rows   cnt[key]++ per valid occurrence (integer atomics: the totals do not depend on the order)
-//   k_count_scan   seg_off = exclusive scan of cnt (one CTA), nvalid
-//   k_count_place  tmp[seg_off[key] + fill[key]++] = occurrence id          (arbitrary order inside a segment)
-//   k_count_canon  one warp per row sorts its segment by occurrence id (rank by counting) -> vals, inv
-// The canonical order inside a segment is ascending occurrence id = what the stable radix sort produces, so the
-// outputs (vals, inv, seg_off) are identical to tlsan_launch_sort's and the step stays bit-reproducible.
-__global__ void __launch_bounds__(256) k_count_rows(const KeySrc src, long long nocc, int* __restrict__ cnt) {
-  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (g >= nocc) return;
-  const int key = occ_key(src, g);
-  if (key != TLSAN_INVALID_KEY) atomicAdd(cnt + key, 1);
-}
-
-__global__ void __launch_bounds__(1024) k_count_scan(const int* __restrict__ cnt, int NR, int* __restrict__ seg_off,
-                                                     int* __restrict__ nvalid) {
-  __shared__ int wsum[32];
-  const int per = (NR + 1023) / 1024;
-  const int lo = min(NR, (int)threadIdx.x * per), hi = min(NR, lo + per);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += cnt[i];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) wsum[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    int v = wsum[lane], t = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, t, o);
-      if (lane >= o) t += y;
-    }
-    wsum[lane] = t - v;                        // exclusive prefix of the warp totals
-    if (lane == 31) { seg_off[NR] = t; *nvalid = t; }
-  }
-  __syncthreads();
-  int run = wsum[warp] + x - s;                // exclusive prefix of this thread's slice
-  for (int i = lo; i < hi; ++i) { seg_off[i] = run; run += cnt[i]; }
-}
-
-__global__ void __launch_bounds__(256) k_count_place(const KeySrc src, long long nocc, const int* __restrict__ seg_off,
-                                                     int* __restrict__ fill, int* __restrict__ tmp) {
-  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (g >= nocc) return;
-  const int key = occ_key(src, g);
-  if (key != TLSAN_INVALID_KEY) tmp[seg_off[key] + atomicAdd(fill + key, 1)] = (int)g;
-}
-
-__global__ void __launch_bounds__(256) k_count_canon(int NR, const int* __restrict__ seg_off, const int* __restrict__ tmp,
-                                                     int* __restrict__ vals, int* __restrict__ inv) {
-  const int lane = threadIdx.x & 31;
-  const int W = gridDim.x * 8;
-  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < NR; r += W) {
-    const int lo = seg_off[r], n = seg_off[r + 1] - lo;
-    for (int base = 0; base < n; base += 32) {                 // my chunk: element base + lane
-      const bool have = base + lane < n;
-      const int mine = have ? tmp[lo + base + lane] : 0x7fffffff;
-      int rank = 0;
-      for (int c = 0; c < n; c += 32) {                        // every chunk of the segment
-        const int other = c + lane < n ? tmp[lo + c + lane] : 0x7fffffff;
-        const int m = min(32, n - c);
-        for (int j = 0; j < m; ++j) rank += __shfl_sync(0xffffffffu, other, j) < mine ? 1 : 0;
-      }
-      if (have) { vals[lo + rank] = mine; inv[mine] = lo + rank; }
-    }
-  }
-}
-
-static int launch_sort_count(const KeySrc& src, const TlsanWs& w, char* ws, const int32_t** sorted_vals,
-                             cudaStream_t st) {
-  int* cnt = reinterpret_cast<int*>(ws + w.row_cnt);
-  int* fill = reinterpret_cast<int*>(ws + w.row_fill);
-  int* tmp = reinterpret_cast<int*>(ws + w.vals_b);
-  int* vals = reinterpret_cast<int*>(ws + w.vals_a);
-  int* seg_off = reinterpret_cast<int*>(ws + w.seg_off);
-  TLSAN_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(w.NR + 2) * 4, st));
-  TLSAN_CHECK_CUDA(cudaMemsetAsync(fill, 0, (size_t)(w.NR + 2) * 4, st));
-  const unsigned gb = (unsigned)((w.nocc + 255) / 256);
-  k_count_rows<<<gb, 256, 0, st>>>(src, w.nocc, cnt);
-  TLSAN_CHECK_LAUNCH("k_count_rows");
-  k_count_scan<<<1, 1024, 0, st>>>(cnt, w.NR, seg_off, reinterpret_cast<int*>(ws + w.nvalid));
-  TLSAN_CHECK_LAUNCH("k_count_scan");
-  k_count_place<<<gb, 256, 0, st>>>(src, w.nocc, seg_off, fill, tmp);
-  TLSAN_CHECK_LAUNCH("k_count_place");
-  int cg = (w.NR + 7) / 8;
-  if (cg > tlsan_num_sms() * 8) cg = tlsan_num_sms() * 8;
-  k_count_canon<<<cg, 256, 0, st>>>(w.NR, seg_off, tmp, vals, reinterpret_cast<int*>(ws + w.inv));
-  TLSAN_CHECK_LAUNCH("k_count_canon");
-  *sorted_vals = vals;
-  return TLSAN_OK;
 }
 
 int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
@@ -296,7 +190,6 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
   src.B = d.B; src.L = d.L; src.S = d.S; src.spsh = w.SPSH; src.NI = d.NI; src.NC = d.NC; src.NR = w.NR;
   src.u = b.u; src.cand = b.i; src.c = b.c; src.sl = b.sl; src.sl_new = b.sl_new;
   src.hist_i = b.hist_i; src.hist_i_new = b.hist_i_new;
-  if (sort_count_selected() && w.NR <= 262144) return launch_sort_count(src, w, ws, sorted_vals, st);
   int bits = 1;
   while ((1ll << bits) < (long long)w.NR) ++bits;
   const int passes = (bits + 7) / 8;

@@ -5,6 +5,7 @@
 //   k_finalize2    global norm, clip scale, loss, SGD on the 4449 small parameters
 //   k_apply_rows / k_apply_cate   W <- W - lr * scale * (g_sparse + reg * W) for every table row
 //   k_label_rank   full-catalogue rank of the label item (model.py:140-156)
+#include <stdlib.h>
 #include "tlsan_common.cuh"
 
 // ------------------------------------------------------------------ segmented reduce
@@ -442,18 +443,28 @@ __device__ __forceinline__ void dp_signal_when_grid_done(int* counter, int* flag
 
 struct DpPeers { float* arena[16]; };
 
-// spin until every peer's flag `which` has reached `epoch` (bounded: a dead peer must not hang the GPU)
-__device__ __forceinline__ void dp_wait(const DpPeers& peers, long long flag_off, int which, int world, int epoch,
-                                        int* err) {
+// spin until every peer's flag `which` has reached `epoch`.  Bounded (a dead peer must not hang the GPU): after
+// `timeout_ns` the sticky error word is raised and the caller's kernel SKIPS its work -- the weights of this rank
+// stay as they were and stats[TLSAN_STAT_DP_ERR] tells the host.  Returns false on (any earlier) error.
+__device__ __forceinline__ bool dp_wait(const DpPeers& peers, long long flag_off, int which, int world, int epoch,
+                                        int* err, long long timeout_ns) {
   if (threadIdx.x < world) {
     const int* f = reinterpret_cast<const int*>(peers.arena[threadIdx.x] + flag_off) + which;
-    const long long t0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (ld_flag(f) < epoch) {
-      if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if ((long long)(t1 - t0) > timeout_ns || *reinterpret_cast<volatile int*>(err)) { atomicExch(err, 1); break; }
       __nanosleep(64);
     }
   }
   __syncthreads();
+  return *reinterpret_cast<volatile int*>(err) == 0;
+}
+static long long dp_timeout_ns() {
+  static long long v = 0;
+  if (!v) { const char* e = getenv("TLSAN_DP_TIMEOUT_S"); const double s = e ? atof(e) : 30.0; v = (long long)((s > 0 ? s : 30.0) * 1e9); }
+  return v;
 }
 
 // category gradient of category k (item-row cate halves in CSR order + the direct u_cate row) -> item half of flat
@@ -479,8 +490,12 @@ __global__ void __launch_bounds__(256) k_dp_reduce_cate(int NI, float* __restric
 
 // dense gradients + loss / norm partials summed over ranks (fixed order) into the partial-row layout k_finalize2 reads
 __global__ void __launch_bounds__(1024) k_dp_dense_sum(DpPeers peers, DpLayout y, long long f_dgrad, int world, int epoch,
-                                                       float* __restrict__ dtot, int* __restrict__ err) {
-  dp_wait(peers, y.flat_count + y.chunk, 0, world, epoch, err);
+                                                       float* __restrict__ dtot, int* __restrict__ err,
+                                                       long long timeout_ns, float* __restrict__ stats) {
+  if (!dp_wait(peers, y.flat_count + y.chunk, 0, world, epoch, err, timeout_ns)) {
+    if (threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
+    return;
+  }
   for (int e = threadIdx.x; e < TLSAN_PART; e += 1024) {
     if (e < TLSAN_DENSE_COUNT || e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ) {
       float v[16];                       // every peer's word in flight together, then the fixed-order sum
@@ -521,7 +536,9 @@ __device__ __forceinline__ float4 dp_grad4(const float* __restrict__ flat, long 
 __global__ void __launch_bounds__(256) k_dp_apply_slice(DpPeers peers, DpLayout y, int rank, int world, int NIC, int NU,
                                                         int L, int PU, long long f_gb, long long f_gu,
                                                         float* __restrict__ wflat, float lr, float reg,
-                                                        const float* __restrict__ stats, int epoch) {
+                                                        const float* __restrict__ stats, int epoch,
+                                                        const int* __restrict__ err) {
+  if (*reinterpret_cast<const volatile int*>(err)) return;      // a wait timed out: leave the weights untouched
   const float scale = stats[TLSAN_STAT_SCALE];
   const long long lo = (long long)rank * y.chunk, hi = min(lo + y.chunk, y.n_tab);
   float* wnew = peers.arena[rank] + y.flat_count;
@@ -549,8 +566,12 @@ __global__ void __launch_bounds__(256) k_dp_apply_slice(DpPeers peers, DpLayout 
 
 // the other ranks' updated slices -> local weights
 __global__ void __launch_bounds__(256) k_dp_gather(DpPeers peers, DpLayout y, int rank, int world, int epoch,
-                                                   float* __restrict__ wflat, int* __restrict__ err) {
-  dp_wait(peers, y.flat_count + y.chunk, 1, world, epoch, err);
+                                                   float* __restrict__ wflat, int* __restrict__ err,
+                                                   long long timeout_ns, float* __restrict__ stats) {
+  if (!dp_wait(peers, y.flat_count + y.chunk, 1, world, epoch, err, timeout_ns)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
+    return;
+  }
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (int p = 0; p < world; ++p) {
     if (p == rank) continue;
@@ -581,7 +602,7 @@ int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, con
   k_dp_reduce_cate<<<d.NC, 256, 0, st>>>(d.NI, flat + w.f_gi, p.cate_off, p.cate_items, flags, epoch);
   TLSAN_CHECK_LAUNCH("k_dp_reduce_cate");
   float* dtot = reinterpret_cast<float*>(ws + w.part_a);          // the per-CTA partials are consumed by now
-  k_dp_dense_sum<<<1, 1024, 0, st>>>(peers, y, (long long)w.f_dgrad, world, epoch, dtot, err);
+  k_dp_dense_sum<<<1, 1024, 0, st>>>(peers, y, (long long)w.f_dgrad, world, epoch, dtot, err, dp_timeout_ns(), stats);
   TLSAN_CHECK_LAUNCH("k_dp_dense_sum");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
   k_finalize2<<<1, 1024, 0, st>>>(dtot, reinterpret_cast<float*>(ws + w.tsq), tsq_grid(), nullptr, 0, invB, lr, reg,
@@ -589,9 +610,9 @@ int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, con
   TLSAN_CHECK_LAUNCH("k_finalize2");
   k_dp_apply_slice<<<tlsan_num_sms() * 4, 256, 0, st>>>(peers, y, rank, world, d.NI + d.NC, d.NU, d.L, w.PU,
                                                         (long long)w.f_gb, (long long)w.f_gu, p.emb, lr, reg, stats,
-                                                        epoch);
+                                                        epoch, err);
   TLSAN_CHECK_LAUNCH("k_dp_apply_slice");
-  k_dp_gather<<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, epoch, p.emb, err);
+  k_dp_gather<<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, epoch, p.emb, err, dp_timeout_ns(), stats);
   TLSAN_CHECK_LAUNCH("k_dp_gather");
   return TLSAN_OK;
 }

@@ -10,7 +10,8 @@ Same constructor and methods as the reference class (TLSAN/model.py:13-313):
     global_step / global_epoch_step / global_epoch_step_op (``.eval()``)
 
 ``sess`` is accepted and ignored (there is no TF session).  ``batch`` is the 9-tuple of
-TLSAN/input.py:54,107 (lists / numpy, any integer dtype): it is packed into ONE pinned host
+TLSAN/input.py:54,107 (lists / numpy, any integer dtype; element 5 may also be the RAW integer day gaps
+d[B,L] -- then proc_time_emb of build_dataset.py:16-21 runs inside the gather kernels): it is packed into ONE pinned host
 buffer, copied host->device once and handed to the CUDA kernels through the C ABI of
 include/tlsan_b200.h.  There is no CPU path: without the CUDA library every compute method
 raises.  PyTorch is used for device memory, streams and torch.distributed only.
@@ -77,14 +78,15 @@ class _IncrOp:
 class DeviceBatch:
     """A batch resident in HBM: one packed int32 buffer + the C struct pointing into it."""
 
-    def __init__(self, buf, B, L, S, offs, is_test):
-        self.buf, self.B, self.L, self.S, self.is_test = buf, B, L, S, is_test
+    def __init__(self, buf, B, L, S, offs, is_test, raw_gaps=False):
+        self.buf, self.B, self.L, self.S, self.is_test, self.raw_gaps = buf, B, L, S, is_test, raw_gaps
         base = buf.data_ptr()
         p = lambda k: base + 4 * offs[k]
         self.offs = offs
         self.c = Batch(u=p("u"), i=p("i"), i2=p("second") if is_test else None,
                        y=None if is_test else p("second"), hist_i=p("hist_i"), hist_i_new=p("hist_i_new"),
-                       hist_t=p("hist_t"), sl=p("sl"), sl_new=p("sl_new"), c=p("c"))
+                       hist_t=p("hist_t"), sl=p("sl"), sl_new=p("sl_new"), c=p("c"),
+                       hist_d=p("hist_t") if raw_gaps else None)     # raw int32 day gaps travel in the hist_t words
         self.nbytes = buf.numel() * 4
 
 
@@ -110,7 +112,11 @@ def pack_batch(lib, batch, dims, is_test, out, validate=True, dev_ptr=None, stre
     hist_i_new = i64(batch[4])
     if hist_i_new.shape[1] == 0:
         hist_i_new = np.zeros((B, 1), np.int64)
-    hist_t = np.ascontiguousarray(batch[5], dtype=np.float32)
+    if np.issubdtype(np.asarray(batch[5]).dtype, np.integer):
+        # raw day gaps d = cur_day - day + 1 (0 = padding): same 4-byte words, bucketed on the GPU while gathering
+        hist_t = np.ascontiguousarray(batch[5], dtype=np.int32).view(np.float32)
+    else:
+        hist_t = np.ascontiguousarray(batch[5], dtype=np.float32)
     i2 = i64(batch[2]) if is_test else None
     y = None if is_test else np.ascontiguousarray(batch[2], dtype=np.float32)
     if hist_i.shape != (B, dims.L) or hist_t.shape != (B, dims.L) or hist_i_new.shape != (B, S):
@@ -169,6 +175,10 @@ class Model(object):
             raise ValueError("dp_mode must be 'p2p' or 'nccl'")
         self._arenas = None
         self._dp_epoch = 0
+        self._dp_steps_unchecked = 0
+        # the peer-memory exchange spins (bounded) on its peers' flags; a timed-out step skips its update and raises
+        # TLSAN_STAT_DP_ERR, which is read back (one 4-byte D2H) every `dp_check_every` steps
+        self.dp_check_every = int(os.environ.get("TLSAN_DP_CHECK_EVERY", "64"))
 
         icl = np.ascontiguousarray(np.asarray(item_cate_list, dtype=np.int32))
         if icl.shape != (self.NI,) or icl.min() < 0 or icl.max() >= self.NC:
@@ -263,7 +273,7 @@ class Model(object):
             if self._ws[slot] is not None:
                 torch.cuda.synchronize(self.device)      # the library's side streams may still be using the old one
             self._ws[slot] = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
-            if self._presorted is not None and self._presorted[4] == slot:
+            if self._presorted is not None and self._presorted[2] == slot:
                 self._presorted = None
         return self._ws[slot]
 
@@ -290,7 +300,8 @@ class Model(object):
         # bytes that actually crossed PCIe: everything but the padded session matrix, plus its ragged form
         n_new = int(np.clip(np.asarray(batch[7], dtype=np.int64), 0, S).sum())
         self.last_h2d_bytes = 4 * (total - (B * S + 3) // 4 * 4 + B + n_new)
-        return DeviceBatch(dev, B, self.L, S, offs, is_test)
+        return DeviceBatch(dev, B, self.L, S, offs, is_test,
+                           raw_gaps=np.issubdtype(np.asarray(batch[5]).dtype, np.integer))
 
     # ------------------------------------------------------------------ training
     def train_staged(self, db, lr, global_batch=None, next_db=None):
@@ -298,12 +309,15 @@ class Model(object):
         (index with ``tlsan_b200._lib.STAT``) without synchronising.  ``next_db`` (optional) is the batch the
         NEXT call will train on: its occurrence sort is then enqueued behind this step's backward kernels
         (tlsan_*_pipelined), off the next step's critical path.  Results do not depend on it."""
-        Bg = global_batch if global_batch is not None else db.B * self.world
+        Bg = self._global_rows(db.B, global_batch)
         slot = self._ws_slot
         flags = 0
         if self._presorted is not None:
-            if self._presorted == (db.buf.data_ptr(), db.B, db.S, Bg, self._presorted[4]):
-                slot, flags = self._presorted[4], 2
+            # the announced batch is matched by IDENTITY (the model holds a reference, so its buffer can neither be
+            # freed under the presort kernels nor be recycled for a different batch at the same address)
+            pdb, pBg, pslot = self._presorted
+            if pdb is db and pBg == Bg:
+                slot, flags = pslot, 2
             self._presorted = None
         dims = self._dims(db.B, db.S, Bg, flags)
         ws = self._workspace(dims, slot)
@@ -311,6 +325,9 @@ class Model(object):
         nxt = None
         if next_db is not None:
             nBg = next_db.B * self.world if global_batch is None else global_batch
+            if self.world > 1 and global_batch is None and next_db.B != db.B:
+                next_db = None          # its global row count is unknown until its own step: no presort
+        if next_db is not None:
             ndims = self._dims(next_db.B, next_db.S, nBg)
             nws = self._workspace(ndims, 1 - slot)
             nxt = Next(dims=C.pointer(ndims), batch=C.pointer(next_db.c), workspace=nws.data_ptr(),
@@ -340,11 +357,35 @@ class Model(object):
                 check(self._lib.tlsan_apply_flat(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
                                                  self.reg, self.clip, ws.data_ptr(), ws.numel(),
                                                  self._stats.data_ptr(), st))
+        if self.world > 1 and self.dp_mode == "p2p" and self.world <= 16:
+            self._dp_steps_unchecked += 1
+            if self._dp_steps_unchecked >= self.dp_check_every:
+                self.check_dp_health()
         if next_db is not None:
-            self._presorted = (next_db.buf.data_ptr(), next_db.B, next_db.S, nBg, 1 - slot)
+            self._presorted = (next_db, nBg, 1 - slot)
             self._ws_slot = 1 - slot
         self.global_step.value += 1
         return self._stats
+
+    def _global_rows(self, B, global_batch):
+        """Denominator of reduce_mean (model.py:171) = rows of the GLOBAL batch.  One process: B.  Data parallel:
+        the caller's `global_batch`, else the sum of the ranks' row counts (one 8-byte all_reduce per step -- ranks
+        may hold uneven blocks, parallel.shard_rows, and the last batch of an epoch is ragged)."""
+        if global_batch is not None:
+            return int(global_batch)
+        if self.world == 1:
+            return B
+        t = torch.tensor([B], dtype=torch.int64, device=self.device)
+        torch.distributed.all_reduce(t, group=self.pg)
+        return int(t.item())
+
+    def check_dp_health(self):
+        """Raise if a peer-memory exchange step timed out waiting for a peer (that step left the weights
+        untouched on this rank; the replicas may have diverged)."""
+        self._dp_steps_unchecked = 0
+        if float(self._stats[STAT["dp_err"]].item()) != 0.0:
+            raise _lib.TlsanError("tlsan_dp_exchange: timed out waiting for a peer rank; the update of that step "
+                                  "was skipped on this rank -- replicas may have diverged, restore from a checkpoint")
 
     def __del__(self):
         # kernels on the library's side streams (sort, table norms, a presort of the next batch) may still be reading
@@ -377,10 +418,12 @@ class Model(object):
             self._arenas = ptrs
         return self._arenas
 
-    def train(self, sess, batch, lr, add_summary=False):
-        """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op]."""
+    def train(self, sess, batch, lr, add_summary=False, global_batch=None):
+        """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op].
+        Data parallel: `batch` is this rank's block of the global batch; `global_batch` = its total row count
+        (found with one small all_reduce when omitted)."""
         db = self.stage_batch(batch, is_test=False)
-        stats = self.train_staged(db, float(lr))
+        stats = self.train_staged(db, float(lr), global_batch=global_batch)
         loss = float(stats[STAT["loss"]].item())
         self.last_d2h_bytes = 4
         if add_summary and self.train_writer is not None:
@@ -500,15 +543,15 @@ class Model(object):
         checkpoint_path = os.path.join(self.config["model_dir"], "TLSAN")
         step = self.global_step.eval()
         save_path = "%s-%d" % (checkpoint_path, step)
-        torch.save({"variables": self.state_dict(), "global_step": step,
-                    "global_epoch_step": self.global_epoch_step.eval()}, save_path)
+        torch.save({"variables": OrderedDict(self.state_dict()), "global_step": int(step),
+                    "global_epoch_step": int(self.global_epoch_step.eval())}, save_path)
         json.dump(dict(self.config), open("%s-%d.json" % (checkpoint_path, step), "w"), indent=2)
         print("model saved at %s" % save_path, flush=True)
         return save_path
 
     def restore(self, sess, path):
         """Reference Model.restore (model.py:310-313)."""
-        ck = torch.load(path, weights_only=False)
+        ck = torch.load(path, map_location="cpu", weights_only=True)     # tensors + ints only: no unpickling of objects
         self.load_state_dict(ck["variables"])
         self.global_step.value = int(ck["global_step"])
         self.global_epoch_step.value = int(ck["global_epoch_step"])
