@@ -53,7 +53,7 @@ struct TlsanWs {
   int64_t nocc;
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
-  size_t rows_i, rows_u, gscal, scratch, meta;
+  size_t rows_i, rows_u, gscal, scratch, meta, smeta, sscal;
   size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
   size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
@@ -86,6 +86,8 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.gscal = take((size_t)d.B * 4);
   w.scratch = take((size_t)d.B * TLSAN_SCR * 64 * 4);
   w.meta = take((size_t)d.B * d.L * 16);       // resolved per-token metadata of the long-term sequence (k_long_meta)
+  w.smeta = take((size_t)d.B * (d.S + 2) * 8); // row pairs of candidate / user vector / session items
+  w.sscal = take((size_t)d.B * 16);            // per-sample scalars of the short-term kernel
   w.part_a = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_c = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);

@@ -390,7 +390,8 @@ static int launch_async(const FArgs& a, int* grid_out, cudaStream_t st) {
 int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
-int tlsan_launch_long_meta(const FArgs& a, void* meta, cudaStream_t st);                          // tlsan_fused_pf.cu
+int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st);   // tlsan_fused_pf.cu
+int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, int* grid_a, cudaStream_t st);
 int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st);
 int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st);
 
@@ -413,7 +414,9 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   int rc;
   void* meta = ws + w.meta;
-  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, st))) return rc;
+  void* smeta = ws + w.smeta;
+  void* sscal = ws + w.sscal;
+  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, st))) return rc;
   if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, long_ctas, st)
                          : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
     return rc;
@@ -422,7 +425,7 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
-  if ((rc = launch_async<2>(a, grid_a, st))) return rc;
+  if ((rc = variant == 2 ? tlsan_launch_short_pf(a, smeta, sscal, grid_a, st) : launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
   if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))
     return rc;

@@ -24,9 +24,12 @@
 //     gradient outer products from LDS.128 broadcasts instead of quad shuffles and reduced d tau through shared
 //     memory was measured and dropped: +25 % instructions after register allocation, profiles/experiments/.)
 //
-//   k_long_meta   per-token metadata of the long-term sequence                    (model.py:84-86,98-99,109)
+//   k_long_meta   per-token metadata of the long-term sequence and of the session / candidate / user rows
+//                                                                                  (model.py:84-86,98-99,109)
 //   k_pf_long<1>  long-term FWA forward -> o_long + softmax statistics (scratch)  (model.py:98-109,334-345)
 //   k_pf_long<3>  backward of the long-term FWA and of the time-aware position term
+//   k_pf_short    short-term FWA forward + logit + loss + backward of logit / short FWA, same pipeline, one
+//                 sample per round                                                 (model.py:135-137,164-172,350-364)
 #include <stdlib.h>
 #include "tlsan_mma_common.cuh"
 
@@ -69,6 +72,9 @@ __device__ __forceinline__ void cp16_s(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp4_s(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp8_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,19 +96,46 @@ __device__ __forceinline__ FwaW load_fwa_log2(const float* __restrict__ dense, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pre-pass: one thread per (sample, history slot)
-__global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)a.B * a.L) return;
-  const int b = (int)(idx / a.L), t = (int)(idx - (long long)b * a.L);
-  int4 m = make_int4(0, 0, 0, 0);
-  if (t < __ldg(a.sl + b)) {
-    const int id = __ldg(a.hist_i + idx);
-    const float ht = a.hist_d ? bucket_weight(__ldg(a.hist_d + idx)) : __ldg(a.hist_t + idx);   // bucketing fused
-    const float pt = __ldg(a.usert + (size_t)__ldg(a.u + b) * a.L + t) * ht;                   // model.py:99
-    m = make_int4(id, a.NI + __ldg(a.icl + id), __float_as_int(pt), __float_as_int(ht));
+// pre-pass: B x L threads resolve the long-term history (one token each), then B threads the short-term kernel's
+// rows (one sample each; smeta == NULL: scoring, long-term part only).  smeta[b][0] = candidate, [1] = user vector,
+// [2 + j] = session item j, each {row of the item / user half, row of the category half};
+// sscal[b] = {sl_new, candidate, y, item_b[candidate]}
+__global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta, int2* __restrict__ smeta,
+                                                   int4* __restrict__ sscal) {
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nlong = (long long)a.B * a.L;
+  if (gidx < nlong) {
+    const int b = (int)(gidx / a.L), t = (int)(gidx - (long long)b * a.L);
+    int4 m = make_int4(0, 0, 0, 0);
+    if (t < __ldg(a.sl + b)) {
+      const int id = __ldg(a.hist_i + gidx);
+      const float ht = a.hist_d ? bucket_weight(__ldg(a.hist_d + gidx)) : __ldg(a.hist_t + gidx);   // bucketing fused
+      const float pt = __ldg(a.usert + (size_t)__ldg(a.u + b) * a.L + t) * ht;                     // model.py:99
+      m = make_int4(id, a.NI + __ldg(a.icl + id), __float_as_int(pt), __float_as_int(ht));
+    }
+    meta[gidx] = m;
+    return;
   }
-  meta[idx] = m;
+  const long long bb = gidx - nlong;
+  if (!smeta || bb >= a.B) return;
+  const int b = (int)bb;
+  const int cand = __ldg(a.i + b), u = __ldg(a.u + b), uc = __ldg(a.c + b), s = min(__ldg(a.sl_new + b), a.S);
+  const float y = __ldg(a.y + b);
+  int2* out = smeta + (size_t)b * (a.S + 2);
+  const int* hn = a.hist_i_new + (size_t)b * a.S;
+  int id0 = s > 0 ? __ldg(hn) : 0, id1 = s > 1 ? __ldg(hn + 1) : 0;          // 96 % of the sessions hold <= 2 items
+  const int ccand = __ldg(a.icl + cand);
+  const float ib = __ldg(a.item_b + cand);
+  const int c0 = __ldg(a.icl + id0), c1 = __ldg(a.icl + id1);
+  out[0] = make_int2(cand, a.NI + ccand);
+  out[1] = make_int2(a.NI + a.NC + u, a.NI + uc);
+  if (s > 0) out[2] = make_int2(id0, a.NI + c0);
+  if (s > 1) out[3] = make_int2(id1, a.NI + c1);
+  for (int j = 2; j < s; ++j) {
+    const int id = __ldg(hn + j);
+    out[2 + j] = make_int2(id, a.NI + __ldg(a.icl + id));
+  }
+  sscal[b] = make_int4(s, cand, __float_as_int(y), __float_as_int(ib));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -409,12 +442,192 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// short-term kernel: one sample per pipeline step.  Buffer = { rows[PS_RS + 2][64] : staged session items, candidate,
+// user vector ; z[64] } ; ring slot = { int4 scalars ; int2 rows[2 + 32] ; int rank[2 + 32] }.
+#define PS_RS 6        // session items whose rows are staged (99.5 % of the sessions; longer ones gather the rest directly)
+struct PsArgs {
+  FArgs a;
+  const int2* smeta;        // [B][S + 2]
+  const int4* sscal;        // [B]
+};
+#define PS_BUF ((PS_RS + 2) * 256 + 256)
+#define PS_RING (16 + 34 * 8 + 34 * 4 + 8)
+#define PS_PER_WARP ((2 * PS_BUF + 3 * PS_RING + 127) / 128 * 128)
+
+__global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FArgs& a = A.a;
+  LaneGeo L; L.init();
+  const int warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * PF_WARPS;
+  const int h = L.lane >> 4, c16 = L.lane & 15;
+  unsigned char* mine = smem + (size_t)warp * PS_PER_WARP;
+  const FwaW w = load_fwa_log2(a.dense, TLSAN_OFF_W1S, L.g, L.t);
+  const FwaWT wt = load_fwa_t(a.dense, TLSAN_OFF_W1S, L.g, L.t);
+  FwaGrad G; G.init();
+  float loss_acc = 0.f, sq_acc = 0.f;
+  auto ring = [&](int n) { return mine + 2 * PS_BUF + (n % 3) * PS_RING; };
+  const int SW = a.S + 2;
+  // metadata of sample b -> ring slot: scalars, the row pairs and the sorted ranks of its first 34 slots
+  auto issue_meta = [&](int b, unsigned char* dst) {
+    if (b >= a.B) return;
+    if (L.lane == 0) cp16_s(smem_addr(dst), A.sscal + b);
+    const uint32_t rp = smem_addr(dst) + 16, pp = rp + 34 * 8;
+    for (int k = L.lane; k < min(SW, 34); k += 32) {
+      cp8_s(rp + k * 8, A.smeta + (size_t)b * SW + k);
+      // slot order of the occurrence sort: session item j -> L + j, candidate -> L + S, virtual (u_cate) -> L + S + 1
+      const int slot = k == 0 ? a.L + a.S : k == 1 ? a.L + a.S + 1 : a.L + (k - 2);
+      cp4_s(pp + k * 4, a.inv + ((size_t)b << a.spsh) + slot);
+    }
+  };
+  // rows of sample b (metadata in ring slot `src`) -> buffer
+  auto issue_rows = [&](int b, const unsigned char* src, unsigned char* buf) {
+    if (b >= a.B) return;
+    const int s = reinterpret_cast<const int*>(src)[0];
+    const int2* rp = reinterpret_cast<const int2*>(src + 16);
+    // staged row r: 0..PS_RS-1 = session items, PS_RS = candidate, PS_RS + 1 = user vector; 16 lanes x 16 B per row
+    const int n = min(s, PS_RS);
+    const uint32_t dst = smem_addr(buf) + c16 * 16;
+    const int col = (c16 & 7) * 4;
+    for (int r = h; r < n; r += 2) {
+      const int2 p = rp[2 + r];
+      cp16_s(dst + r * 256, a.emb + (size_t)(c16 < 8 ? p.x : p.y) * 32 + col);
+    }
+    {
+      const int2 p = rp[h];                                     // half 0: candidate, half 1: user vector
+      cp16_s(dst + (PS_RS + h) * 256, a.emb + (size_t)(c16 < 8 ? p.x : p.y) * 32 + col);
+    }
+    if (h == 0) cp16_s(dst + (PS_RS + 2) * 256, a.scratch + (size_t)b * (TLSAN_SCR * 64) + 320 + c16 * 4);   // z
+  };
+
+  int b0 = blockIdx.x * PF_WARPS + warp;
+  issue_meta(b0, ring(0));
+  issue_meta(b0 + nw, ring(1));
+  cp_commit();
+  cp_wait_group<0>();
+  __syncwarp();
+  issue_rows(b0, ring(0), mine);
+  cp_commit();
+
+  for (int n = 0; b0 < a.B; ++n, b0 += nw) {
+    const int b = b0;
+    unsigned char* buf = mine + (size_t)(n & 1) * PS_BUF;
+    cp_wait_group<0>();
+    __syncwarp();
+    issue_rows(b + nw, ring(n + 1), mine + (size_t)((n + 1) & 1) * PS_BUF);
+    issue_meta(b + 2 * nw, ring(n + 2));
+    cp_commit();
+
+    const unsigned char* mr = ring(n);
+    const int4 sc4 = *reinterpret_cast<const int4*>(mr);
+    const int s = sc4.x;
+    const float yb = __int_as_float(sc4.z), ib = __int_as_float(sc4.w);
+    const int2* rp = reinterpret_cast<const int2*>(mr + 16);
+    const int* pos = reinterpret_cast<const int*>(mr + 16 + 34 * 8);
+    const float (*rows)[64] = reinterpret_cast<const float (*)[64]>(buf);
+    const int ntok = s + 1;
+    const float2 zz = *reinterpret_cast<const float2*>(&rows[PS_RS + 2][L.f0]);
+    const float z[2] = {zz.x, zz.y};
+    // token n >= 1 is session item n-1: staged row, else direct gather
+    auto item_x = [&](int it) -> float2 {
+      if (it < PS_RS) return *reinterpret_cast<const float2*>(&rows[it][L.f0]);
+      int id, cr;
+      if (it < 32) { const int2 p = rp[2 + it]; id = p.x; cr = p.y; }
+      else { id = __ldg(a.hist_i_new + (size_t)b * a.S + it); cr = a.NI + __ldg(a.icl + id); }
+      return ldg2(a.emb + (size_t)(L.half ? cr : id) * 32 + L.col);
+    };
+    // ================= short-term FWA forward over [z ; e(hist_i_new)] (model.py:350-364)
+    SoftL2 ss; ss.init();
+    for (int k = 0; k < ntok; k += 2) {
+      const bool okB = k + 1 < ntok;
+      float x[4];
+      if (k == 0) { x[0] = z[0]; x[1] = z[1]; } else { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
+      if (okB) { const float2 e = item_x(k); x[2] = e.x; x[3] = e.y; } else { x[2] = 0.f; x[3] = 0.f; }
+      float m1[4], m2[4];
+      tile_maps(x, w, m1, m2);
+      if (!okB) { m2[2] = -INFINITY; m2[3] = -INFINITY; }
+      ss.push2(m2, x);
+    }
+    const float inv_s[2] = {1.f / ss.den[0], 1.f / ss.den[1]};
+    const float v[2] = {ss.acc[0] * inv_s[0], ss.acc[1] * inv_s[1]};
+    // ---- user vector, candidate, logit (model.py:84-95,135-137)
+    const float2 q = *reinterpret_cast<const float2*>(&rows[PS_RS][L.f0]);
+    const float2 p = *reinterpret_cast<const float2*>(&rows[PS_RS + 1][L.f0]);
+    const float ut[2] = {v[0] + p.x, v[1] + p.y};
+    const float logit = warp_sum_f(fmaf(ut[0], q.x, ut[1] * q.y)) + ib;
+    // ---- sigmoid cross entropy (model.py:171) and its gradient through reduce_mean
+    const float ex = expf(-fabsf(logit));
+    const float bce = fmaxf(logit, 0.f) - logit * yb + log1pf(ex);
+    const float sig = logit >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
+    const float gl = (sig - yb) * a.invB;
+    if (L.lane == 0) { loss_acc += bce; sq_acc = fmaf(gl, gl, sq_acc); a.gscal[b] = gl; }
+    // gradient-row destinations: ring rank k = 0 candidate, 1 virtual (u_cate), 2 + j session item j
+    auto slot_row = [&](int k) -> float* {
+      const int ps = k < 34 ? pos[k] : __ldg(a.inv + ((size_t)b << a.spsh) + a.L + (k - 2));
+      return a.rows_i + (size_t)ps * 64 + L.f0;
+    };
+    const float dq[2] = {gl * ut[0], gl * ut[1]};
+    const float du[2] = {gl * q.x, gl * q.y};
+    sq_acc = fmaf(dq[0], dq[0], sq_acc); sq_acc = fmaf(dq[1], dq[1], sq_acc);
+    sq_acc = fmaf(du[0], du[0], sq_acc); sq_acc = fmaf(du[1], du[1], sq_acc);
+    st2(slot_row(0), dq[0], dq[1]);                                       // -> item_emb[i] | cate_emb[icl[i]]
+    float* rvirt = slot_row(1);
+    if (L.half) st2(rvirt, du[0], du[1]);                                 // -> cate_emb[u_cate]
+    else { st2(rvirt, 0.f, 0.f); st2(a.rows_u + (size_t)b * a.PU + L.f0, du[0], du[1]); }  // -> user_emb[u]
+    // ---- short-term FWA backward, d v = du
+    const float kf[2] = {inv_s[0] * du[0], inv_s[1] * du[1]};
+    const float nmx[2] = {-ss.mx[0], -ss.mx[1]};
+    float dz[2] = {0.f, 0.f};
+    for (int k = 0; k < ntok; k += 2) {
+      const bool okB = k + 1 < ntok;
+      float x[4], dx[4];
+      if (k == 0) { x[0] = z[0]; x[1] = z[1]; } else { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
+      if (okB) { const float2 e = item_x(k); x[2] = e.x; x[3] = e.y; } else { x[2] = 0.f; x[3] = 0.f; }
+      tile_bwd_l2(x, okB, v, kf, nmx, w, wt, L.lane, dx, G);
+      if (k == 0) { dz[0] = dx[0]; dz[1] = dx[1]; }
+      else {
+        sq_acc = fmaf(dx[0], dx[0], sq_acc); sq_acc = fmaf(dx[1], dx[1], sq_acc);
+        st2(slot_row(2 + k - 1), dx[0], dx[1]);
+      }
+      if (okB) {
+        sq_acc = fmaf(dx[2], dx[2], sq_acc); sq_acc = fmaf(dx[3], dx[3], sq_acc);
+        st2(slot_row(2 + k), dx[2], dx[3]);
+      }
+    }
+    st2(a.scratch + (size_t)b * (TLSAN_SCR * 64) + 256 + L.f0, dz[0], dz[1]);   // -> k_dense_bwd_mma
+    __syncwarp();
+  }
+  cp_wait_group<0>();
+
+  // ---- per-CTA partial sums, fixed order: butterfly over g -> warps 0..7 -> global
+  __syncthreads();
+  float (*red)[160] = reinterpret_cast<float (*)[160]>(smem);
+  pf_reduce_grads(G, L, red[warp]);
+  {
+    const float r1 = warp_sum_f(loss_acc), r2 = warp_sum_f(sq_acc);
+    if (L.lane == 0) { red[warp][144] = r1; red[warp][145] = r2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 146) {
+    float r = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < PF_WARPS; ++wv) r += red[wv][threadIdx.x];
+    const int dst = threadIdx.x < 144 ? TLSAN_OFF_W1S + threadIdx.x
+                                      : (threadIdx.x == 144 ? TLSAN_PART_LOSS : TLSAN_PART_SUMSQ);
+    a.part[(size_t)blockIdx.x * TLSAN_PART + dst] = r;
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 size_t tlsan_long_meta_bytes(int B, int L) { return (size_t)B * L * sizeof(int4); }
 
-int tlsan_launch_long_meta(const FArgs& a, void* meta, cudaStream_t st) {
-  const long long n = (long long)a.B * a.L;
-  k_long_meta<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<int4*>(meta));
+// smeta / sscal may be NULL (scoring: long-term part only)
+int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st) {
+  const long long n = (long long)a.B * a.L + (smeta ? a.B : 0);
+  k_long_meta<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<int4*>(meta), reinterpret_cast<int2*>(smeta),
+                                                          reinterpret_cast<int4*>(sscal));
   TLSAN_CHECK_LAUNCH("k_long_meta");
   return TLSAN_OK;
 }
@@ -442,4 +655,21 @@ int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, 
 }
 int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st) {
   return launch_pf_long<3>(a, meta, 2, grid_b, st);
+}
+
+int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, int* grid_a, cudaStream_t st) {
+  PsArgs A;
+  A.a = a; A.smeta = reinterpret_cast<const int2*>(smeta); A.sscal = reinterpret_cast<const int4*>(sscal);
+  const int smem = PS_PER_WARP * PF_WARPS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_short, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int need = (a.B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * 2;
+  const int gr = need < cap ? need : cap;
+  if (grid_a) *grid_a = gr;
+  k_pf_short<<<gr, PF_THREADS, smem, st>>>(A);
+  TLSAN_CHECK_LAUNCH("k_pf_short");
+  return TLSAN_OK;
 }
