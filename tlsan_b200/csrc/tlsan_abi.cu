@@ -52,7 +52,7 @@ static bool use_mma() { return fused_impl() >= 1; }
 // The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
 // onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
 // events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
-struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr; };
+struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
 static SideStream* side_stream() {
   static SideStream per_dev[64];
   static int enabled = -1;
@@ -70,6 +70,7 @@ static SideStream* side_stream() {
     if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, lo) != cudaSuccess ||   // presort: fills gaps
         cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.part, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
       s.st = nullptr;
@@ -82,14 +83,16 @@ static bool g_prof_overlap = false;   // the recorded steps ran the sort on the 
 
 // Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
 // one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
-struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr; bool valid = false; };
+struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr, ev_part = nullptr; bool valid = false; };
 static Presort g_presort[32];
 static Presort* presort_slot(char* ws, bool create) {
   for (auto& e : g_presort) if (e.ws == ws) return &e;
   if (!create) return nullptr;
   for (auto& e : g_presort)
     if (!e.valid) {
-      if (!e.ev && cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (!e.ev && (cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&e.ev_part, cudaEventDisableTiming) != cudaSuccess))
+        return nullptr;
       e.ws = ws;
       return &e;
     }
@@ -179,9 +182,10 @@ int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_b
   return tlsan_launch_score(*dims, *p, *b, ncand, logits, ut, (cudaStream_t)stream);
 }
 
-// scratch [B][TLSAN_SCR][64] + per-token metadata [B][L] x 16 B, each 256-B aligned
+// scratch [B][TLSAN_SCR][64] + per-token metadata [B][L] x 16 B + the balanced partition, each 256-B aligned
 static size_t score_ws_bytes(const tlsan_dims_t* d) {
-  return tlsan_align_up((size_t)d->B * TLSAN_SCR * 64 * sizeof(float), 256) + (size_t)d->B * d->L * 16 + 512;
+  return tlsan_align_up((size_t)d->B * TLSAN_SCR * 64 * sizeof(float), 256) +
+         tlsan_align_up((size_t)d->B * d->L * 16, 256) + tlsan_partition_bytes() + 512;
 }
 
 int tlsan_score_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {
@@ -243,7 +247,8 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   const int32_t* sorted_vals = nullptr;
   tlsan_profile_mark(-1, st);
   SideStream* side = use_mma() ? side_stream() : nullptr;
-  cudaEvent_t sorted = nullptr;
+  cudaEvent_t sorted = nullptr, part_ready = nullptr;
+  const bool pf = fused_impl() == 4;                            // kernels that take the balanced partition
   int long_ctas = 3;
   // bit 1 = "the previous *_pipelined call announced this batch": honoured only if that call really enqueued the
   // presort (it does not when the side streams are off); otherwise the step sorts in place like a plain one
@@ -252,6 +257,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   if (presorted) {
     ps->valid = false;
     sorted = ps->ev;
+    if (pf) part_ready = ps->ev_part;
     sorted_vals = tlsan_sorted_vals(w, ws);
     tlsan_profile_mark(TLSAN_PHASE_SORT, st);
     if (with_tsq) {
@@ -268,6 +274,12 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
       // kernels may still be writing the sort buffers we are about to reuse
       if (stale->valid) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev, 0));
       stale->valid = false;
+    }
+    long_ctas = tlsan_overlap_ctas();
+    if (pf) {                                                   // balanced partition: first thing on the side stream
+      if ((rc = tlsan_launch_partition_batch(*dims, *p, *b, long_ctas, ws + w.part, side->st))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(side->part, side->st));
+      part_ready = side->part;
     }
     if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, side->st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
@@ -286,7 +298,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
     rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() - 2, sorted,
-                                    long_ctas, st);
+                                    part_ready, long_ctas, st);
   else if (fused_impl() == 1)
     rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, long_ctas, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
@@ -305,6 +317,10 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     const int32_t* unused = nullptr;
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
+    if (pf) {     // the consuming (presorted) step runs its forward kernel with 3 CTAs per SM
+      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, side->st2))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, side->st2));
+    }
     if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, side->st2))) return rc;
     TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev, side->st2));
     ps->valid = true;

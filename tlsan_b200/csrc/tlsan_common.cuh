@@ -53,12 +53,14 @@ struct TlsanWs {
   int64_t nocc;
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
-  size_t rows_i, rows_u, gscal, scratch, meta, smeta, sscal;
+  size_t rows_i, rows_u, gscal, scratch, meta, smeta, sscal, part;
   size_t part_a, part_b, part_c, tsq, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
   size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
   size_t total;
 };
+
+size_t tlsan_partition_bytes();
 
 static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   TlsanWs w;
@@ -88,6 +90,7 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.meta = take((size_t)d.B * d.L * 16);       // resolved per-token metadata of the long-term sequence (k_long_meta)
   w.smeta = take((size_t)d.B * (d.S + 2) * 8); // row pairs of candidate / user vector / session items
   w.sscal = take((size_t)d.B * 16);            // per-sample scalars of the short-term kernel
+  w.part = take(tlsan_partition_bytes());      // balanced partitions of the three pipelined kernels + their scratch
   w.part_a = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_c = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
@@ -124,7 +127,9 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
                              int long_ctas, cudaStream_t st);
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
-                               cudaEvent_t sorted, int long_ctas, cudaStream_t st);
+                               cudaEvent_t sorted, cudaEvent_t part_ready, int long_ctas, cudaStream_t st);
+int tlsan_launch_partition_batch(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int fwd_ctas,
+                                 void* part, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
                           float* logits, float* ut, float* scratch, cudaStream_t st);

@@ -391,9 +391,11 @@ int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st);   // tlsan_fused_pf.cu
-int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, int* grid_a, cudaStream_t st);
-int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st);
-int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st);
+int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int* grid_a,
+                          cudaStream_t st);
+int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st);
+int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, const void* part, int* grid_b, cudaStream_t st);
 
 // `hybrid` (default): per kernel, whichever formulation measured faster on B200 (profiles/):
 // synchronous gathers for the two long-term kernels (24 / 16 resident warps already hide the
@@ -404,7 +406,7 @@ int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cuda
 // domain there).  variant: 0 = async everywhere, 1 = hybrid, 2 = pf.
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
-                               cudaEvent_t sorted, int long_ctas, cudaStream_t st) {
+                               cudaEvent_t sorted, cudaEvent_t part_ready, int long_ctas, cudaStream_t st) {
   const bool hybrid = variant == 1;
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
@@ -416,8 +418,13 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   void* meta = ws + w.meta;
   void* smeta = ws + w.smeta;
   void* sscal = ws + w.sscal;
+  void* part = ws + w.part;
+  // the balanced partition depends on the batch only: the caller computed it beside the sort (part_ready), or asks
+  // for it here (no side stream)
+  if (variant == 2 && !part_ready && (rc = tlsan_launch_partition(a, long_ctas, true, part, st))) return rc;
   if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, st))) return rc;
-  if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, long_ctas, st)
+  if (variant == 2 && part_ready) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, part_ready, 0));
+  if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, part, long_ctas, st)
                          : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
@@ -425,13 +432,13 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
-  if ((rc = variant == 2 ? tlsan_launch_short_pf(a, smeta, sscal, grid_a, st) : launch_async<2>(a, grid_a, st))) return rc;
+  if ((rc = variant == 2 ? tlsan_launch_short_pf(a, smeta, sscal, part, grid_a, st) : launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
   if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
-  if ((rc = variant == 2 ? tlsan_launch_bwd_long_pf(a, meta, grid_b, st)
+  if ((rc = variant == 2 ? tlsan_launch_bwd_long_pf(a, meta, part, grid_b, st)
                          : hybrid ? tlsan_launch_bwd_long_mma(a, grid_b, st) : launch_async<3>(a, grid_b, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);

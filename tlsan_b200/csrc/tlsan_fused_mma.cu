@@ -654,7 +654,9 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
 }
 
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st);   // tlsan_fused_pf.cu
-int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st);
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st);
+int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
+size_t tlsan_partition_bytes();
 
 // scoring with a caller-provided scratch [B][TLSAN_SCR][64]: long FWA -> batched dense GEMM -> short FWA + logits
 int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int ncand,
@@ -665,8 +667,10 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
   static int use_ws = -1;
   if (use_ws < 0) { const char* e = getenv("TLSAN_FUSED_IMPL"); use_ws = (e && *e && strcmp(e, "pf") != 0) ? 0 : 1; }
   void* meta = reinterpret_cast<char*>(scratch) + tlsan_align_up((size_t)d.B * TLSAN_SCR * 64 * sizeof(float), 256);
+  void* part = reinterpret_cast<char*>(meta) + tlsan_align_up((size_t)d.B * d.L * 16, 256);
+  if (use_ws && (rc = tlsan_launch_partition(a, 3, false, part, st))) return rc;
   if (use_ws && (rc = tlsan_launch_long_meta(a, meta, nullptr, nullptr, st))) return rc;
-  if ((rc = use_ws ? tlsan_launch_long_fwd_pf(a, meta, 3, st) : tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
+  if ((rc = use_ws ? tlsan_launch_long_fwd_pf(a, meta, part, 3, st) : tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
   if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
   k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short score>");

@@ -63,6 +63,7 @@ static PfGeo pf_geo(int L, bool bwd) {
 struct PfArgs {
   FArgs a;
   const int4* meta;         // [B][L] {item row, category row, P*hist_t, hist_t}
+  const int* starts;        // [#warps + 1] balanced partition (k_partition)
   PfGeo g;
 };
 
@@ -136,6 +137,115 @@ __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restri
     out[2 + j] = make_int2(id, a.NI + __ldg(a.icl + id));
   }
   sscal[b] = make_int4(s, cand, __float_as_int(y), __float_as_int(ib));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Balanced static partition.  Samples differ in length (1..L history entries, 1..S session items), so dealing them
+// round-robin leaves the slowest of a few thousand warps ~30 % above the mean and every CTA waiting for its slowest
+// warp (ncu: 9 % of the backward's stall samples sat on the final barrier).  Instead warp w of a kernel with NW warps
+// takes the CONTIGUOUS range [starts[w], starts[w+1]) whose cost prefix sums are equal shares of the total:
+// starts[w] = min { b : P(b) >= floor(w * total / NW) }, P = exclusive prefix of cost.  The partition is a pure
+// function of the batch and the grid, so the per-warp summation order -- and every result bit -- stays reproducible.
+//   cost_long(b) = 2 ceil(sl / 2) + 2          cost_short(b) = 2 ceil((sl_new + 1) / 2) + 3        (tiles + overhead)
+struct PartArgs { const int* sl; const int* sl_new; int B; int nw[3]; int* starts[3]; };   // [0] fwd, [1] bwd, [2] short
+
+// Two small kernels.  k_part_scan (PART_CTAS CTAs): CTA c owns samples [c * per, (c+1) * per) -- per-chunk (8 samples)
+// exclusive prefixes LOCAL to the CTA and the CTA's total, for both cost kinds.  k_part_bounds: every CTA stages the
+// global chunk prefixes in shared memory (CTA totals are scanned on the fly), each thread places one boundary by
+// binary search over the chunks and a walk of at most 8 samples; comparisons are w * total <= P * nw + nw - 1
+// (no division).
+#define PART_CTAS 64
+#define PART_MAXB (200 * 1024)                                   // chunk prefixes of both kinds must fit one CTA's smem
+__device__ __forceinline__ int part_cost_of(int kind, int v) {
+  return kind == 0 ? 2 * ((min(max(v, 0), 120) + 1) / 2) + 2 : 2 * ((min(max(v, 0), 120) + 2) / 2) + 3;
+}
+// scan[kind][chunk] = CTA-local exclusive prefix ; tot[kind][cta]
+__global__ void __launch_bounds__(256) k_part_scan(const PartArgs p, unsigned int* __restrict__ scan,
+                                                   unsigned int* __restrict__ tot, int nchunk, int cpc) {
+  __shared__ unsigned int wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c_lo = blockIdx.x * cpc, c_hi = min(c_lo + cpc, nchunk);       // this CTA's chunks
+  for (int kind = 0; kind < 2; ++kind) {
+    const int* src = kind == 0 ? p.sl : p.sl_new;
+    unsigned int carry = 0;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 256) {                  // 256 chunks (2048 samples) per sweep, one per thread
+      const int c = c0 + tid;
+      unsigned int mine = 0;
+      if (c < c_hi) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int b = c * 8 + i; if (b < p.B) mine += part_cost_of(kind, __ldg(src + b)); }
+      }
+      unsigned int inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      __syncthreads();
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      unsigned int base = carry;
+      for (int k = 0; k < wid; ++k) base += wsum[k];
+      if (c < c_hi) scan[(size_t)kind * nchunk + c] = base + inc - mine;
+      unsigned int all = 0;
+      for (int k = 0; k < 8; ++k) all += wsum[k];
+      carry += all;
+    }
+    if (tid == 0) tot[kind * PART_CTAS + blockIdx.x] = carry;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_part_bounds(const PartArgs p, const unsigned int* __restrict__ scan,
+                                                     const unsigned int* __restrict__ tot, int nchunk, int cpc) {
+  extern __shared__ unsigned int pre[];                          // [2][nchunk + 1] global exclusive chunk prefixes
+  __shared__ unsigned int cbase[2][PART_CTAS + 1];
+  const int tid = threadIdx.x;
+  if (tid < 2) {
+    unsigned int run = 0;
+    for (int c = 0; c < PART_CTAS; ++c) { cbase[tid][c] = run; run += __ldg(tot + tid * PART_CTAS + c); }
+    cbase[tid][PART_CTAS] = run;
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * nchunk; e += 256) {
+    const int kind = e >= nchunk, c = e - kind * nchunk;
+    pre[kind * (nchunk + 1) + c] = cbase[kind][c / cpc] + __ldg(scan + e);
+  }
+  if (tid < 2) pre[tid * (nchunk + 1) + nchunk] = cbase[tid][PART_CTAS];
+  __syncthreads();
+  const int stride = TLSAN_MAX_GRID * PF_WARPS + 1;
+  const int idx = blockIdx.x * 256 + tid;
+  const int t = idx / stride, w = idx - t * stride;
+  if (t >= 3 || p.nw[t] <= 0 || w > p.nw[t]) return;
+  const int nw = p.nw[t], kind = t == 2 ? 1 : 0;
+  const unsigned int* P = pre + kind * (nchunk + 1);
+  const int* src = kind == 0 ? p.sl : p.sl_new;
+  int out = p.B;
+  if (w < nw) {
+    const unsigned long long total = P[nchunk] > 0 ? P[nchunk] : 1;
+    const unsigned long long lhs = (unsigned long long)w * total;
+    auto ge = [&](unsigned int x) { return lhs <= (unsigned long long)x * nw + (nw - 1); };
+    int lo = 0, hi = nchunk;                                     // first chunk whose prefix satisfies ge (hi: none)
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ge(P[mid])) hi = mid; else lo = mid + 1; }
+    int b = lo * 8;                                              // inside chunk lo - 1 (after its first sample) or at chunk lo
+    if (lo > 0) {
+      const int base = (lo - 1) * 8;
+      int v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = base + i < p.B ? __ldg(src + base + i) : 0;
+      unsigned int x = P[lo - 1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x += base + i < p.B ? part_cost_of(kind, v[i]) : 0;
+        if (b == lo * 8 && ge(x)) b = base + i + 1;
+      }
+    }
+    out = min(b, p.B);
+  }
+  p.starts[t][w] = out;
+}
+
+__global__ void k_partition_uniform(const PartArgs p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = idx / (TLSAN_MAX_GRID * PF_WARPS + 1), w = idx - t * (TLSAN_MAX_GRID * PF_WARPS + 1);
+  if (t < 3 && p.nw[t] > 0 && w <= p.nw[t]) p.starts[t][w] = (int)((long long)w * p.B / p.nw[t]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -254,13 +364,15 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
   const PfGeo& g = A.g;
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
-  const int nw = gridDim.x * PF_WARPS;
+  const int gw = blockIdx.x * PF_WARPS + warp;
+  const int bBeg = __ldg(A.starts + gw), bEnd = __ldg(A.starts + gw + 1);     // this warp's contiguous samples
   const int h = L.lane >> 4, c16 = L.lane & 15;
   unsigned char* mine = smem + (size_t)warp * g.per_warp;
   const FwaW wl = load_fwa_log2(a.dense, TLSAN_OFF_W1L, L.g, L.t);
 
   const float gamma = a.dense[TLSAN_OFF_GAMMA];
-  auto ell_of = [&](int b) { return b < a.B ? __ldg(a.sl + b) : -1; };
+  auto ell_of = [&](int b) { return b < bEnd ? __ldg(a.sl + b) : -1; };
+  auto nextb = [&](int b) { return b + 1 < bEnd ? b + 1 : a.B; };        // a.B: end marker
   auto ring = [&](int n) { return mine + g.o_ring + (n % 3) * g.ring; };
   // copy the metadata of a round into ring slot `dst`: lane t < 16 serves token r0 + t
   auto issue_meta = [&](const PfIter& it, unsigned char* dst) {
@@ -293,16 +405,16 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
   auto advance = [&](const PfIter& it, int ell_next) {
     PfIter n;
     if (it.r0 + PF_R < it.ell) { n.b = it.b; n.r0 = it.r0 + PF_R; n.ell = it.ell; }
-    else { n.b = it.b + nw; n.r0 = 0; n.ell = ell_next; }
+    else { n.b = nextb(it.b); n.r0 = 0; n.ell = ell_next; }
     return n;
   };
 
   // ---- pipeline prologue: metadata of rounds 0 and 1, then the rows of round 0
   PfIter it0, it1, it2;
-  it0.b = blockIdx.x * PF_WARPS + warp; it0.r0 = 0; it0.ell = ell_of(it0.b);
-  int eN = ell_of(it0.b + nw);                                  // length of the sample after the newest iterator's
+  it0.b = bBeg < bEnd ? bBeg : a.B; it0.r0 = 0; it0.ell = ell_of(it0.b);
+  int eN = ell_of(nextb(it0.b));                                // length of the sample after the newest iterator's
   it1 = advance(it0, eN);
-  if (it1.r0 == 0) eN = ell_of(it1.b + nw);
+  if (it1.r0 == 0) eN = ell_of(nextb(it1.b));
   issue_meta(it0, ring(0));
   issue_meta(it1, ring(1));
   cp_commit();
@@ -326,7 +438,7 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
     // ---- next round's rows, the metadata of the round after it
     issue_round(it1, ring(n + 1), mine + (size_t)((n + 1) & 1) * g.buf);
     it2 = advance(it1, eN);
-    if (it2.r0 == 0) eN = ell_of(it2.b + nw);
+    if (it2.r0 == 0) eN = ell_of(nextb(it2.b));
     issue_meta(it2, ring(n + 2));
     cp_commit();
 
@@ -451,6 +563,7 @@ struct PsArgs {
   FArgs a;
   const int2* smeta;        // [B][S + 2]
   const int4* sscal;        // [B]
+  const int* starts;        // [#warps + 1] balanced partition (k_partition)
 };
 #define PS_BUF ((PS_RS + 2) * 256 + 256)
 #define PS_RING (16 + 34 * 8 + 34 * 4 + 8)
@@ -461,7 +574,8 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
   const FArgs& a = A.a;
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
-  const int nw = gridDim.x * PF_WARPS;
+  const int gw = blockIdx.x * PF_WARPS + warp;
+  const int bBeg = __ldg(A.starts + gw), bEnd = __ldg(A.starts + gw + 1);     // this warp's contiguous samples
   const int h = L.lane >> 4, c16 = L.lane & 15;
   unsigned char* mine = smem + (size_t)warp * PS_PER_WARP;
   const FwaW w = load_fwa_log2(a.dense, TLSAN_OFF_W1S, L.g, L.t);
@@ -472,7 +586,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
   const int SW = a.S + 2;
   // metadata of sample b -> ring slot: scalars, the row pairs and the sorted ranks of its first 34 slots
   auto issue_meta = [&](int b, unsigned char* dst) {
-    if (b >= a.B) return;
+    if (b >= bEnd) return;
     if (L.lane == 0) cp16_s(smem_addr(dst), A.sscal + b);
     const uint32_t rp = smem_addr(dst) + 16, pp = rp + 34 * 8;
     for (int k = L.lane; k < min(SW, 34); k += 32) {
@@ -484,7 +598,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
   };
   // rows of sample b (metadata in ring slot `src`) -> buffer
   auto issue_rows = [&](int b, const unsigned char* src, unsigned char* buf) {
-    if (b >= a.B) return;
+    if (b >= bEnd) return;
     const int s = reinterpret_cast<const int*>(src)[0];
     const int2* rp = reinterpret_cast<const int2*>(src + 16);
     // staged row r: 0..PS_RS-1 = session items, PS_RS = candidate, PS_RS + 1 = user vector; 16 lanes x 16 B per row
@@ -502,22 +616,22 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
     if (h == 0) cp16_s(dst + (PS_RS + 2) * 256, a.scratch + (size_t)b * (TLSAN_SCR * 64) + 320 + c16 * 4);   // z
   };
 
-  int b0 = blockIdx.x * PF_WARPS + warp;
+  int b0 = bBeg;
   issue_meta(b0, ring(0));
-  issue_meta(b0 + nw, ring(1));
+  issue_meta(b0 + 1, ring(1));
   cp_commit();
   cp_wait_group<0>();
   __syncwarp();
   issue_rows(b0, ring(0), mine);
   cp_commit();
 
-  for (int n = 0; b0 < a.B; ++n, b0 += nw) {
+  for (int n = 0; b0 < bEnd; ++n, ++b0) {
     const int b = b0;
     unsigned char* buf = mine + (size_t)(n & 1) * PS_BUF;
     cp_wait_group<0>();
     __syncwarp();
-    issue_rows(b + nw, ring(n + 1), mine + (size_t)((n + 1) & 1) * PS_BUF);
-    issue_meta(b + 2 * nw, ring(n + 2));
+    issue_rows(b + 1, ring(n + 1), mine + (size_t)((n + 1) & 1) * PS_BUF);
+    issue_meta(b + 2, ring(n + 2));
     cp_commit();
 
     const unsigned char* mr = ring(n);
@@ -632,17 +746,68 @@ int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal,
   return TLSAN_OK;
 }
 
+// grids of the three pipelined kernels (the partition is computed for exactly these)
+static int pf_grid(int B, int ctas_per_sm) {
+  const int need = (B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * ctas_per_sm;
+  return need < cap ? need : cap;
+}
+size_t tlsan_partition_bytes() {
+  return ((size_t)3 * (TLSAN_MAX_GRID * PF_WARPS + 4) + (size_t)2 * ((PART_MAXB + 7) / 8) + 2 * PART_CTAS + 64) * sizeof(int);
+}
+
+// balanced partitions for the forward (fwd_ctas CTAs per SM), backward and short-term kernels of one batch
+int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st) {
+  PartArgs p;
+  p.sl = a.sl; p.sl_new = a.sl_new; p.B = a.B;
+  int* base = reinterpret_cast<int*>(part);
+  for (int t = 0; t < 3; ++t) p.starts[t] = base + (size_t)t * (TLSAN_MAX_GRID * PF_WARPS + 4);
+  p.nw[0] = pf_grid(a.B, fwd_ctas) * PF_WARPS;
+  p.nw[1] = train ? pf_grid(a.B, 2) * PF_WARPS : 0;
+  p.nw[2] = train ? pf_grid(a.B, 2) * PF_WARPS : 0;
+  const int nchunk = (a.B + 7) / 8;
+  if (a.B > PART_MAXB) {                                         // chunk prefixes would not fit shared memory: equal counts
+    k_partition_uniform<<<(3 * (TLSAN_MAX_GRID * PF_WARPS + 1) + 255) / 256, 256, 0, st>>>(p);
+    TLSAN_CHECK_LAUNCH("k_partition_uniform");
+    return TLSAN_OK;
+  }
+  // scratch of the two kernels lives behind the three boundary arrays
+  unsigned int* scan = reinterpret_cast<unsigned int*>(base + (size_t)3 * (TLSAN_MAX_GRID * PF_WARPS + 4));
+  unsigned int* tot = scan + (size_t)2 * ((PART_MAXB + 7) / 8);
+  const int cpc = (nchunk + PART_CTAS - 1) / PART_CTAS;          // chunks per CTA
+  k_part_scan<<<PART_CTAS, 256, 0, st>>>(p, scan, tot, nchunk, cpc);
+  TLSAN_CHECK_LAUNCH("k_part_scan");
+  const int smem = 2 * (nchunk + 1) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_part_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    attr_set = true;
+  }
+  k_part_bounds<<<(3 * (TLSAN_MAX_GRID * PF_WARPS + 1) + 255) / 256, 256, smem, st>>>(p, scan, tot, nchunk, cpc);
+  TLSAN_CHECK_LAUNCH("k_part_bounds");
+  return TLSAN_OK;
+}
+FArgs tlsan_make_fargs(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b);
+int tlsan_launch_partition_batch(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int fwd_ctas,
+                                 void* part, cudaStream_t st) {
+  const FArgs a = tlsan_make_fargs(d, p, b);
+  return tlsan_launch_partition(a, fwd_ctas, true, part, st);
+}
+static const int* part_starts(const void* part, int which) {
+  return reinterpret_cast<const int*>(part) + (size_t)which * (TLSAN_MAX_GRID * PF_WARPS + 4);
+}
+
 template <int KIND>
-static int launch_pf_long(const FArgs& a, const void* meta, int ctas_per_sm, int* grid_out, cudaStream_t st) {
+static int launch_pf_long(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, int* grid_out,
+                          cudaStream_t st) {
   PfArgs A;
   A.a = a; A.meta = reinterpret_cast<const int4*>(meta); A.g = pf_geo(a.L, KIND == 3);
+  A.starts = part_starts(part, KIND == 1 ? 0 : 1);
   static bool attr_set = false;
   if (!attr_set) {
     TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_long<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set = true;
   }
-  const int need = (a.B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * ctas_per_sm;
-  const int gr = need < cap ? need : cap;
+  const int gr = pf_grid(a.B, ctas_per_sm);
   if (grid_out) *grid_out = gr;
   k_pf_long<KIND><<<gr, PF_THREADS, A.g.total, st>>>(A);
   TLSAN_CHECK_LAUNCH(KIND == 1 ? "k_pf_long<fwd>" : "k_pf_long<bwd>");
@@ -650,24 +815,26 @@ static int launch_pf_long(const FArgs& a, const void* meta, int ctas_per_sm, int
 }
 
 // ctas_per_sm (forward): 3 fills the SM; 2 leaves room for the radix-sort kernels running beside it on the side stream
-int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, int ctas_per_sm, cudaStream_t st) {
-  return launch_pf_long<1>(a, meta, ctas_per_sm, nullptr, st);
+// (the same ctas_per_sm must have been given to tlsan_launch_partition)
+int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st) {
+  return launch_pf_long<1>(a, meta, part, ctas_per_sm, nullptr, st);
 }
-int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, int* grid_b, cudaStream_t st) {
-  return launch_pf_long<3>(a, meta, 2, grid_b, st);
+int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, const void* part, int* grid_b, cudaStream_t st) {
+  return launch_pf_long<3>(a, meta, part, 2, grid_b, st);
 }
 
-int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, int* grid_a, cudaStream_t st) {
+int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int* grid_a,
+                          cudaStream_t st) {
   PsArgs A;
   A.a = a; A.smeta = reinterpret_cast<const int2*>(smeta); A.sscal = reinterpret_cast<const int4*>(sscal);
+  A.starts = part_starts(part, 2);
   const int smem = PS_PER_WARP * PF_WARPS;
   static bool attr_set = false;
   if (!attr_set) {
     TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_short, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int need = (a.B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * 2;
-  const int gr = need < cap ? need : cap;
+  const int gr = pf_grid(a.B, 2);
   if (grid_a) *grid_a = gr;
   k_pf_short<<<gr, PF_THREADS, smem, st>>>(A);
   TLSAN_CHECK_LAUNCH("k_pf_short");
