@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- TLSAN train-step throughput on B200 (contract: see the task statement / DESIGN.md).
+"""bench.py -- TLSAN train-step throughput on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--batch B] [--Ls L] [--no-cpu-baseline] [--workload electronics|movies] [--strong]
+                    [--batch B] [--Ls L] [--workload electronics|movies] [--strong]
+                    [--no-cpu-baseline] [--skip-extras] [--no-pipeline]
 
---workload movies = BASELINE.json configs[2] (Movies-TV shape: NU 35 896, NI 28 589, NC 15); --strong keeps the
-GLOBAL batch at --batch and gives every rank batch/N rows (strong scaling); the default is weak scaling.
+Headline workload = BASELINE.json configs[1]: "TLSAN Electronics-shape synthetic (40k users, 22k items, 673 cates)
+fp32": NU 39 991, NI 22 048, NC 673, generators of SURVEY.md 8d (tlsan_b200/synth.py, numpy default_rng(1234 + rank)),
+per-GPU batch 65 536, Ls 10.  A step = one Model.train step (forward, loss, backward, segmented reduce,
+L2 + clip + SGD over every table row).  ONE JSON line on stdout:
 
-Workload (BASELINE.json configs[1]): "TLSAN Electronics-shape synthetic (40k users, 22k items,
-673 cates) fp32": NU 39 991, NI 22 048, NC 673, generators of SURVEY.md section 8d config 2
-(numpy default_rng(1234 + rank)), per-GPU batch 65 536, Ls 10.  A step = one Model.train step
-(forward, loss, backward, segmented reduce, L2 + clip + SGD over every table row).
-
-  value : train samples/s, all ranks, device-resident batches (several distinct batches cycled)
-  e2e   : the same step through Model.train(sess, batch, lr) with HOST numpy batches
-          (pack -> pinned -> H2D -> step -> loss D2H inside the timed region)
-  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+  value            train samples/s, all ranks, device-resident batches (several distinct batches cycled, the next
+                   batch's occurrence sort pipelined behind the current step)
+  e2e              the same step through Model.train(sess, batch, lr) with HOST numpy batches: pack -> pinned ->
+                   H2D -> step -> loss D2H inside the timed region (>= 200 steps), batch k+1 staged while step k runs
+  sustained        >= 3 s of back-to-back steps with the SM clock seen under that load
+  roofline         SURVEY 8d byte model: the whole step (headline) and the dominant kernel, against MEASURED_PEAKS.json
+  cpu_baseline     the oracle port on the host cores, bounded sample (rank 0, N = 1)
+  dp_parity        N > 1: a fixed global batch trained data-parallel (nccl / p2p exchange) and row-sharded must give
+                   bit-identical weights on every rank and the weights of a 1-rank step
+  dataset_resident, eval, eval_rank, movies (configs[2], weak + strong), scoring_sweep (configs[3]),
+  sharded_10M (configs[4]): the other BASELINE configurations, compact.
 """
 import argparse
 import ctypes as C
@@ -32,62 +37,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NU, NI, NC = 39991, 22048, 673
+from tlsan_b200.synth import S_MAX, WORKLOADS, algorithmic_bytes, synth_batches as _synth, table_bytes  # noqa: E402
+
+WL_NAME, NU, NI, NC = WORKLOADS["electronics"]
 N_SAMPLES = 561100
-WORKLOADS = {"electronics": ("TLSAN Electronics-shape synthetic", 39991, 22048, 673),
-             "movies": ("TLSAN Movies-TV-shape synthetic", 35896, 28589, 15)}
-WL_NAME = WORKLOADS["electronics"][0]
-# Digital-Music empirical laws: P(min(len,10) = k), k = 1..10 ; short length pmf
-P_LONG = np.array([7.0, 6.9, 6.7, 6.5, 6.3, 5.9, 5.2, 4.5, 3.9, 47.1]) / 100.0
-P_SHORT_HEAD = np.array([.8724, .0886, .0223, .0085, .0040])
-S_MAX = 18
 
 
-def synth_batches(rng, n_batches, B, L):
-    """Electronics-shape synthetic batches in the TLSAN/input.py layout."""
-    p_long = P_LONG / P_LONG.sum()
-    tail = np.full(S_MAX - 5, (1.0 - P_SHORT_HEAD.sum()) / (S_MAX - 5))
-    p_short = np.concatenate([P_SHORT_HEAD, tail])
-    p_short /= p_short.sum()
-    out = []
-    for _ in range(n_batches):
-        frac = rng.choice(10, B, p=p_long) + 1                           # law of min(len, 10)
-        sl = np.maximum(1, np.round(frac * (L / 10.0))).astype(np.int64) if L != 10 else frac.astype(np.int64)
-        new_sl = (rng.choice(S_MAX, B, p=p_short) + 1).astype(np.int64)
-        S = int(new_sl.max())
-        hist_i = rng.integers(0, NI, (B, L)).astype(np.int64)
-        hist_i_new = rng.integers(0, NI, (B, S)).astype(np.int64)
-        n = np.sort(rng.integers(1, 13, (B, L)), axis=1)[:, ::-1]        # bucket non-increasing in t
-        hist_t = (1.0 / n).astype(np.float32)
-        col = np.arange(L)[None, :]
-        hist_i[col >= sl[:, None]] = 0
-        hist_t[col >= sl[:, None]] = 0
-        hist_i_new[np.arange(S)[None, :] >= new_sl[:, None]] = 0
-        out.append((rng.integers(0, NU, B).astype(np.int64), rng.integers(0, NI, B).astype(np.int64),
-                    rng.integers(0, 2, B).astype(np.int64), hist_i, hist_i_new, hist_t, sl, new_sl,
-                    rng.integers(0, NC, B).astype(np.int64)))
-    return out
-
-
-def algorithmic_bytes(batch, L):
-    """SURVEY.md 8d byte model, evaluated on the actual lengths of `batch` (totals per batch).
-    Per sample: R = 2(l+s)+4 embedding rows of 128 B.  The per-kernel figures split the train-step
-    formula by which kernel touches what; scratch traffic is never credited."""
-    sl = np.asarray(batch[6], np.int64); s = np.asarray(batch[7], np.int64)
-    S = batch[4].shape[1]
-    R = 2 * (sl + s) + 4
-    scoring1 = 4 * (2 * L + S + 6) + 4 * (sl + s + 1) + 128 * R + (4 * L + 4) + 4
-    train = scoring1 + 2 * (128 * R + 4 * sl + 4) + 4
-    long_fwd = 4 * (2 * L + 2) + 4 * sl + 128 * 2 * sl + 4 * L                 # ids, hist_t, icl, rows, usert row
-    short = 4 * (S + 6) + 4 * (s + 1) + 128 * (2 * s + 4) + 4 + 128 * (2 * s + 4) + 8   # reads + gradient rows written
-    bwd_long = 4 * 2 * L + 4 * sl + 128 * 2 * sl + 4 * L + 128 * 2 * sl + 4 * sl
-    reduce_ = 128 * R + 4 * sl + 4                                              # every gradient row read once
-    return {"scoring1": int(scoring1.sum()), "train": int(train.sum()), "long_fwd": int(long_fwd.sum()),
-            "short": int(short.sum()), "bwd_long": int(bwd_long.sum()), "reduce": int(reduce_.sum())}
-
-
-def table_bytes(L):
-    return 4 * (33 * NI + 32 * NU + L * NU + 32 * NC)
+def synth_batches(rng, n_batches, B, L, **kw):
+    """Batches of the currently selected workload (module globals NU / NI / NC)."""
+    return _synth(rng, n_batches, B, L, NU, NI, NC, **kw)
 
 
 _SAMPLER_SRC = r"""
@@ -105,26 +63,29 @@ while True:
         bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
     except Exception:
         bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), bits, flush=True)
+    try:
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+    except Exception:
+        pw = 0.0
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), bits, pw, flush=True)
     time.sleep(0.002)
 """
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: a side process polls NVML every
-    ~2 ms (started early; samples are filtered to the [mark_begin, mark_end] window)."""
+    """SM clock, power and throttle reasons DURING a timed region: a side process polls NVML every ~2 ms (started
+    early); window(t0, t1) summarises the samples that fall inside a wall-clock window."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index):
-        self.proc, self.t0, self.t1 = None, None, None
+        self.proc, self.lines = None, []
         try:
             import torch
             p = torch.cuda.get_device_properties(index)
             bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
             self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, bus, str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.lines = []
 
             def pump():
                 for ln in self.proc.stdout:
@@ -134,37 +95,37 @@ class ClockSampler:
         except Exception as e:                      # pragma: no cover
             self.err = repr(e)
 
-    def mark_begin(self):
+    def wait_ready(self):
         t_end = time.time() + 5.0                  # the side process needs ~1 s to import + nvmlInit
         while self.proc is not None and not self.lines and time.time() < t_end:
             time.sleep(0.01)
-        self.t0 = time.time()
 
-    def mark_end(self):
-        self.t1 = time.time()
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml sampler unavailable"]}
+        time.sleep(0.01)
+        sm, pw, bits, mx = [], [], 0, None
+        for ln in list(self.lines):
+            f = ln.split()
+            try:
+                if f[0] == "max":
+                    mx = int(f[1])
+                elif t0 <= float(f[0]) <= t1:
+                    sm.append(int(f[1])); bits |= int(f[2]); pw.append(float(f[3]))
+            except Exception:
+                pass
+        reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None, "reasons": reasons}
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml sampler unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        self.t.join(timeout=1)
-        sm, bits, mx = [], 0, None
-        for ln in self.lines:
-            f = ln.split()
-            try:
-                if f[0] == "max":
-                    mx = int(f[1])
-                elif self.t0 <= float(f[0]) <= self.t1:
-                    sm.append(int(f[1])); bits |= int(f[2])
-            except Exception:
-                pass
-        reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": reasons}
 
 
 def cpu_port_throughput(L, budget_s, B=1024, seed=99):
@@ -183,8 +144,7 @@ def cpu_port_throughput(L, budget_s, B=1024, seed=99):
         params = r["new_params"]
         n += 1
     dt = time.perf_counter() - t0
-    return n * B / dt, torch.get_num_threads(), "%d steps of B=%d, L=%d, Electronics-shape synthetic (%.1f s)" % (
-        n, B, L, dt)
+    return n * B / dt, torch.get_num_threads(), "%d steps of B=%d, L=%d, %s (%.1f s)" % (n, B, L, WL_NAME, dt)
 
 
 def run_reference(args, rank):
@@ -208,12 +168,12 @@ def run_reference(args, rank):
         params = O.train_step(params, icl, batches[k % 4], 1.0, cfg)["new_params"]
     dt = time.perf_counter() - t0
     v = args.steps * B / dt
-    sample = "each step = B=%d rows of the Electronics-shape workload (bounded sample of the 65536-row step)" % B
+    sample = "each step = B=%d rows of the %s workload (bounded sample of the 65536-row step)" % (B, WL_NAME)
     _emit({
         "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, B),
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, B),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -250,6 +210,213 @@ def _emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+class Ctx:
+    """Process-wide handles of one bench run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.pg = None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.pg = dist.group.WORLD
+        assert self.world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peaks = peaks
+        self.hbm = float(peaks.get("hbm_gbs", 6650.0))
+        self.hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, n):
+        """n calls of fn between barriers, CUDA events on the current stream; ms per call, max over ranks."""
+        self.barrier()
+        self.e0.record()
+        for k in range(n):
+            fn(k)
+        self.e1.record()
+        self.barrier()
+        return self.max_over_ranks(self.e0.elapsed_time(self.e1)) / n
+
+
+def train_loop(model, dbs, steps, pipe, first=0, global_batch=None):
+    n = len(dbs)
+    for k in range(steps):
+        model.train_staged(dbs[(first + k) % n], 1.0, global_batch=global_batch,
+                           next_db=dbs[(first + k + 1) % n] if pipe else None)
+
+
+def make_model(ctx, L, seed=1234, pg="ctx", **kw):
+    from oracle import tlsan_oracle as O            # flag defaults (train.py:26-49) only
+    from tlsan_b200.model import Model
+    cfg = O.default_config(NU, NI, NC, Ls=L)
+    icl = np.random.default_rng(1234).integers(0, NC, NI).astype(np.int32)     # same on every rank
+    return Model(cfg, icl, seed=seed, process_group=ctx.pg if pg == "ctx" else pg, **kw), cfg, icl
+
+
+# ---------------------------------------------------------------------------------------------------- dp parity
+def dp_parity(ctx):
+    """A fixed global batch, trained (a) data-parallel with the NCCL exchange, (b) with the peer-memory exchange,
+    (c) with row-sharded item tables, against 1-rank steps on the whole batch computed redundantly on every rank."""
+    torch, dist = ctx.torch, ctx.dist
+    from tlsan_b200.parallel import shard_rows
+    from tlsan_b200.sharded import ShardedModel
+    Bg, L = 8192, 10
+    rng = np.random.default_rng(4242)
+    batches = synth_batches(rng, 2, Bg, L)
+    g = torch.Generator().manual_seed(77)
+    ref, cfg, icl = make_model(ctx, L, pg=None)
+    sd0 = ref.state_dict()
+    for k in ("usert_emb", "item_b"):
+        sd0[k] = sd0[k] + 0.3 * torch.randn(sd0[k].shape, generator=g)
+    for k in list(sd0):
+        if k.endswith("/bias"):
+            sd0[k] = sd0[k] + 0.1 * torch.randn(sd0[k].shape, generator=g)
+    ref.load_state_dict(sd0)
+    ref_sd = []
+    for b in batches:
+        ref.train(None, b, 1.0)
+        ref_sd.append({k: v.clone() for k, v in ref.state_dict().items()})
+    scale = {k: float((ref_sd[-1][k] - sd0[k]).abs().max()) + 1e-12 for k in sd0}
+    out = {}
+
+    def compare(sd, want, label):
+        err = max(float((sd[k] - want[k]).abs().max()) / scale[k] for k in want)
+        flat = torch.cat([v.reshape(-1) for v in sd.values()]).cuda().view(torch.int32)
+        hi, lo = flat.clone(), flat.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(hi, lo))
+        e = torch.tensor([err], device="cuda")
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        out[label] = {"ok": bool(float(e.item()) < 1e-5 and same), "err": float(e.item()),
+                      "bit_identical_across_ranks": same}
+
+    for mode in ("nccl", "p2p"):
+        try:
+            m, _, _ = make_model(ctx, L, dp_mode=mode)
+            m.load_state_dict(sd0)
+            for b in batches:
+                local, _ = shard_rows(b, ctx.rank, ctx.world)
+                m.train_staged(m.stage_batch(local), 1.0, global_batch=Bg)
+            if mode == "p2p":
+                m.check_dp_health()
+            compare(m.state_dict(), ref_sd[-1], mode)
+            del m
+        except Exception as e:                                    # reported, not hidden
+            out[mode] = {"ok": False, "error": repr(e)[:200]}
+    try:
+        sm = ShardedModel(cfg, icl, process_group=ctx.pg)
+        sm.load_full_state(sd0)
+        local, _ = shard_rows(batches[0], ctx.rank, ctx.world)
+        sm.train_staged(sm.stage_batch(local), 1.0, global_batch=Bg)
+        compare(sm.gather_full_state(), ref_sd[0], "sharded")
+        del sm
+    except Exception as e:
+        out["sharded"] = {"ok": False, "error": repr(e)[:200]}
+    out["what"] = ("global batch %d, %s shape, 2 steps (sharded: 1); err = max |w - w_1rank| / max |w_1rank - w_0| over "
+                   "all variables, max over ranks; ok = err < 1e-5 and bit-identical weights on every rank" % (Bg, WL_NAME))
+    torch.cuda.synchronize()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- extra legs
+def leg_other_workload(ctx, name, L, pipe, steps):
+    """BASELINE configs[2]: Movies-TV shape, data parallel; weak (per-GPU batch 65 536) and strong (global 65 536)."""
+    global WL_NAME, NU, NI, NC
+    keep = (WL_NAME, NU, NI, NC)
+    WL_NAME, NU, NI, NC = WORKLOADS[name]
+    out = {"workload": "%s (NU %d, NI %d, NC %d)" % (WL_NAME, NU, NI, NC)}
+    try:
+        model, _, _ = make_model(ctx, L)
+        for label, B in (("weak", 65536), ("strong", max(1, 65536 // ctx.world))):
+            hb = synth_batches(np.random.default_rng(99 + 1000 * ctx.rank), 3, B, L)
+            dbs = [model.stage_batch(b) for b in hb]
+            train_loop(model, dbs, 4, pipe, global_batch=B * ctx.world)
+            ms = ctx.timed(lambda k: model.train_staged(dbs[k % 3], 1.0, global_batch=B * ctx.world,
+                                                        next_db=dbs[(k + 1) % 3] if pipe else None), steps)
+            bts = float(np.mean([algorithmic_bytes(b, L)["train"] for b in hb])) + 2 * table_bytes(L, NU, NI, NC) + 2 * 4 * 4449
+            out[label] = {"per_gpu_batch": B, "global_batch": B * ctx.world, "ms_per_step": ms,
+                          "value": B * ctx.world / (ms * 1e-3), "unit": "samples/s",
+                          "algorithmic_GBps_per_gpu": bts / (ms * 1e-3) / 1e9, "frac_of_hbm": bts / (ms * 1e-3) / 1e9 / ctx.hbm}
+            del dbs
+        del model
+    finally:
+        WL_NAME, NU, NI, NC = keep
+    return out
+
+
+def leg_scoring_sweep(ctx):
+    """BASELINE configs[3]: eval_auc-style scoring (2 candidates), rows sharded over the ranks, no collective;
+    four corner points of the sweep, every row at full length (the roofline variant)."""
+    torch = ctx.torch
+    pts = []
+    for L in (10, 90):
+        model, _, _ = make_model(ctx, L, pg=None)
+        for B in (1024, 65536):
+            b = synth_batches(np.random.default_rng(7 + ctx.rank), 1, B, L, full=True, is_test=True)[0]
+            db = model.stage_batch(b, is_test=True)
+            for _ in range(3):
+                model.score_staged(db, 2)
+            n = 20 if B <= 4096 else 8
+            ms = ctx.timed(lambda k: model.score_staged(db, 2), n)
+            gbs = algorithmic_bytes(b, L)["scoring2"] / (ms * 1e-3) / 1e9
+            pts.append({"Ls": L, "B_per_gpu": B, "ms": ms, "seqs_per_s": B * ctx.world / (ms * 1e-3),
+                        "algorithmic_GBps_per_gpu": gbs, "frac_of_hbm": gbs / ctx.hbm})
+        del model
+    torch.cuda.synchronize()
+    return {"what": "eval_auc scoring, 2 candidates, full-length rows, rows sharded (no collective)", "points": pts}
+
+
+def leg_sharded(ctx, steps=12):
+    """BASELINE configs[4]: 10 M-item catalogue, item tables row-sharded over the ranks + all-to-all."""
+    global WL_NAME, NU, NI, NC
+    from oracle import tlsan_oracle as O
+    from tlsan_b200.sharded import ShardedModel
+    keep = (WL_NAME, NU, NI, NC)
+    WL_NAME, NU, NI, NC = WORKLOADS["items10m"]
+    try:
+        L, B = 10, 65536
+        cfg = O.default_config(NU, NI, NC, Ls=L)
+        icl = np.random.default_rng(1234).integers(0, NC, NI).astype(np.int32)
+        m = ShardedModel(cfg, icl, process_group=ctx.pg, partition="mod")
+        hb = synth_batches(np.random.default_rng(1234 + 1000 * ctx.rank), 3, B, L)
+        dbs = [m.stage_batch(b) for b in hb]
+        for w in range(3):
+            m.train_staged(dbs[w % 3], 1.0, global_batch=B * ctx.world)
+        ms = ctx.timed(lambda k: m.train_staged(dbs[k % 3], 1.0, global_batch=B * ctx.world), steps)
+        out = {"workload": "%s (NU %d, NI %d, NC %d), item_emb / item_b / icl row-sharded (id mod N)" % (WL_NAME, NU, NI, NC),
+               "per_gpu_batch": B, "ms_per_step": ms, "value": B * ctx.world / (ms * 1e-3), "unit": "samples/s",
+               "distinct_ids_per_rank": int(m.last_unique), "exchange_bytes_per_rank_step": int(2 * m.last_exchange_bytes),
+               "item_shard_bytes_per_rank": int(m.n_local) * 33 * 4}
+        del m, dbs
+        return out
+    finally:
+        WL_NAME, NU, NI, NC = keep
+
+
+# ---------------------------------------------------------------------------------------------------- main
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -262,7 +429,8 @@ def main():
     ap.add_argument("--resident", type=int, default=6, help="distinct device-resident batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no e2e / scoring / cpu legs")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of back-to-back steps in the sustained leg")
+    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: only the device-resident leg")
     ap.add_argument("--no-pipeline", action="store_true", help="do not presort the next batch behind the current step")
     ap.add_argument("--workload", default="electronics", choices=sorted(WORKLOADS))
     ap.add_argument("--strong", action="store_true", help="fixed GLOBAL batch: every rank gets batch / N rows")
@@ -272,94 +440,110 @@ def main():
     WL_NAME, NU, NI, NC = WORKLOADS[args.workload]
     if args.strong:
         args.batch = max(1, args.batch // max(args.gpus, 1))
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, int(os.environ.get("RANK", "0")))
         return
 
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx(args)
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
     from tlsan_b200 import _lib
-    from tlsan_b200.model import Model
-    from oracle import tlsan_oracle as O            # config defaults + cpu_baseline leg only
-
-    torch.cuda.set_device(local_rank)
-    pg = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        pg = dist.group.WORLD
-    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
-
+    lib = _lib.lib()
     B, L = args.batch, args.Ls
-    cfg = O.default_config(NU, NI, NC, Ls=L)
-    icl = np.random.default_rng(1234).integers(0, NC, NI).astype(np.int32)     # same on every rank
-    clocks = ClockSampler(local_rank) if rank == 0 else None       # side process; started early
-    model = Model(cfg, icl, seed=1234, process_group=pg)
+    clocks = ClockSampler(ctx.local_rank) if rank == 0 else None       # side process; started early
+    model, cfg, icl = make_model(ctx, L)
     rng = np.random.default_rng(1234 + 1000 * rank)
     host_batches = synth_batches(rng, args.resident, B, L)
     dev_batches = [model.stage_batch(b) for b in host_batches]
     torch.cuda.synchronize()
-    lib = _lib.lib()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident timed region
-    nres = len(dev_batches)
     pipe = not args.no_pipeline          # name the next batch: its occurrence sort runs behind this step's backward
-    for w in range(args.warmup):
-        model.train_staged(dev_batches[w % nres], 1.0, next_db=dev_batches[(w + 1) % nres] if pipe else None)
-    barrier()
+    Bg = B * world
+    nres = len(dev_batches)
+
+    # ---------------- device-resident timed region (the contract's K steps)
+    train_loop(model, dev_batches, args.warmup, pipe, global_batch=Bg)
+    ctx.barrier()
     launches0 = lib.tlsan_launch_count()
     _lib.check(lib.tlsan_profile_begin(args.steps))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     if clocks:
-        clocks.mark_begin()
-    e0.record()
-    for k in range(args.steps):
-        model.train_staged(dev_batches[(args.warmup + k) % nres], 1.0,
-                           next_db=dev_batches[(args.warmup + k + 1) % nres] if pipe else None)
-    e1.record()
-    barrier()
-    if clocks:
-        clocks.mark_end()
-    ms = e0.elapsed_time(e1)
+        clocks.wait_ready()
+    t_w0 = time.time()
+    ctx.e0.record()
+    t_h0 = time.perf_counter()
+    train_loop(model, dev_batches, args.steps, pipe, first=args.warmup, global_batch=Bg)
+    t_enqueue = time.perf_counter() - t_h0             # host time to ENQUEUE the K steps (launch-bound if ~ device time)
+    ctx.e1.record()
+    ctx.barrier()
+    t_w1 = time.time()
+    ms = ctx.max_over_ranks(ctx.e0.elapsed_time(ctx.e1))
     phase = np.zeros((args.steps, len(_lib.PHASES)), np.float32)
     nrec = C.c_int32()
     _lib.check(lib.tlsan_profile_end(phase.ctypes.data, C.byref(nrec)))
     launches = lib.tlsan_launch_count() - launches0
-    clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    clk = clocks.window(t_w0, t_w1) if clocks else None
     loss = float(model._stats[0].item())
+    ph = phase[:nrec.value].mean(axis=0)
+    phases_ms = {n: float(v) for n, v in zip(_lib.PHASES, ph)}
 
-    # ---------------- end to end through Model.train with host batches
     if args.skip_extras:
         if rank == 0:
-            _emit({"ms_per_step": ms / args.steps, "phases_ms": dict(zip(_lib.PHASES, map(float, phase[:nrec.value].mean(axis=0))))})
+            _emit({"ms_per_step": ms / args.steps, "phases_ms": phases_ms,
+                   "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps})
+        if clocks:
+            clocks.stop()
+        if world > 1:
+            dist.destroy_process_group()
         return
-    for w in range(2):
-        model.train(None, host_batches[w % len(host_batches)], 1.0)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+
+    # ---------------- sustained: >= sustain_s seconds of back-to-back steps
+    chunk, done = 500, 0
+    ctx.barrier()
+    t_s0 = time.time()
+    ctx.e0.record()
+    while True:
+        train_loop(model, dev_batches, chunk, pipe, first=done, global_batch=Bg)
+        done += chunk
+        torch.cuda.synchronize()
+        stop = torch.tensor([1.0 if time.time() - t_s0 >= args.sustain_s else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(stop, op=dist.ReduceOp.MAX)
+        if float(stop.item()) > 0 or done >= 40000:
+            break
+    ctx.e1.record()
+    ctx.barrier()
+    t_s1 = time.time()
+    ms_sus = ctx.max_over_ranks(ctx.e0.elapsed_time(ctx.e1)) / done
+    clk_sus = clocks.window(t_s0, t_s1) if clocks else None
+    sustained = {"seconds": t_s1 - t_s0, "steps": done, "ms_per_step": ms_sus, "value": Bg / (ms_sus * 1e-3),
+                 "unit": "samples/s", "clocks": clk_sus}
+
+    # ---------------- end to end through Model.train with host batches (batch k+1 staged while step k runs)
+    for w in range(3):
+        model.train(None, host_batches[w % nres], 1.0, global_batch=Bg)
+    ctx.barrier()
+    e2e_steps = max(200, args.steps)
     t0 = time.perf_counter()
+    model.prefetch(host_batches[0])
     for k in range(e2e_steps):
-        model.train(None, host_batches[k % len(host_batches)], 1.0)
+        model.train(None, host_batches[k % nres], 1.0, global_batch=Bg, prefetch=host_batches[(k + 1) % nres])
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    model.drop_prefetch()
     h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
+    # the same loop fed with int32 batches (tlsan_b200.input index_dtype=np.int32): no 64 -> 32 bit narrowing pass
+    hb32 = [tuple(np.ascontiguousarray(f, dtype=np.int32) if n not in (2, 5) else f for n, f in enumerate(b))
+            for b in host_batches]
+    for w in range(2):
+        model.train(None, hb32[w % nres], 1.0, global_batch=Bg)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    model.prefetch(hb32[0])
+    for k in range(e2e_steps):
+        model.train(None, hb32[k % nres], 1.0, global_batch=Bg, prefetch=hb32[(k + 1) % nres])
+    torch.cuda.synchronize()
+    e2e32_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    model.drop_prefetch()
+    del hb32
 
     # ---------------- epoch loop over a device-resident dataset: GPU batch assembly + train step
     from tlsan_b200.dataset import DeviceDataset
@@ -377,41 +561,30 @@ def main():
     dds = DeviceDataset(csr, is_test=False)
     perm = torch.randperm(len(dds), device="cuda", dtype=torch.int32)
     nb = len(dds) // B
+
     def ds_batch(k):
         return dds.batch(perm[(k % nb) * B:(k % nb + 1) * B], L, width="max")
-    cur = ds_batch(0)
-    for k in range(4):                   # warm-up with the same call pattern (both workspaces get allocated here)
+    state = {"cur": ds_batch(0)}
+
+    def ds_step(k):                      # batch k+1 is assembled (and, pipelined, sorted) while step k runs
         nxt = ds_batch(k + 1)
-        model.train_staged(cur, 1.0, next_db=nxt if pipe else None)
-        cur = nxt
-    barrier()
-    ds_steps = max(3, min(args.steps, 50))
-    cur = ds_batch(0)
-    barrier()
-    e0.record()
-    for k in range(ds_steps):            # batch k+1 is assembled (and, pipelined, sorted) while step k runs
-        nxt = ds_batch(k + 1)
-        model.train_staged(cur, 1.0, next_db=nxt if pipe else None)
-        cur = nxt
-    e1.record()
-    barrier()
-    t_ds = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ds, op=dist.ReduceOp.MAX)
-    ms_ds = float(t_ds.item()) / ds_steps
+        model.train_staged(state["cur"], 1.0, global_batch=Bg, next_db=nxt if pipe else None)
+        state["cur"] = nxt
+    for k in range(6):                   # warm-up with the same call pattern (both workspaces get allocated here)
+        ds_step(k)
+    ds_steps = max(100, min(args.steps, 400))
+    t_h0 = time.perf_counter()
+    ms_ds = ctx.timed(ds_step, ds_steps)
+    ds_wall = (time.perf_counter() - t_h0) / ds_steps
 
     # ---------------- scoring (eval_auc-style, 2 candidates) device-resident
     test_b = list(host_batches[0]); test_b[2] = host_batches[1][1]
-    db = model.stage_batch(tuple(test_b), is_test=True)
+    test_b = tuple(test_b)
+    db = model.stage_batch(test_b, is_test=True)
     for _ in range(3):
         model.score_staged(db, 2)
-    barrier()
-    e0.record()
-    for _ in range(10):
-        model.score_staged(db, 2)
-    e1.record()
-    barrier()
-    ms_score = e0.elapsed_time(e1) / 10
+    ms_score = ctx.timed(lambda k: model.score_staged(db, 2), 20)
+    score_bytes = algorithmic_bytes(test_b, L)["scoring2"]
 
     # ---------------- full-catalogue ranking (eval_prec / eval_recall hot kernel, tcgen05 3xTF32 GEMM)
     rb = min(B, 65536)
@@ -423,39 +596,40 @@ def main():
     _lib.check(lib.tlsan_rank_workspace_bytes(C.byref(rdims), C.byref(need)))
     rws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
 
-    def rank_once():
+    def rank_once(k):
         _lib.check(lib.tlsan_label_rank_ws(C.byref(rdims), C.byref(model._params), ut.data_ptr(), lab.data_ptr(),
                                            rk.data_ptr(), rws.data_ptr(), rws.numel(), None))
     for _ in range(3):
-        rank_once()
-    barrier()
-    e0.record()
-    for _ in range(10):
-        rank_once()
-    e1.record()
-    barrier()
-    ms_rank = e0.elapsed_time(e1) / 10
+        rank_once(0)
+    ms_rank = ctx.timed(rank_once, 10)
+
+    # ---------------- the other BASELINE configurations + multi-GPU correctness
+    extras = {}
+    for name, fn in (("movies", lambda: leg_other_workload(ctx, "movies", L, pipe, 60)),
+                     ("scoring_sweep", lambda: leg_scoring_sweep(ctx)),
+                     ("sharded_10M", lambda: leg_sharded(ctx)),
+                     ("dp_parity", (lambda: dp_parity(ctx)) if world > 1 else None)):
+        if fn is None:
+            continue
+        try:
+            extras[name] = fn()
+        except Exception as e:                                    # a failing extra leg is reported, the line still prints
+            extras[name] = {"error": repr(e)[:300]}
+        ctx.barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (CUDA events recorded around it on its stream)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    ph = phase[:nrec.value].mean(axis=0)
-    phases_ms = {n: float(v) for n, v in zip(_lib.PHASES, ph)}
+    # ---------------- roofline (SURVEY 8d byte model; CUDA events recorded by the library on the launching stream)
     per_batch = [algorithmic_bytes(b, L) for b in host_batches]
     used = [per_batch[(args.warmup + k) % len(per_batch)] for k in range(args.steps)]
     mean_bytes = {k: float(np.mean([u[k] for u in used])) for k in used[0]}
-    train_bytes = mean_bytes["train"] + 2 * table_bytes(L) + 2 * 4 * 4449
-    # dominant kernel = the longest of the per-sample gather kernels (each phase below is ONE kernel)
+    train_bytes = mean_bytes["train"] + 2 * table_bytes(L, NU, NI, NC) + 2 * 4 * 4449
+    step_ms = ms / args.steps
+    # dominant kernel = the longest of the per-sample gather kernels (each phase below is ONE kernel; the forward
+    # phase also holds the 12 us metadata pre-pass)
     pname = max(("long_fwd", "short", "bwd_long", "reduce"), key=lambda n: phases_ms[n])
     kname, kbytes, kms = _lib.PHASE_KERNEL[pname], mean_bytes[pname], phases_ms[pname]
     traffic = None
@@ -464,47 +638,65 @@ def main():
     except Exception:
         pass
     achieved = kbytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": ctx.hbm, "unit": "GB/s",
+                "frac": achieved / ctx.hbm, "traffic": traffic, "peak_source": ctx.hbm_src,
                 "kernel_ms": kms, "algorithmic_bytes_per_launch": kbytes, "phases_ms": phases_ms,
+                "note": "per-kernel bytes follow SURVEY 8d: what each kernel must read / write once; the backward's "
+                        "re-read of the token rows, scratch and sort traffic are not credited",
                 "per_kernel": {_lib.PHASE_KERNEL[n]: {"ms": phases_ms[n], "algorithmic_GBps": mean_bytes[n] / (phases_ms[n] * 1e-3) / 1e9,
-                                                      "frac": mean_bytes[n] / (phases_ms[n] * 1e-3) / 1e9 / peak}
+                                                      "frac": mean_bytes[n] / (phases_ms[n] * 1e-3) / 1e9 / ctx.hbm}
                                for n in ("long_fwd", "short", "bwd_long", "reduce")},
-                "step": {"algorithmic_bytes": train_bytes,
-                         "achieved": train_bytes / (ms / args.steps * 1e-3) / 1e9,
-                         "frac": train_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}}
+                "step": {"algorithmic_bytes": train_bytes, "achieved": train_bytes / (step_ms * 1e-3) / 1e9,
+                         "frac": train_bytes / (step_ms * 1e-3) / 1e9 / ctx.hbm,
+                         "sustained_frac": train_bytes / (ms_sus * 1e-3) / 1e9 / ctx.hbm}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_port_throughput(L, args.cpu_budget)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
 
+    tf32_peak = float(ctx.peaks.get("bf16_tflops", 1590.0)) / 2.0
+    issued = 3 * 2.0 * rb * NI * 72 / (ms_rank * 1e-3) / 1e12
+    algo = 2.0 * rb * NI * 64 / (ms_rank * 1e-3) / 1e12
     line = {
-        "metric": "train_samples_per_s", "value": args.steps * B * world / (ms * 1e-3), "unit": "samples/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "metric": "train_samples_per_s", "value": args.steps * Bg / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, B),
-        "e2e": {"value": e2e_steps * B * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "e2e": {"value": e2e_steps * Bg / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "how": "Model.train(sess, host batch, lr, prefetch=next host batch): pack + H2D of batch k+1 overlap "
+                       "step k; every step ends with the loss read-back; int64 ids as TLSAN/input.py emits them",
+                "int32_feed": {"value": e2e_steps * Bg / e2e32_s, "ms_per_step": 1e3 * e2e32_s / e2e_steps,
+                               "what": "same loop, batches already int32 (tlsan_b200.input index_dtype=np.int32)"}},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-        "dataset_resident": {"metric": "train_samples_per_s", "value": B * world / (ms_ds * 1e-3), "unit": "samples/s",
+        "sustained": sustained,
+        "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps,
+        "dataset_resident": {"metric": "train_samples_per_s", "value": Bg / (ms_ds * 1e-3), "unit": "samples/s",
+                             "ms_per_step": ms_ds, "host_wall_ms_per_step": 1e3 * ds_wall, "steps": ds_steps,
                              "what": "shuffled epoch loop over a CSR dataset resident in HBM: tlsan_collate (GPU batch "
-                                     "assembly in the input.py layout) + train step, no host batcher", "steps": ds_steps},
-        "eval": {"metric": "eval_seqs_per_s", "value": B * world / (ms_score * 1e-3), "unit": "seqs/s",
-                 "candidates": 2},
+                                     "assembly in the input.py layout) + train step, no host batcher; when "
+                                     "host_wall_ms_per_step ~ ms_per_step the loop is bound by the host enqueueing "
+                                     "~30 launches per step, not by the GPU"},
+        "eval": {"metric": "eval_seqs_per_s", "value": Bg / (ms_score * 1e-3), "unit": "seqs/s", "candidates": 2,
+                 "ms": ms_score,
+                 "roofline": {"bound": "hbm", "achieved": score_bytes / (ms_score * 1e-3) / 1e9, "peak": ctx.hbm,
+                              "unit": "GB/s", "frac": score_bytes / (ms_score * 1e-3) / 1e9 / ctx.hbm,
+                              "algorithmic_bytes_per_seq": score_bytes / B}},
         "eval_rank": {"metric": "full_catalogue_rank_seqs_per_s", "value": rb * world / (ms_rank * 1e-3), "unit": "seqs/s",
                       "what": "eval_prec/eval_recall hot kernel: [B,64]x[64,NI] 3xTF32 tcgen05 GEMM + count-only "
                               "epilogue (k_build_catalogue + k_label_rank_tc), B=%d, NI=%d" % (rb, NI),
-                      "roofline": {"bound": "tensor", "achieved": 3 * 2.0 * rb * NI * 72 / (ms_rank * 1e-3) / 1e12,
-                                   "peak": float(peaks.get("bf16_tflops", 1590.0)) / 2.0, "unit": "TFLOP/s",
-                                   "frac": 3 * 2.0 * rb * NI * 72 / (ms_rank * 1e-3) / 1e12 /
-                                           (float(peaks.get("bf16_tflops", 1590.0)) / 2.0),
-                                   "note": "issued tf32 flops (3 terms, K padded 64->72); peak = measured bf16 "
-                                           "cuBLAS burst / 2 (tf32 runs at half the bf16 rate)"}},
+                      "roofline": {"bound": "tensor", "achieved": algo, "peak": tf32_peak, "unit": "TFLOP/s",
+                                   "frac": algo / tf32_peak, "issued_TFLOPs": issued, "issued_frac": issued / tf32_peak,
+                                   "note": "achieved = ALGORITHMIC flops 2*B*NI*64; issued = 3 tf32 terms x K padded "
+                                           "64->72; peak = measured bf16 cuBLAS burst / 2 (tf32 runs at half the bf16 rate)"}},
         "final_loss": loss,
     }
+    line.update(extras)
     _emit(line)
+    if clocks:
+        clocks.stop()
     if world > 1:
         dist.destroy_process_group()
 

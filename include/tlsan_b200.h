@@ -223,7 +223,8 @@ int tlsan_label_rank_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const
 
 /* Host helper (no GPU work): pack the 9-tuple of TLSAN/input.py:54,107 (int64 ids, fp32 hist_t) into
  * ONE int32 staging buffer -- the int64->int32 feed cast of model.py:210-222 -- multi-threaded, with
- * the id range checks TF's CPU gather performs.  Segment order (each rounded up to 4 words):
+ * the id range checks TF's CPU gather performs (nthreads = 0: min(8, host cores / LOCAL_WORLD_SIZE), so the ranks of a
+ * node share the cores).  Segment order (each rounded up to 4 words):
  * u, i, second (i2 as int32, or y as fp32 bits), c, sl, sl_new, hist_i[B*L], hist_i_new[B*S],
  * hist_t[B*L].  Returns TLSAN_E_DIMS and names the field in tlsan_last_error() if an id is out of range. */
 int tlsan_pack_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int64_t* i, const int64_t* i2,
@@ -242,6 +243,17 @@ int tlsan_stage_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int
                            const float* y, const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t,
                            const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* pinned, int32_t* dev,
                            int64_t words, int32_t validate, int32_t nthreads, void* stream);
+
+/* The same two helpers for batches whose integer fields are already int32 (no narrowing pass; tlsan_b200/input.py
+ * emits such batches): half the host memory traffic of the feed, same range checks. */
+int tlsan_pack_batch_host_i32(const tlsan_dims_t* dims, const int32_t* u, const int32_t* i, const int32_t* i2,
+                              const float* y, const int32_t* hist_i, const int32_t* hist_i_new, const float* hist_t,
+                              const int32_t* sl, const int32_t* sl_new, const int32_t* c, int32_t* out,
+                              int64_t out_words, int32_t validate, int32_t nthreads);
+int tlsan_stage_batch_host_i32(const tlsan_dims_t* dims, const int32_t* u, const int32_t* i, const int32_t* i2,
+                               const float* y, const int32_t* hist_i, const int32_t* hist_i_new, const float* hist_t,
+                               const int32_t* sl, const int32_t* sl_new, const int32_t* c, int32_t* pinned,
+                               int32_t* dev, int64_t words, int32_t validate, int32_t nthreads, void* stream);
 
 /* Device-resident dataset.  CSR image, in HBM, of the samples built by
  * TLSAN/build_dataset.py:58-59,71: per sample r its user, its long-term history

@@ -77,6 +77,9 @@ _SIGS = {
     "tlsan_label_rank_ws": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
+    "tlsan_pack_batch_host_i32": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
+    "tlsan_stage_batch_host_i32": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32,
+                                                                                      C.c_void_p]),
     "tlsan_stage_words": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_int64)]),
     "tlsan_stage_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32,
                                                                                   C.c_void_p]),

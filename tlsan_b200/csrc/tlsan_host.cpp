@@ -3,6 +3,7 @@
 // validation TF's CPU gather would do (InvalidArgumentError) folded into the same pass.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 #include <vector>
@@ -20,17 +21,34 @@ namespace {
 // Both are plain SSE2 shifts / subtracts / ORs, so the loop runs at memory speed.
 struct Chk { uint64_t hi64 = 0; uint32_t neg = 0; bool used = false; };
 
-void cvt(const int64_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n, int32_t hi, Chk& c) {
+template <typename IdT>
+void cvt(const IdT* __restrict__ src, int32_t* __restrict__ dst, int64_t n, int32_t hi, Chk& c) {
   uint64_t h = c.hi64; uint32_t g = c.neg;
   const int32_t hi1 = hi - 1;
   for (int64_t k = 0; k < n; ++k) {
-    const int64_t v = src[k];
+    const int64_t v = (int64_t)src[k];
     const int32_t w = (int32_t)v;
-    h |= (uint64_t)v >> 31;
+    h |= (uint64_t)v >> 31;                 // int32 input: negative values sign-extend and are caught here too
     g |= (uint32_t)(hi1 - w);
     dst[k] = w;
   }
   c.hi64 = h; c.neg = g; c.used = true;
+}
+// worker threads per staging call: at most 8, and the host cores are shared by the ranks of the node (torchrun
+// exports LOCAL_WORLD_SIZE): 8 ranks x 32 threads on 32 cores was the largest piece of the round-1 8-GPU e2e loss
+int pool_threads(int32_t nthreads) {
+  if (nthreads > 0) return nthreads < 8 ? nthreads : 8;
+  static int cached = 0;
+  if (!cached) {
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    const char* e = getenv("LOCAL_WORLD_SIZE");
+    const int ranks = e && atoi(e) > 0 ? atoi(e) : 1;
+    int t = hw / ranks;
+    if (const char* o = getenv("TLSAN_PACK_THREADS")) t = atoi(o);
+    cached = t < 1 ? 1 : (t > 8 ? 8 : t);
+  }
+  return cached;
 }
 inline bool bad(const Chk& c) { return c.used && (c.hi64 != 0 || (c.neg >> 31) != 0); }
 inline int64_t up4(int64_t n) { return (n + 3) / 4 * 4; }
@@ -101,9 +119,10 @@ Layout layout_of(const tlsan_dims_t* d) {
 
 // Pack in three phases (hist_i_new | hist_t + scalars | hist_i); after phase k is complete on every thread the
 // caller's thread issues the host->device copy of that phase's words, which overlaps the packing of phase k+1.
-int pack_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const int64_t* i2, const float* y,
-              const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t, const int64_t* sl,
-              const int64_t* sl_new, const int64_t* c, int32_t* out, int64_t out_words, int32_t validate,
+template <typename IdT>
+int pack_impl(const tlsan_dims_t* d, const IdT* u, const IdT* i, const IdT* i2, const float* y,
+              const IdT* hist_i, const IdT* hist_i_new, const float* hist_t, const IdT* sl,
+              const IdT* sl_new, const IdT* c, int32_t* out, int64_t out_words, int32_t validate,
               int32_t nthreads, int32_t* dev, cudaStream_t st) {
   if (!d || !u || !i || !hist_i || !hist_i_new || !hist_t || !sl || !sl_new || !c || !out || (!i2 && !y)) {
     tlsan_set_error("tlsan_pack_batch_host: NULL argument");
@@ -115,9 +134,7 @@ int pack_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const i
     tlsan_set_error("tlsan_pack_batch_host: output holds %lld words, need %lld", (long long)out_words, (long long)Y.total);
     return TLSAN_E_WORKSPACE;
   }
-  int T = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
-  if (T < 1) T = 1;
-  if (T > 8) T = 8;
+  int T = pool_threads(nthreads);
   if (B * (2 * L + S) < 200000) T = 1;
   std::vector<Chk> k_hi(T), k_hn(T);
   Chk k_u, k_i, k_2, k_c, k_sl, k_sn;
@@ -185,9 +202,10 @@ int pack_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const i
 // ---- compact staging: the session matrix hist_i_new [B][S] is almost all padding (S = longest session of the batch,
 // 87 % of the sessions hold one item), so it travels ragged -- offsets [B] + the valid items -- and a kernel rebuilds
 // the padded matrix in HBM.  Staging layout = the packed batch layout followed by [offsets up4(B) | items up4(B*S)].
-int stage_compact_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const int64_t* i2, const float* y,
-                       const int64_t* hist_i, const int64_t* hist_i_new, const float* hist_t, const int64_t* sl,
-                       const int64_t* sl_new, const int64_t* c, int32_t* out, int32_t* dev, int64_t words,
+template <typename IdT>
+int stage_compact_impl(const tlsan_dims_t* d, const IdT* u, const IdT* i, const IdT* i2, const float* y,
+                       const IdT* hist_i, const IdT* hist_i_new, const float* hist_t, const IdT* sl,
+                       const IdT* sl_new, const IdT* c, int32_t* out, int32_t* dev, int64_t words,
                        int32_t validate, int32_t nthreads, cudaStream_t st) {
   if (!d || !u || !i || !hist_i || !hist_i_new || !hist_t || !sl || !sl_new || !c || !out || !dev || (!i2 && !y)) {
     tlsan_set_error("tlsan_stage_batch_host: NULL argument");
@@ -201,9 +219,7 @@ int stage_compact_impl(const tlsan_dims_t* d, const int64_t* u, const int64_t* i
                     (long long)need);
     return TLSAN_E_WORKSPACE;
   }
-  int T = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
-  if (T < 1) T = 1;
-  if (T > 8) T = 8;
+  int T = pool_threads(nthreads);
   if (B * (2 * L + S) < 200000) T = 1;
   struct PerThread { Chk u, i, s2, c, sl, sn, hi, hn; int64_t nnew = 0; bool sl_low = false; };
   std::vector<PerThread> pt(T);
@@ -319,6 +335,25 @@ extern "C" int tlsan_stage_batch_host(const tlsan_dims_t* d, const int64_t* u, c
                                       const float* hist_t, const int64_t* sl, const int64_t* sl_new, const int64_t* c,
                                       int32_t* pinned, int32_t* dev, int64_t words, int32_t validate,
                                       int32_t nthreads, void* stream) {
+  return stage_compact_impl(d, u, i, i2, y, hist_i, hist_i_new, hist_t, sl, sl_new, c, pinned, dev, words, validate,
+                            nthreads, (cudaStream_t)stream);
+}
+
+// The same two entry points for batches whose integer fields are ALREADY int32 (tlsan_b200/input.py emits them):
+// no 64 -> 32 bit narrowing, half the host memory traffic; the range checks are unchanged.
+extern "C" int tlsan_pack_batch_host_i32(const tlsan_dims_t* d, const int32_t* u, const int32_t* i, const int32_t* i2,
+                                         const float* y, const int32_t* hist_i, const int32_t* hist_i_new,
+                                         const float* hist_t, const int32_t* sl, const int32_t* sl_new, const int32_t* c,
+                                         int32_t* out, int64_t out_words, int32_t validate, int32_t nthreads) {
+  return pack_impl(d, u, i, i2, y, hist_i, hist_i_new, hist_t, sl, sl_new, c, out, out_words, validate, nthreads,
+                   nullptr, nullptr);
+}
+
+extern "C" int tlsan_stage_batch_host_i32(const tlsan_dims_t* d, const int32_t* u, const int32_t* i, const int32_t* i2,
+                                          const float* y, const int32_t* hist_i, const int32_t* hist_i_new,
+                                          const float* hist_t, const int32_t* sl, const int32_t* sl_new,
+                                          const int32_t* c, int32_t* pinned, int32_t* dev, int64_t words,
+                                          int32_t validate, int32_t nthreads, void* stream) {
   return stage_compact_impl(d, u, i, i2, y, hist_i, hist_i_new, hist_t, sl, sl_new, c, pinned, dev, words, validate,
                             nthreads, (cudaStream_t)stream);
 }

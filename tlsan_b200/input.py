@@ -55,8 +55,17 @@ class CsrDataset:
         return cls(uid, pre_off, pre_items, pre_time.astype(np.float32), new_off, new_items, cand, second, ucate,
                    is_test)
 
-    def collate(self, idx, k):
-        """Rows ``idx`` in the layout of DataInput.__next__ / DataInputTest.__next__."""
+    def collate(self, idx, k, index_dtype=np.int64):
+        """Rows ``idx`` in the layout of DataInput.__next__ / DataInputTest.__next__.  ``index_dtype=np.int32``
+        emits every integer field as int32 (same values): Model.stage_batch then skips the 64 -> 32 bit narrowing
+        pass of the feed (model.py:210-222 casts to int32 anyway)."""
+        out = self._collate(idx, k)
+        if np.dtype(index_dtype) == np.int64:
+            return out
+        return tuple(np.ascontiguousarray(f, dtype=index_dtype) if n != 5 and np.issubdtype(np.asarray(f).dtype, np.integer)
+                     else f for n, f in enumerate(out))
+
+    def _collate(self, idx, k):
         idx = np.asarray(idx, np.int64)
         start, stop = self.pre_off[idx], self.pre_off[idx + 1]
         length = stop - start
@@ -87,8 +96,9 @@ class CsrDataset:
 class _Input:
     is_test = False
 
-    def __init__(self, data, batch_size, k):
+    def __init__(self, data, batch_size, k, index_dtype=np.int64):
         self.k = k
+        self.index_dtype = index_dtype
         self.batch_size = batch_size
         self.data = data
         self.csr = data if isinstance(data, CsrDataset) else CsrDataset.from_samples(data, self.is_test)
@@ -105,7 +115,7 @@ class _Input:
         lo = self.i * self.batch_size
         hi = min(lo + self.batch_size, len(self.csr))
         self.i += 1
-        return self.i, self.csr.collate(np.arange(lo, hi), self.k)
+        return self.i, self.csr.collate(np.arange(lo, hi), self.k, self.index_dtype)
 
 
 class DataInput(_Input):

@@ -104,14 +104,19 @@ def pack_batch(lib, batch, dims, is_test, out, validate=True, dev_ptr=None, stre
     Out-of-range ids raise IndexError, like tf.gather on CPU (InvalidArgumentError).
     With ``dev_ptr`` the words are also copied to the device on ``stream``, phase by phase while the
     rest is still being packed (tlsan_stage_batch_host; ``out`` must then be pinned memory)."""
+    # integer fields that are ALL int32 already (tlsan_b200.input emits them) skip the 64 -> 32 bit narrowing pass
+    ints = [batch[k] for k in (0, 1, 3, 4, 6, 7, 8)] + ([batch[2]] if is_test else [])
+    narrow = all(isinstance(x, np.ndarray) and x.dtype == np.int32 for x in ints)
+    idt = np.int32 if narrow else np.int64
+
     def i64(x):
-        return np.ascontiguousarray(x, dtype=np.int64)
+        return np.ascontiguousarray(x, dtype=idt)
     B, S = dims.B, dims.S
     u, i, c, sl, sl_new = i64(batch[0]), i64(batch[1]), i64(batch[8]), i64(batch[6]), i64(batch[7])
     hist_i = i64(batch[3])
     hist_i_new = i64(batch[4])
     if hist_i_new.shape[1] == 0:
-        hist_i_new = np.zeros((B, 1), np.int64)
+        hist_i_new = np.zeros((B, 1), idt)
     if np.issubdtype(np.asarray(batch[5]).dtype, np.integer):
         # raw day gaps d = cur_day - day + 1 (0 = padding): same 4-byte words, bucketed on the GPU while gathering
         hist_t = np.ascontiguousarray(batch[5], dtype=np.int32).view(np.float32)
@@ -122,11 +127,13 @@ def pack_batch(lib, batch, dims, is_test, out, validate=True, dev_ptr=None, stre
     if hist_i.shape != (B, dims.L) or hist_t.shape != (B, dims.L) or hist_i_new.shape != (B, S):
         raise ValueError("batch arrays have inconsistent shapes")
     p = lambda a: None if a is None else a.ctypes.data
+    f_pack = lib.tlsan_pack_batch_host_i32 if narrow else lib.tlsan_pack_batch_host
+    f_stage = lib.tlsan_stage_batch_host_i32 if narrow else lib.tlsan_stage_batch_host
     if dev_ptr is None:
-        rc = lib.tlsan_pack_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
+        rc = f_pack(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
                                        p(sl), p(sl_new), p(c), out.ctypes.data, out.size, 1 if validate else 0, 0)
     else:
-        rc = lib.tlsan_stage_batch_host(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
+        rc = f_stage(C.byref(dims), p(u), p(i), p(i2), p(y), p(hist_i), p(hist_i_new), p(hist_t),
                                         p(sl), p(sl_new), p(c), out.ctypes.data, dev_ptr, out.size,
                                         1 if validate else 0, 0, stream)
     if rc == -1:
@@ -239,6 +246,8 @@ class Model(object):
         self._rank_ws = None
         self._flat = None
         self._stage_cache = {}
+        self._copy_stream = None
+        self._prefetched = None
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
 
@@ -277,9 +286,10 @@ class Model(object):
                 self._presorted = None
         return self._ws[slot]
 
-    def stage_batch(self, batch, is_test=False):
+    def stage_batch(self, batch, is_test=False, out=None):
         """Pack the input.py 9-tuple into pinned memory (tlsan_pack_batch_host: multi-threaded
-        int64->int32 cast + id range checks) and copy it to the device (one H2D)."""
+        int64->int32 cast + id range checks) and copy it to the device (one H2D).  `out` (optional): a device
+        int32 tensor to stage into instead of a fresh allocation (the double-buffered feed of `prefetch`)."""
         B = len(batch[0])
         S = max(int(np.shape(batch[4])[1]), 1)
         if np.shape(batch[3])[1] != self.L:
@@ -291,10 +301,13 @@ class Model(object):
         words = int(words.value)
         key = (B, S)
         if key not in self._stage_cache:
-            self._stage_cache[key] = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.cuda.Event())
-        host, ev = self._stage_cache[key]
+            self._stage_cache[key] = [0, [(torch.empty(words, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                                          for _ in range(2)]]
+        slot = self._stage_cache[key]
+        slot[0] ^= 1                          # two pinned buffers per shape: one may still feed a copy in flight
+        host, ev = slot[1][slot[0]]
         ev.synchronize()                      # the previous copy out of this pinned buffer has finished
-        dev = torch.empty(words, dtype=torch.int32, device=self.device)
+        dev = out[:words] if out is not None else torch.empty(words, dtype=torch.int32, device=self.device)
         pack_batch(self._lib, batch, dims, is_test, host.numpy(), self.validate, dev.data_ptr(), self._stream())
         ev.record(torch.cuda.current_stream(self.device))
         # bytes that actually crossed PCIe: everything but the padded session matrix, plus its ragged form
@@ -418,12 +431,55 @@ class Model(object):
             self._arenas = ptrs
         return self._arenas
 
-    def train(self, sess, batch, lr, add_summary=False, global_batch=None):
+    def prefetch(self, batch, is_test=False):
+        """Stage `batch` NOW on a side copy stream (pack on the host, H2D, session expansion); the next train /
+        eval call that is given the same tuple object picks the staged copy up instead of staging again."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._feed_ring, self._feed_i = [], 0
+        B, S = len(batch[0]), max(int(np.shape(batch[4])[1]), 1)
+        words = C.c_int64()
+        check(self._lib.tlsan_stage_words(C.byref(self._dims(B, S)), C.byref(words)))
+        words = int(words.value)
+        if len(self._feed_ring) < 3:          # three persistent device buffers: staged / in use / being filled
+            self._feed_ring.append([torch.empty(words + words // 8, dtype=torch.int32, device=self.device), None])
+        slot = self._feed_ring[self._feed_i % len(self._feed_ring)]
+        self._feed_i += 1
+        if slot[0].numel() < words:
+            torch.cuda.synchronize(self.device)
+            slot[0] = torch.empty(words + words // 8, dtype=torch.int32, device=self.device)
+            slot[1] = None
+        if slot[1] is not None:
+            self._copy_stream.wait_event(slot[1])      # the step that last read this buffer has finished
+        with torch.cuda.stream(self._copy_stream):
+            db = self.stage_batch(batch, is_test=is_test, out=slot[0])
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._prefetched = (batch, is_test, db, ev, slot)
+
+    def drop_prefetch(self):
+        self._prefetched = None
+
+    def _staged(self, batch, is_test):
+        """(DeviceBatch, ring slot or None) for `batch`: the prefetched copy if it is this very tuple."""
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf[0] is batch and pf[1] == is_test:
+            torch.cuda.current_stream(self.device).wait_event(pf[3])
+            return pf[2], pf[4]
+        return self.stage_batch(batch, is_test=is_test), None
+
+    def train(self, sess, batch, lr, add_summary=False, global_batch=None, prefetch=None):
         """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op].
         Data parallel: `batch` is this rank's block of the global batch; `global_batch` = its total row count
-        (found with one small all_reduce when omitted)."""
-        db = self.stage_batch(batch, is_test=False)
+        (found with one small all_reduce when omitted).  `prefetch` (optional) = the batch of the NEXT call: it is
+        packed and copied to the device while this step's kernels run (double-buffered feed)."""
+        db, slot = self._staged(batch, False)
         stats = self.train_staged(db, float(lr), global_batch=global_batch)
+        if slot is not None:                  # its staging buffer may be refilled once this step has run
+            slot[1] = torch.cuda.Event()
+            slot[1].record(torch.cuda.current_stream(self.device))
+        if prefetch is not None:
+            self.prefetch(prefetch)
         loss = float(stats[STAT["loss"]].item())
         self.last_d2h_bytes = 4
         if add_summary and self.train_writer is not None:

@@ -30,3 +30,28 @@ dbs = [m.stage_batch(b) for b in hb]
 print("step ms", t(lambda k: m.train_staged(dbs[k % 4], 1.0)))
 print("stage ms", t(lambda k: m.stage_batch(hb[k % 4])))
 print("train ms", t(lambda k: m.train(None, hb[k % 4], 1.0)))
+
+# double-buffered feed: where the wall time of one call goes
+import time as _t
+m.prefetch(hb[0])
+acc = np.zeros(4)
+torch.cuda.synchronize()
+N = 50
+t00 = _t.perf_counter()
+for k in range(N):
+    t0 = _t.perf_counter()
+    db, slot = m._staged(hb[k % 4], False)
+    t1 = _t.perf_counter()
+    st = m.train_staged(db, 1.0)
+    if slot is not None:
+        slot[1] = torch.cuda.Event(); slot[1].record()
+    t2 = _t.perf_counter()
+    m.prefetch(hb[(k + 1) % 4])
+    t3 = _t.perf_counter()
+    st[0].item()
+    t4 = _t.perf_counter()
+    acc += [t1 - t0, t2 - t1, t3 - t2, t4 - t3]
+print("prefetch loop ms/step", (_t.perf_counter() - t00) / N * 1e3, "take/enqueue/prefetch/item ms", acc / N * 1e3)
+hb32 = [tuple(np.ascontiguousarray(f, dtype=np.int32) if n != 5 and n != 2 else f for n, f in enumerate(b)) for b in hb]
+print("train int32 feed ms", t(lambda k: m.train(None, hb32[k % 4], 1.0, prefetch=hb32[(k + 1) % 4]), 50))
+print("train int64 feed ms", t(lambda k: m.train(None, hb[k % 4], 1.0, prefetch=hb[(k + 1) % 4]), 50))
