@@ -38,9 +38,10 @@ def main():
     ap.add_argument("--test-batch-size", type=int, default=128)
     ap.add_argument("--eval-freq", type=int, default=1000)
     ap.add_argument("--no-topk", action="store_true", help="skip the P@k / R@k passes at every evaluation")
+    ap.add_argument("--seed", type=int, default=1234, help="shuffle + initialisation seed (train.py:176-178 uses 1234)")
     args = ap.parse_args()
-    random.seed(1234)
-    np.random.seed(1234)
+    random.seed(args.seed)
+    np.random.seed(args.seed)
     dm = load_digital_music()
     user_count, item_count, cate_count = dm.counts
     train_set, test_set = list(dm.train_set), list(dm.test_set)
@@ -48,7 +49,7 @@ def main():
               "itemid_embedding_size": 32, "userid_embedding_size": 32, "cateid_embedding_size": 32,
               "optimizer": "sgd", "max_gradient_norm": 5.0, "model_dir": "save_path",
               "user_count": user_count, "item_count": item_count, "cate_count": cate_count}
-    model = Model(config, dm.icl, seed=1234)
+    model = Model(config, dm.icl, seed=args.seed)
     print("Init finish.\tCost time: 0.00s\tInit AUC: %.4f" % eval_auc(test_set, model, args.test_batch_size, 10), flush=True)
     lr, best_auc, avg_loss, start = 1.0, 0.0, 0.0, time.time()
     best_prec, best_recall, curve = [0.0] * 6, [0.0] * 6, []
@@ -82,7 +83,7 @@ def main():
         print("Epoch %d DONE\tCost time: %.2f" % (model.global_epoch_step.eval(), time.time() - start), flush=True)
         model.global_epoch_step_op.eval()
     wall = time.time() - start
-    print(json.dumps({"best_test_auc": round(float(best_auc), 4), "readme_auc": 0.9753, "steps": model.global_step.eval(),
+    print(json.dumps({"seed": args.seed, "best_test_auc": round(float(best_auc), 4), "readme_auc": 0.9753, "steps": model.global_step.eval(),
                       "wall_s": round(wall, 1), "train_samples_per_s_incl_eval": round(model.global_step.eval() * args.train_batch_size / wall),
                       "best_recall_at_1_10_20_30_40_50": [round(float(x), 4) for x in best_recall], "curve": curve}))
 

@@ -297,8 +297,27 @@ int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int3
  *   tlsan_sgd_dense           W <- W - lr*((g + reg*W) * *scale) element-wise (g may be NULL: pure L2 decay)
  *   tlsan_shard_apply_replicated  norm / clip scale / loss statistics and the update of cate_emb, user_emb,
  *                             usert_emb and the small parameters from rank-summed gradients; item_sumsq =
- *                             rank-summed partial sums of squares of the whole sharded item_emb. */
+ *                             rank-summed partial sums of squares of the whole sharded item_emb.
+ *   tlsan_shard_apply_grads   owner: W[local_ids[k]] -= lr * *scale * packed[k] (ids < 0 = padding, skipped); the L2
+ *                             decay of every shard row is a separate dense pass (tlsan_sgd_dense with g = NULL)
+ *   tlsan_route_ids           device-side routing of the distinct item ids of a batch, no host round trip: position
+ *                             p = owner * ceil(NI / world) + local of every id (cyclic: owner = id % world; block: p = id),
+ *                             presence bitmap over the positions, compact row of an id = owner * cap + its rank inside
+ *                             the owner's group.  phase 0: bitmap + per-word popcounts into word_prefix (the caller
+ *                             turns them into an INCLUSIVE prefix, e.g. torch.cumsum); phase 1: send_ids[world][cap] =
+ *                             owner-local row ids requested from every owner (ascending, padded with -1), counts[world],
+ *                             *overflow = 1 if a group exceeds cap, and dst[q][e] = compact row of src[q][e] for the
+ *                             nfields id arrays of the packed batch.  With fixed cap the all-to-alls run with equal
+ *                             splits.  dst_index / src_index of the pack / unpack helpers may then be NULL (identity),
+ *                             and negative local ids mark padding slots (zero rows, skipped by accum / apply).
+ *   tlsan_route_bitmap_words  words of the presence bitmap (= of word_prefix) for (NI, world) */
 #define TLSAN_SHARD_ROW 36
+int tlsan_shard_apply_grads(const float* packed, const int32_t* local_ids, int64_t n, float* W_emb, float* W_b,
+                            float lr, const float* scale, void* stream);
+int tlsan_route_bitmap_words(int64_t NI, int32_t world, int64_t* words);
+int tlsan_route_ids(const int32_t* const* src, int32_t* const* dst, const int64_t* n, int32_t nfields, int64_t NI,
+                    int32_t world, int32_t cyclic, int32_t cap, uint32_t* bitmap, int32_t* word_prefix,
+                    int32_t* send_ids, int32_t* counts, int32_t* overflow, int32_t phase, void* stream);
 int tlsan_shard_pack_rows(const float* emb_shard, const float* item_b_shard, const int32_t* icl_shard,
                           const int32_t* local_ids, int64_t n, int64_t n_local, float* out, int32_t* bad_flag,
                           void* stream);

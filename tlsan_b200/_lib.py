@@ -91,6 +91,12 @@ _SIGS = {
                                           C.c_void_p]),
     "tlsan_shard_pack_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tlsan_shard_accum_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tlsan_shard_apply_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                          C.c_void_p]),
+    "tlsan_route_bitmap_words": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
+    "tlsan_route_ids": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p]),
     "tlsan_shard_apply_replicated": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                                C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -22,7 +22,11 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_pack_rows(const float* 
   const int c = (int)(g - k * 9);
   if (k >= n) return;
   const long long id = ids[k];
-  if (id < 0 || id >= n_local) {          // a foreign id reached this owner: flag, do not fault
+  if (id < 0) {                           // padding slot of a fixed-capacity request list: zero row
+    reinterpret_cast<float4*>(out + k * TLSAN_SHARD_ROW)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  if (id >= n_local) {                    // a foreign id reached this owner: flag, do not fault
     if (c == 0) atomicExch(bad, 1);
     return;
   }
@@ -42,7 +46,8 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_unpack_rows(const float
   const long long k = g / 9;
   const int c = (int)(g - k * 9);
   if (k >= n) return;
-  const long long r = dst[k];
+  const long long r = dst ? dst[k] : k;
+  if (r < 0) return;
   const float4 v = __ldg(reinterpret_cast<const float4*>(packed + k * TLSAN_SHARD_ROW) + c);
   if (c < 8) reinterpret_cast<float4*>(emb_c + r * 32)[c] = v;
   else { item_b_c[r] = v.x; icl_c[r] = __float_as_int(v.y); }
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_pack_grads(const float*
   const long long k = g / 9;
   const int c = (int)(g - k * 9);
   if (k >= n) return;
-  const long long r = src[k];
+  const long long r = src ? src[k] : k;
   float4 v;
   if (c < 8) v = __ldg(reinterpret_cast<const float4*>(g_i + r * 64) + c);
   else v = make_float4(__ldg(g_b + r), 0.f, 0.f, 0.f);
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_accum_grads(const float
   const int c = (int)(g - k * 9);
   if (k >= n) return;
   const long long id = ids[k];
+  if (id < 0) return;                     // padding slot
   const float4 v = __ldg(reinterpret_cast<const float4*>(packed + k * TLSAN_SHARD_ROW) + c);
   if (c < 8) {
     float4* p = reinterpret_cast<float4*>(g_emb + id * 32) + c;
@@ -85,6 +91,109 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_accum_grads(const float
   } else {
     g_b[id] += v.x;
   }
+}
+
+// W[ids[k]] -= lr * scale * packed[k][0..32), b[ids[k]] -= lr * scale * packed[k][32]  (the L2 decay of every row is a
+// separate dense pass, k_sgd_dense with g = NULL).  Same race rule as k_shard_accum_grads.
+__global__ void __launch_bounds__(SHARD_THREADS) k_shard_apply_grads(const float* __restrict__ packed,
+                                                                     const int* __restrict__ ids, long long n,
+                                                                     float* __restrict__ W, float* __restrict__ b,
+                                                                     float lr, const float* __restrict__ scale_p) {
+  const long long g = (long long)blockIdx.x * SHARD_THREADS + threadIdx.x;
+  const long long k = g / 9;
+  const int c = (int)(g - k * 9);
+  if (k >= n) return;
+  const long long id = ids[k];
+  if (id < 0) return;
+  const float f = lr * *scale_p;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(packed + k * TLSAN_SHARD_ROW) + c);
+  if (c < 8) {
+    float4* p = reinterpret_cast<float4*>(W + id * 32) + c;
+    float4 a = *p;
+    a.x -= f * v.x; a.y -= f * v.y; a.z -= f * v.z; a.w -= f * v.w;
+    *p = a;
+  } else {
+    b[id] -= f * v.x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side routing of the distinct item ids of a batch (no torch.unique, no host round trip).
+// Every id has an owner-major POSITION p = owner * nloc + local (nloc = ceil(NI / W); cyclic partition: owner =
+// id % W, local = id / W; block partition: p = id).  A presence bitmap over the positions is the set of distinct ids;
+// an exclusive prefix of its word popcounts turns a position into its rank inside the owner's group, and the
+// COMPACT row of an id is owner * cap + rank -- a pure function of the batch, so the compact table, the category
+// CSR built on it and every summation order downstream are reproducible.  `cap` is a fixed per-owner capacity:
+// the all-to-alls run with equal splits; a group that does not fit raises the overflow flag.
+struct RouteGeo { int W, nloc, mod, cap; long long NI; };
+__device__ __forceinline__ long long route_pos(const RouteGeo& g, int id) {
+  return g.mod ? (long long)(id % g.W) * g.nloc + id / g.W : (long long)id;
+}
+struct RouteFields { const int* src[4]; int* dst[4]; long long n[4]; int nf; };
+
+__global__ void __launch_bounds__(256) k_route_mark(const RouteFields f, const RouteGeo g, unsigned int* __restrict__ bits) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int q = 0; q < f.nf; ++q)
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < f.n[q]; e += stride) {
+      const int id = __ldg(f.src[q] + e);
+      if (id < 0 || id >= g.NI) continue;                      // validated on the host; never fault here
+      const long long p = route_pos(g, id);
+      atomicOr(bits + (p >> 5), 1u << (p & 31));
+    }
+}
+__global__ void __launch_bounds__(256) k_route_popc(const unsigned int* __restrict__ bits, long long nwords,
+                                                    int* __restrict__ cnt) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nwords) cnt[w] = __popc(bits[w]);
+}
+// set bits strictly before position p, given the INCLUSIVE prefix of the word popcounts
+__device__ __forceinline__ int route_rank(const unsigned int* __restrict__ bits, const int* __restrict__ incl, long long p) {
+  const long long w = p >> 5;
+  const unsigned int word = __ldg(bits + w);
+  return __ldg(incl + w) - __popc(word) + __popc(word & ((1u << (p & 31)) - 1u));
+}
+// per owner: its request list (owner-local row ids, ascending, padded with -1 to cap) and its count
+__global__ void __launch_bounds__(256) k_route_emit(const unsigned int* __restrict__ bits, const int* __restrict__ incl,
+                                                    long long nwords, const RouteGeo g, int* __restrict__ send_ids,
+                                                    int* __restrict__ counts, int* __restrict__ overflow) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < g.W) {                                                // (first W threads also publish the group sizes)
+    const int lo = route_rank(bits, incl, (long long)w * g.nloc);
+    const long long endp = (long long)(w + 1) * g.nloc;
+    const int hi = endp >= nwords * 32 ? __ldg(incl + nwords - 1) : route_rank(bits, incl, endp);
+    counts[w] = hi - lo;
+    if (hi - lo > g.cap) atomicExch(overflow, 1);
+  }
+  if (w >= nwords) return;
+  unsigned int word = __ldg(bits + w);
+  int before = __ldg(incl + w) - __popc(word);
+  while (word) {
+    const int b = __ffs(word) - 1;
+    word &= word - 1;
+    const long long p = w * 32 + b;
+    const int o = (int)(p / g.nloc);
+    const int local = (int)(p - (long long)o * g.nloc);
+    const int rank = before - route_rank(bits, incl, (long long)o * g.nloc);
+    if (rank < g.cap) send_ids[(long long)o * g.cap + rank] = local;
+    ++before;
+  }
+}
+// id fields of the packed batch -> compact rows owner * cap + rank
+__global__ void __launch_bounds__(256) k_route_rewrite(const RouteFields f, const RouteGeo g,
+                                                       const unsigned int* __restrict__ bits, const int* __restrict__ incl) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int q = 0; q < f.nf; ++q)
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < f.n[q]; e += stride) {
+      const int id = __ldg(f.src[q] + e);
+      int out = 0;
+      if (id >= 0 && id < g.NI) {
+        const long long p = route_pos(g, id);
+        const int o = (int)(p / g.nloc);
+        const int rank = route_rank(bits, incl, p) - route_rank(bits, incl, (long long)o * g.nloc);
+        out = o * g.cap + min(rank, g.cap - 1);
+      }
+      f.dst[q][e] = out;
+    }
 }
 
 // out[k][0..32) = sum of the cate halves of the reduced rows of category k (CSR order) + its direct row
@@ -165,8 +274,7 @@ int tlsan_shard_unpack_rows(const float* packed, const int32_t* dst_index, int64
                             int32_t* icl_c, void* stream) {
   SHARD_REQUIRE(n >= 0, TLSAN_E_DIMS, "tlsan_shard_unpack_rows: n < 0");
   if (n == 0) return TLSAN_OK;
-  SHARD_REQUIRE(packed && dst_index && emb_c && item_b_c && icl_c, TLSAN_E_NULL,
-                "tlsan_shard_unpack_rows: NULL argument");
+  SHARD_REQUIRE(packed && emb_c && item_b_c && icl_c, TLSAN_E_NULL, "tlsan_shard_unpack_rows: NULL argument");
   SHARD_REQUIRE(((uintptr_t)emb_c & 15) == 0 && ((uintptr_t)packed & 15) == 0, TLSAN_E_ALIGN,
                 "tlsan_shard_unpack_rows: emb_c/packed must be 16-B aligned");
   k_shard_unpack_rows<<<grid9(n), SHARD_THREADS, 0, (cudaStream_t)stream>>>(packed, dst_index, n, emb_c, item_b_c,
@@ -179,7 +287,7 @@ int tlsan_shard_pack_grads(const float* g_i, const float* g_b, const int32_t* sr
                            void* stream) {
   SHARD_REQUIRE(n >= 0, TLSAN_E_DIMS, "tlsan_shard_pack_grads: n < 0");
   if (n == 0) return TLSAN_OK;
-  SHARD_REQUIRE(g_i && g_b && src_index && out, TLSAN_E_NULL, "tlsan_shard_pack_grads: NULL argument");
+  SHARD_REQUIRE(g_i && g_b && out, TLSAN_E_NULL, "tlsan_shard_pack_grads: NULL argument");
   SHARD_REQUIRE(((uintptr_t)g_i & 15) == 0 && ((uintptr_t)out & 15) == 0, TLSAN_E_ALIGN,
                 "tlsan_shard_pack_grads: g_i/out must be 16-B aligned");
   k_shard_pack_grads<<<grid9(n), SHARD_THREADS, 0, (cudaStream_t)stream>>>(g_i, g_b, src_index, n, out);
@@ -196,6 +304,63 @@ int tlsan_shard_accum_grads(const float* packed, const int32_t* local_ids, int64
                 "tlsan_shard_accum_grads: g_emb/packed must be 16-B aligned");
   k_shard_accum_grads<<<grid9(n), SHARD_THREADS, 0, (cudaStream_t)stream>>>(packed, local_ids, n, g_emb, g_b);
   TLSAN_CHECK_LAUNCH("k_shard_accum_grads");
+  return TLSAN_OK;
+}
+
+int tlsan_shard_apply_grads(const float* packed, const int32_t* local_ids, int64_t n, float* W_emb, float* W_b,
+                            float lr, const float* scale, void* stream) {
+  SHARD_REQUIRE(n >= 0, TLSAN_E_DIMS, "tlsan_shard_apply_grads: n < 0");
+  if (n == 0) return TLSAN_OK;
+  SHARD_REQUIRE(packed && local_ids && W_emb && W_b && scale, TLSAN_E_NULL, "tlsan_shard_apply_grads: NULL argument");
+  SHARD_REQUIRE(((uintptr_t)W_emb & 15) == 0 && ((uintptr_t)packed & 15) == 0, TLSAN_E_ALIGN,
+                "tlsan_shard_apply_grads: W_emb/packed must be 16-B aligned");
+  k_shard_apply_grads<<<grid9(n), SHARD_THREADS, 0, (cudaStream_t)stream>>>(packed, local_ids, n, W_emb, W_b, lr, scale);
+  TLSAN_CHECK_LAUNCH("k_shard_apply_grads");
+  return TLSAN_OK;
+}
+
+int tlsan_route_bitmap_words(int64_t NI, int32_t world, int64_t* words) {
+  SHARD_REQUIRE(NI > 0 && world > 0 && words, TLSAN_E_DIMS, "tlsan_route_bitmap_words: bad argument");
+  const long long nloc = (NI + world - 1) / world;
+  *words = (nloc * world + 31) / 32;
+  return TLSAN_OK;
+}
+
+int tlsan_route_ids(const int32_t* const* src, int32_t* const* dst, const int64_t* n, int32_t nfields, int64_t NI,
+                    int32_t world, int32_t cyclic, int32_t cap, uint32_t* bitmap, int32_t* word_prefix,
+                    int32_t* send_ids, int32_t* counts, int32_t* overflow, int32_t phase, void* stream) {
+  SHARD_REQUIRE(src && dst && n && bitmap && word_prefix && send_ids && counts && overflow, TLSAN_E_NULL,
+                "tlsan_route_ids: NULL argument");
+  SHARD_REQUIRE(nfields >= 1 && nfields <= 4 && NI > 0 && world > 0 && cap > 0, TLSAN_E_DIMS, "tlsan_route_ids: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  RouteFields f;
+  f.nf = nfields;
+  long long total = 0;
+  for (int q = 0; q < 4; ++q) {
+    f.src[q] = q < nfields ? src[q] : nullptr; f.dst[q] = q < nfields ? dst[q] : nullptr; f.n[q] = q < nfields ? n[q] : 0;
+    total += f.n[q];
+  }
+  RouteGeo g;
+  g.W = world; g.NI = NI; g.nloc = (int)((NI + world - 1) / world); g.mod = cyclic ? 1 : 0; g.cap = cap;
+  const long long nwords = ((long long)g.nloc * world + 31) / 32;
+  long long blocks = (total + 255) / 256;
+  const long long capb = (long long)tlsan_num_sms() * 16;
+  if (blocks > capb) blocks = capb;
+  if (blocks < 1) blocks = 1;
+  if (phase == 0) {            // presence bitmap + word popcounts; the caller turns word_prefix into an inclusive prefix
+    TLSAN_CHECK_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4, st));
+    k_route_mark<<<(unsigned)blocks, 256, 0, st>>>(f, g, bitmap);
+    TLSAN_CHECK_LAUNCH("k_route_mark");
+    k_route_popc<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(bitmap, nwords, word_prefix);
+    TLSAN_CHECK_LAUNCH("k_route_popc");
+    return TLSAN_OK;
+  }
+  // phase 1: request lists + compact batch
+  TLSAN_CHECK_CUDA(cudaMemsetAsync(send_ids, 0xff, (size_t)world * cap * 4, st));
+  k_route_emit<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(bitmap, word_prefix, nwords, g, send_ids, counts, overflow);
+  TLSAN_CHECK_LAUNCH("k_route_emit");
+  k_route_rewrite<<<(unsigned)blocks, 256, 0, st>>>(f, g, bitmap, word_prefix);
+  TLSAN_CHECK_LAUNCH("k_route_rewrite");
   return TLSAN_OK;
 }
 

@@ -8,21 +8,25 @@ same as ``Model.train`` -- the weights after a step equal the replicated model's
 
 One step on every rank:
 
-1. distinct item ids of the local batch (``hist_i``, ``hist_i_new``, ``i`` [, ``i2``]), sorted        -> ``uniq``
-2. NCCL all-to-all of the ids to their owners, owners answer with 144-B exchange rows
+1. distinct item ids of the local batch (``hist_i``, ``hist_i_new``, ``i`` [, ``i2``]) ON THE DEVICE: a presence
+   bitmap over owner-major positions, its popcount prefix, per-owner request lists of fixed capacity ``cap``
+   (tlsan_route_ids; no torch.unique, no host round trip -- the capacity is calibrated once on the first batch)
+2. NCCL all-to-all (equal splits) of the request lists to the owners, owners answer with 144-B exchange rows
    (item_emb row | item_b | icl), all-to-all back                        (tlsan_shard_pack_rows / _unpack_rows)
-3. the rows land in a COMPACT table (row r = r-th distinct id; category and user rows follow at a fixed
-   offset), the batch ids are rewritten to compact indices, and the unchanged fused kernels run on it
-   (``tlsan_step_grads``: sort, forward, backward, deterministic segmented reduce)
+3. the rows land in a COMPACT table (row owner * cap + rank of the id inside the owner's group; category and user
+   rows follow at a fixed offset), the batch ids are rewritten to compact rows, and the unchanged fused kernels
+   run on it (``tlsan_step_grads``: sort, forward, backward, deterministic segmented reduce)
 4. all-reduce (sum) of [user/usert gradients | small-parameter gradients, loss and norm partials | category
    gradients | partial sums of squares of the item shards]                                    -- ONE collective
-5. per-id gradient rows travel back to the owners with the splits of (2); an owner adds the contributions in
-   rank order (deterministic) into a dense shard-shaped buffer and applies W <- W - lr*scale*(g + reg*W) to
-   every row of its shard (the L2 term touches all rows, model.py:164-169)     (tlsan_shard_accum_grads, tlsan_sgd_dense)
+5. per-id gradient rows travel back to the owners (same equal splits); an owner first applies the L2 decay
+   W <- W (1 - lr*scale*reg) to every row of its shard (the L2 term touches all rows, model.py:164-169), then
+   subtracts lr*scale*g for the received rows, source ranks in rank order (deterministic)
+                                                                          (tlsan_sgd_dense, tlsan_shard_apply_grads)
 6. the replicated tables are updated identically on every rank                 (tlsan_shard_apply_replicated)
 
-PyTorch supplies device memory, ``torch.unique`` / ``sort`` for the index bookkeeping of (1) and the NCCL
-collectives; every gather, scatter, reduction and update of table data is a kernel of libtlsan_b200.so.
+PyTorch supplies device memory, one ``cumsum`` (the popcount prefix), one stable ``sort`` (category CSR of the
+compact table) and the NCCL collectives; every gather, scatter, reduction and update of table data is a kernel of
+libtlsan_b200.so.
 There is no CPU path.
 """
 import ctypes as C
@@ -92,7 +96,7 @@ class ShardedModel(object):
     """TLSAN with row-sharded item tables.  Same train / eval_auc surface as ``Model``."""
 
     def __init__(self, config, item_cate_list, process_group=None, partition="mod", seed=1234, device=None,
-                 validate=True):
+                 validate=True, route_capacity=None):
         if partition not in ("mod", "block"):
             raise ValueError("partition must be 'mod' or 'block'")
         Model._check_config(config)
@@ -138,10 +142,17 @@ class ShardedModel(object):
                 dense[off:off + shape[0] * shape[1]] = glorot(*shape).reshape(-1)
         self.dense = dense.to(dev)
 
-        self.cap = 0
+        self.cap = 0                         # rows of the compact table = world * per-owner capacity
+        self.route_cap = int(route_capacity) if route_capacity else 0      # 0: calibrated on the first batch
         self._grow(1024)
-        self._g_emb = torch.zeros(max(self.n_local, 1), 32, device=dev)
-        self._g_b = torch.zeros(max(self.n_local, 1), device=dev)
+        nw = C.c_int64()
+        check(self._lib.tlsan_route_bitmap_words(self.NI, self.world, C.byref(nw)))
+        self._bits = torch.zeros(int(nw.value), dtype=torch.int32, device=dev)
+        self._wpref = torch.zeros(int(nw.value), dtype=torch.int32, device=dev)
+        self._counts = torch.zeros(self.world, dtype=torch.int32, device=dev)
+        self._overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._xbuf = {}
         self._bad = torch.zeros(1, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
         self._ws = None
@@ -149,7 +160,6 @@ class ShardedModel(object):
         self._flat = None
         self._stage_cache = {}
         self.global_step = 0
-        self.last_unique = 0
         self.last_exchange_bytes = 0
         self.profile = None          # set to [] to collect (label, cuda event) marks per step (tools/bench_sharded.py)
 
@@ -226,51 +236,84 @@ class ShardedModel(object):
             f.append(("second", db.B))
         return f
 
-    def _fetch(self, db):
-        """Steps (1)-(3a): returns (compact DeviceBatch, plan) with the touched rows in the compact table."""
-        lib, st = self._lib, self._stream()
-        fields = self._id_fields(db)
-        ids = torch.cat([db.buf[db.offs[k]:db.offs[k] + n] for k, n in fields])
-        uniq, inv = torch.unique(ids, sorted=True, return_inverse=True)
-        n_u = int(uniq.numel())
-        self._grow(n_u)
-        order, recv_ids, in_splits, out_splits = route_ids(uniq.to(torch.int64), self.world, self.NI, self.partition,
-                                                           self.pg)
-        n_recv = int(recv_ids.numel())
-        local = local_of(recv_ids, self.world, self.NI, self.partition).to(torch.int32)
-        rows_out = torch.empty(max(n_recv, 1), SHARD_ROW, dtype=torch.float32, device=self.device)
-        check(lib.tlsan_shard_pack_rows(self.item_emb_shard.data_ptr(), self.item_b_shard.data_ptr(),
-                                        self.icl_shard.data_ptr(), local.data_ptr(), n_recv, self.n_local,
-                                        rows_out.data_ptr(), self._bad.data_ptr(), st))
-        rows_in = exchange(rows_out[:n_recv], out_splits, in_splits, self.pg, self.world)
-        order32 = order.to(torch.int32)
-        check(lib.tlsan_shard_unpack_rows(rows_in.data_ptr(), order32.data_ptr(), n_u, self.emb_c.data_ptr(),
-                                          self.item_b_c.data_ptr(), self.icl_c.data_ptr(), st))
-        # compact batch: same packed buffer with the id fields rewritten
-        cbuf = db.buf.clone()
-        inv32, o = inv.to(torch.int32), 0
-        for k, n in fields:
-            cbuf[db.offs[k]:db.offs[k] + n] = inv32[o:o + n]
-            o += n
-        cb = DeviceBatch(cbuf, db.B, db.L, db.S, db.offs, db.is_test)
-        self.last_unique = n_u
-        self.last_exchange_bytes = (n_u + n_recv) * (4 + 4 * SHARD_ROW)
-        plan = dict(n_u=n_u, order32=order32, local=local, in_splits=in_splits, out_splits=out_splits, n_recv=n_recv)
-        return cb, plan
+    def _calibrate(self, db):
+        """Per-owner capacity of the request lists, once: 1.25 x the largest group of the first batch (max over
+        ranks), rounded up to 1024.  The only place a batch is inspected on the host."""
+        ids = torch.cat([db.buf[db.offs[k]:db.offs[k] + n] for k, n in self._id_fields(db)])
+        uniq = torch.unique(ids.to(torch.int64))
+        cnt = torch.bincount(owner_of(uniq, self.world, self.NI, self.partition), minlength=self.world).max().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.pg)
+        nloc = -(-self.NI // self.world)
+        self.route_cap = min(max(1024, -(-int(1.25 * int(cnt.item())) // 1024) * 1024), -(-nloc // 1024) * 1024)
 
-    def _compact_csr(self, n_u):
+    def _buf(self, name, shape, dtype=torch.float32):
+        t = self._xbuf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._xbuf[name] = t
+        return t
+
+    def _a2a(self, name, send):
+        if self.world == 1:
+            return send
+        recv = self._buf(name, send.shape, send.dtype)
+        dist.all_to_all_single(recv, send, group=self.pg)
+        return recv
+
+    def _fetch(self, db):
+        """Steps (1)-(3a): returns (compact DeviceBatch, owner-side request lists [world * cap])."""
+        lib, st = self._lib, self._stream()
+        if int(self._ovf_host[0]):
+            raise _lib.TlsanError("a rank's request list exceeded route_capacity=%d in an earlier step; construct "
+                                  "ShardedModel(..., route_capacity=N) with a larger N" % self.route_cap)
+        if not self.route_cap:
+            self._calibrate(db)
+        W, cap = self.world, self.route_cap
+        self._grow(W * cap)
+        fields = self._id_fields(db)
+        cbuf = db.buf.clone()
+        nf = len(fields)
+        src = (C.c_void_p * 4)(*([db.buf.data_ptr() + 4 * db.offs[k] for k, _ in fields] + [None] * (4 - nf)))
+        dst = (C.c_void_p * 4)(*([cbuf.data_ptr() + 4 * db.offs[k] for k, _ in fields] + [None] * (4 - nf)))
+        cnt = (C.c_int64 * 4)(*([n for _, n in fields] + [0] * (4 - nf)))
+        send_ids = self._buf("send_ids", (W * cap,), torch.int32)
+        args = (src, dst, cnt, nf, self.NI, W, 1 if self.partition == "mod" else 0, cap, self._bits.data_ptr(),
+                self._wpref.data_ptr(), send_ids.data_ptr(), self._counts.data_ptr(), self._overflow.data_ptr())
+        check(lib.tlsan_route_ids(*args, 0, st))
+        self._wpref.cumsum_(0)                                       # inclusive prefix of the word popcounts
+        check(lib.tlsan_route_ids(*args, 1, st))
+        self._ovf_host.copy_(self._overflow, non_blocking=True)      # looked at by a LATER call: never waited for
+        recv_ids = self._a2a("recv_ids", send_ids)
+        rows_out = self._buf("rows_out", (W * cap, SHARD_ROW))
+        check(lib.tlsan_shard_pack_rows(self.item_emb_shard.data_ptr(), self.item_b_shard.data_ptr(),
+                                        self.icl_shard.data_ptr(), recv_ids.data_ptr(), W * cap, self.n_local,
+                                        rows_out.data_ptr(), self._bad.data_ptr(), st))
+        rows_in = self._a2a("rows_in", rows_out)
+        check(lib.tlsan_shard_unpack_rows(rows_in.data_ptr(), None, W * cap, self.emb_c.data_ptr(),
+                                          self.item_b_c.data_ptr(), self.icl_c.data_ptr(), st))
+        cb = DeviceBatch(cbuf, db.B, db.L, db.S, db.offs, db.is_test)
+        self.last_exchange_bytes = W * cap * (4 + 4 * SHARD_ROW)
+        return cb, recv_ids
+
+    @property
+    def last_unique(self):
+        """Distinct item ids of the last batch on this rank (reads the device counters: synchronises)."""
+        return int(self._counts.sum().item())
+
+    def _compact_csr(self):
         """Items of the compact table grouped by category (stable), for the hierarchical category reduce."""
-        icl = self.icl_c[:n_u]
-        self.cate_items[:n_u] = torch.sort(icl, stable=True).indices.to(torch.int32)
+        icl = self.icl_c[:self.cap]
+        self.cate_items[:self.cap] = torch.sort(icl, stable=True).indices.to(torch.int32)
         self.cate_off[1:] = torch.cumsum(torch.bincount(icl, minlength=self.NC), 0).to(torch.int32)
 
     # ------------------------------------------------------------------ training
     def train_staged(self, db, lr, global_batch=None):
         lib, st = self._lib, self._stream()
         self._mark("start")
-        cb, plan = self._fetch(db)
-        n_u = plan["n_u"]
-        self._compact_csr(n_u)
+        cb, recv_ids = self._fetch(db)
+        W, cap = self.world, self.route_cap
+        self._compact_csr()
         self._mark("fetch_rows")
         Bg = global_batch if global_batch is not None else db.B * self.world
         dims = self._dims(db.B, db.S, Bg)
@@ -298,28 +341,21 @@ class ShardedModel(object):
         if self.world > 1:
             dist.all_reduce(flat[f_gu:], group=self.pg)
         self._mark("allreduce")
-        # gradient rows of the distinct ids -> owners (reverse of the row exchange)
-        grads_out = torch.empty(max(n_u, 1), SHARD_ROW, dtype=torch.float32, device=self.device)
-        check(lib.tlsan_shard_pack_grads(flat.data_ptr(), fp(f_gb), plan["order32"].data_ptr(), n_u,
-                                         grads_out.data_ptr(), st))
-        grads_in = exchange(grads_out[:n_u], plan["in_splits"], plan["out_splits"], self.pg, self.world)
-        self._g_emb.zero_()
-        self._g_b.zero_()
-        o = 0
-        for cnt in plan["out_splits"]:          # source ranks in rank order: fixed summation order
-            if cnt:
-                check(lib.tlsan_shard_accum_grads(grads_in.data_ptr() + 4 * SHARD_ROW * o,
-                                                  plan["local"].data_ptr() + 4 * o, cnt, self._g_emb.data_ptr(),
-                                                  self._g_b.data_ptr(), st))
-            o += cnt
+        # gradient rows of the requested ids -> owners (reverse of the row exchange, same equal splits)
+        grads_out = self._buf("grads_out", (W * cap, SHARD_ROW))
+        check(lib.tlsan_shard_pack_grads(flat.data_ptr(), fp(f_gb), None, W * cap, grads_out.data_ptr(), st))
+        grads_in = self._a2a("grads_in", grads_out)
         self._mark("return_grads")
         check(lib.tlsan_shard_apply_replicated(C.byref(dims), C.byref(self._params), fp(f_cate), fp(f_gu), fp(f_dgrad),
                                                fp(f_sq), NSQ, lr, self.reg, self.clip, self._ws.data_ptr(),
                                                self._ws.numel(), self._stats.data_ptr(), st))
         scale = self._stats.data_ptr() + 4 * STAT["scale"]
-        check(lib.tlsan_sgd_dense(self.item_emb_shard.data_ptr(), self._g_emb.data_ptr(), self.n_local * 32, lr,
-                                  self.reg, scale, st))
-        check(lib.tlsan_sgd_dense(self.item_b_shard.data_ptr(), self._g_b.data_ptr(), self.n_local, lr, 0.0, scale, st))
+        # L2 decay of every shard row, then the received gradient rows, source ranks in rank order
+        check(lib.tlsan_sgd_dense(self.item_emb_shard.data_ptr(), None, self.n_local * 32, lr, self.reg, scale, st))
+        for o in range(W):
+            check(lib.tlsan_shard_apply_grads(grads_in.data_ptr() + 4 * SHARD_ROW * o * cap,
+                                              recv_ids.data_ptr() + 4 * o * cap, cap, self.item_emb_shard.data_ptr(),
+                                              self.item_b_shard.data_ptr(), lr, scale, st))
         self._mark("apply")
         self.global_step += 1
         return self._stats
@@ -329,25 +365,29 @@ class ShardedModel(object):
         stats = self.train_staged(self.stage_batch(batch), float(lr))
         if int(self._bad.item()):
             raise _lib.TlsanError("an item id was routed to a rank that does not own it")
+        if int(self._overflow.item()):
+            raise _lib.TlsanError("a request list exceeded route_capacity=%d" % self.route_cap)
         return float(stats[STAT["loss"]].item())
 
     # ------------------------------------------------------------------ scoring
-    def score_staged(self, db, ncand=1):
+    def score_staged(self, db, ncand=1, want_ut=False):
         cb, _ = self._fetch(db)
         dims = self._dims(db.B, db.S)
         logits = torch.empty(db.B, ncand, dtype=torch.float32, device=self.device)
+        ut = torch.empty(db.B, 64, dtype=torch.float32, device=self.device) if want_ut else None
+        utp = ut.data_ptr() if want_ut else None
         if db.B >= 2048:                                       # same kernel selection as Model.score_staged
             need = C.c_size_t()
             check(self._lib.tlsan_score_workspace_bytes(C.byref(dims), C.byref(need)))
             if self._score_ws is None or self._score_ws.numel() < need.value:
                 self._score_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
             check(self._lib.tlsan_score_ws(C.byref(dims), C.byref(self._params), C.byref(cb.c), ncand,
-                                           logits.data_ptr(), None, self._score_ws.data_ptr(),
+                                           logits.data_ptr(), utp, self._score_ws.data_ptr(),
                                            self._score_ws.numel(), self._stream()))
         else:
             check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(cb.c), ncand,
-                                        logits.data_ptr(), None, self._stream()))
-        return logits
+                                        logits.data_ptr(), utp, self._stream()))
+        return (logits, ut) if want_ut else logits
 
     def eval_auc(self, sess, batch):
         """Model.eval_auc (model.py:237-263) on this rank's rows."""
