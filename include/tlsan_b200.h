@@ -221,6 +221,17 @@ int tlsan_rank_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes);
 int tlsan_label_rank_ws(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* ut, const int32_t* label,
                         int32_t* rank, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same count against ONE row shard of the item tables (row-sharded configuration, SURVEY 8e last row): local
+ * row j of the shard is global item j * gid_mul + gid_add; label_global[B] = global label ids, lab_rows[B][68] = the
+ * labels' augmented rows [item_emb | cate_emb[icl] | item_b | 3 pad] (gathered by the rank that fetched them), so
+ * every shard derives the label's score with the same instruction sequence and ties still break by global index.
+ * rank_partial[b] = this shard's share; the caller sums over shards (integer all-reduce).
+ * Workspace: 73 728 B per 128 shard rows + 256. */
+int tlsan_label_rank_shard(int32_t B, int64_t n_local, const float* item_emb_shard, const float* item_b_shard,
+                           const int32_t* icl_shard, const float* cate_emb, const float* ut,
+                           const int32_t* label_global, const float* lab_rows, int32_t gid_mul, int32_t gid_add,
+                           int32_t* rank_partial, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host helper (no GPU work): pack the 9-tuple of TLSAN/input.py:54,107 (int64 ids, fp32 hist_t) into
  * ONE int32 staging buffer -- the int64->int32 feed cast of model.py:210-222 -- multi-threaded, with
  * the id range checks TF's CPU gather performs (nthreads = 0: min(8, host cores / LOCAL_WORLD_SIZE), so the ranks of a
@@ -302,14 +313,15 @@ int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int3
  *                             decay of every shard row is a separate dense pass (tlsan_sgd_dense with g = NULL)
  *   tlsan_route_ids           device-side routing of the distinct item ids of a batch, no host round trip: position
  *                             p = owner * ceil(NI / world) + local of every id (cyclic: owner = id % world; block: p = id),
- *                             presence bitmap over the positions, compact row of an id = owner * cap + its rank inside
- *                             the owner's group.  phase 0: bitmap + per-word popcounts into word_prefix (the caller
- *                             turns them into an INCLUSIVE prefix, e.g. torch.cumsum); phase 1: send_ids[world][cap] =
- *                             owner-local row ids requested from every owner (ascending, padded with -1), counts[world],
- *                             *overflow = 1 if a group exceeds cap, and dst[q][e] = compact row of src[q][e] for the
- *                             nfields id arrays of the packed batch.  With fixed cap the all-to-alls run with equal
- *                             splits.  dst_index / src_index of the pack / unpack helpers may then be NULL (identity),
- *                             and negative local ids mark padding slots (zero rows, skipped by accum / apply).
+ *                             presence bitmap over the positions, compact row of an id = its rank among all requested
+ *                             ids (owner-major order).  phase 0: bitmap + per-word popcounts into word_prefix (the
+ *                             caller turns them into an INCLUSIVE prefix, e.g. torch.cumsum); phase 1:
+ *                             send_ids[world][cap] = owner-local row ids requested from every owner (ascending, padded
+ *                             with -1), slot_row[world][cap] = compact row of every request slot (-1 padding; the
+ *                             dst_index / src_index of the pack / unpack helpers), counts[world], *overflow = 1 if a
+ *                             group exceeds cap, and dst[q][e] = compact row of src[q][e] for the nfields id arrays of
+ *                             the packed batch.  With fixed cap the all-to-alls run with equal splits; negative ids /
+ *                             rows mark padding slots (zero rows, skipped by unpack / accum / apply).
  *   tlsan_route_bitmap_words  words of the presence bitmap (= of word_prefix) for (NI, world) */
 #define TLSAN_SHARD_ROW 36
 int tlsan_shard_apply_grads(const float* packed, const int32_t* local_ids, int64_t n, float* W_emb, float* W_b,
@@ -317,7 +329,8 @@ int tlsan_shard_apply_grads(const float* packed, const int32_t* local_ids, int64
 int tlsan_route_bitmap_words(int64_t NI, int32_t world, int64_t* words);
 int tlsan_route_ids(const int32_t* const* src, int32_t* const* dst, const int64_t* n, int32_t nfields, int64_t NI,
                     int32_t world, int32_t cyclic, int32_t cap, uint32_t* bitmap, int32_t* word_prefix,
-                    int32_t* send_ids, int32_t* counts, int32_t* overflow, int32_t phase, void* stream);
+                    int32_t* send_ids, int32_t* slot_row, int32_t* counts, int32_t* overflow, int32_t phase,
+                    void* stream);
 int tlsan_shard_pack_rows(const float* emb_shard, const float* item_b_shard, const int32_t* icl_shard,
                           const int32_t* local_ids, int64_t n, int64_t n_local, float* out, int32_t* bad_flag,
                           void* stream);

@@ -76,6 +76,8 @@ _SIGS = {
     "tlsan_rank_workspace_bytes": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_size_t)]),
     "tlsan_label_rank_ws": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tlsan_label_rank_shard": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_void_p,
+                                                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "tlsan_pack_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
     "tlsan_pack_batch_host_i32": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 11 + [C.c_int64, C.c_int32, C.c_int32]),
     "tlsan_stage_batch_host_i32": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32,
@@ -96,7 +98,7 @@ _SIGS = {
     "tlsan_route_bitmap_words": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
     "tlsan_route_ids": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int64,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_int32, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "tlsan_shard_apply_replicated": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                                C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -33,10 +33,12 @@
 #define RK_SMEM (3 * RK_TILE + 256)
 
 // k-chunk c (4 floats) of the augmented catalogue row of item j: [item_emb[j] | cate_emb[icl[j]] | item_b[j], 0...]
-__device__ __forceinline__ float4 catalogue_chunk(int NI, const float* __restrict__ emb, const float* __restrict__ item_b,
-                                                  const int* __restrict__ icl, int j, int c) {
+// (`cate` = first row of cate_emb: emb + NI * 32 in the replicated model, a separate buffer for a row shard)
+__device__ __forceinline__ float4 catalogue_chunk(const float* __restrict__ cate, const float* __restrict__ emb,
+                                                  const float* __restrict__ item_b, const int* __restrict__ icl, int j,
+                                                  int c) {
   if (c < 8) return __ldg(reinterpret_cast<const float4*>(emb + (size_t)j * 32) + c);
-  if (c < 16) return __ldg(reinterpret_cast<const float4*>(emb + (size_t)(NI + __ldg(icl + j)) * 32) + (c - 8));
+  if (c < 16) return __ldg(reinterpret_cast<const float4*>(cate + (size_t)__ldg(icl + j) * 32) + (c - 8));
   if (c == 16) return make_float4(__ldg(item_b + j), 0.f, 0.f, 0.f);
   return make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -49,6 +51,7 @@ __device__ __forceinline__ void split_store(char* plane_hi, int c, int r, float4
 
 // catalogue -> UMMA operand tiles in global memory (one thread per (tile, k-chunk, row))
 __global__ void __launch_bounds__(256) k_build_catalogue(int NI, const float* __restrict__ emb,
+                                                         const float* __restrict__ cate,
                                                          const float* __restrict__ item_b, const int* __restrict__ icl,
                                                          char* __restrict__ img, int ntiles) {
   const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(256) k_build_catalogue(int NI, const float* __
   const long long tile = g / (RK_N * RK_CHUNKS);
   if (tile >= ntiles) return;
   const long long j = tile * RK_N + r;
-  const float4 v = j < NI ? catalogue_chunk(NI, emb, item_b, icl, (int)j, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 v = j < NI ? catalogue_chunk(cate, emb, item_b, icl, (int)j, c) : make_float4(0.f, 0.f, 0.f, 0.f);
   split_store(img + tile * RK_TILE, c, r, v);
 }
 
@@ -74,12 +77,18 @@ __device__ __forceinline__ int count_above(const float (&s)[32], float sl, int d
   return cnt;
 }
 
+// Row shards (tlsan_label_rank_shard): the catalogue holds the rows of ONE shard, local row j is global item
+// j * gid_mul + gid_add; `label` holds GLOBAL ids and `lab_rows` [B][68] the labels' augmented rows
+// (item_emb | cate_emb | item_b, pad) gathered by whoever owns them, so every shard derives the label's score with the
+// same instruction sequence; rank[b] then counts this shard's share and the caller sums over the shards.
 __global__ void __launch_bounds__(RK_THREADS, 1) k_label_rank_tc(int B, int NI, const float* __restrict__ emb,
+                                                                 const float* __restrict__ cate,
                                                                  const float* __restrict__ item_b,
                                                                  const int* __restrict__ icl,
                                                                  const float* __restrict__ ut,
                                                                  const int* __restrict__ label,
-                                                                 const char* __restrict__ img, int ntiles,
+                                                                 const float* __restrict__ lab_rows, int gid_mul,
+                                                                 int gid_add, const char* __restrict__ img, int ntiles,
                                                                  int tiles_per_unit, int* __restrict__ rank) {
   extern __shared__ __align__(128) unsigned char smem[];
   char* sA = reinterpret_cast<char*>(smem);                  // user operand: hi plane, lo plane
@@ -119,8 +128,13 @@ __global__ void __launch_bounds__(RK_THREADS, 1) k_label_rank_tc(int B, int NI, 
       if (c < 16) { if (live) v = __ldg(reinterpret_cast<const float4*>(ut + (size_t)b * 64) + c); }
       else if (c == 16) v.x = 1.f;
       split_store(sA, c, m, v);
-      split_store(sB, c, m, catalogue_chunk(NI, emb, item_b, icl, lab, c));
+      float4 lv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lab_rows) { if (live && c < 17) lv = __ldg(reinterpret_cast<const float4*>(lab_rows + (size_t)b * 68) + c); }
+      else lv = catalogue_chunk(cate, emb, item_b, icl, lab, c);
+      split_store(sB, c, m, lv);
     }
+    // first local row whose global id is >= the label: ties against items before the label count as "above"
+    if (lab_rows) lab = lab <= gid_add ? 0 : (lab - gid_add + gid_mul - 1) / gid_mul;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
   }
   tc_fence_before();
@@ -215,8 +229,20 @@ size_t tlsan_rank_ws_bytes(const tlsan_dims_t& d) {
   return ntiles * RK_TILE + 256;
 }
 
+static int launch_rank_tc(int B, int NI, const float* emb, const float* cate, const float* item_b, const int* icl,
+                          const float* ut, const int32_t* label, const float* lab_rows, int gid_mul, int gid_add,
+                          int32_t* rank, char* img, cudaStream_t st);
+
 int tlsan_launch_label_rank_tc(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
                                int32_t* rank, char* img, cudaStream_t st) {
+  return launch_rank_tc(d.B, d.NI, p.emb, p.emb + (size_t)d.NI * 32, p.item_b, p.icl, ut, label, nullptr, 1, 0, rank, img, st);
+}
+
+static int launch_rank_tc(int B, int NI, const float* emb, const float* cate, const float* item_b, const int* icl,
+                          const float* ut, const int32_t* label, const float* lab_rows, int gid_mul, int gid_add,
+                          int32_t* rank, char* img, cudaStream_t st) {
+  struct { int B, NI; } d = {B, NI};
+  struct { const float* emb; const float* item_b; const int* icl; } p = {emb, item_b, icl};
   static bool attr = false;
   if (!attr) {
     TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_label_rank_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM));
@@ -224,7 +250,7 @@ int tlsan_launch_label_rank_tc(const tlsan_dims_t& d, const tlsan_params_t& p, c
   }
   const int ntiles = (d.NI + RK_N - 1) / RK_N, mtiles = (d.B + RK_M - 1) / RK_M;
   const long long nthreads = (long long)ntiles * RK_N * RK_CHUNKS;
-  k_build_catalogue<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(d.NI, p.emb, p.item_b, p.icl, img, ntiles);
+  k_build_catalogue<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(d.NI, p.emb, cate, p.item_b, p.icl, img, ntiles);
   TLSAN_CHECK_LAUNCH("k_build_catalogue");
   TLSAN_CHECK_CUDA(cudaMemsetAsync(rank, 0, (size_t)d.B * sizeof(int32_t), st));
   // work units: enough (user tile, item range) pairs to fill the SMs about twice, each at least 8 item tiles
@@ -233,8 +259,33 @@ int tlsan_launch_label_rank_tc(const tlsan_dims_t& d, const tlsan_params_t& p, c
   if (splits < 1) splits = 1;
   const int per = (ntiles + splits - 1) / splits;
   splits = (ntiles + per - 1) / per;
-  k_label_rank_tc<<<dim3(mtiles, splits), RK_THREADS, RK_SMEM, st>>>(d.B, d.NI, p.emb, p.item_b, p.icl, ut, label, img,
-                                                                     ntiles, per, rank);
+  k_label_rank_tc<<<dim3(mtiles, splits), RK_THREADS, RK_SMEM, st>>>(d.B, d.NI, p.emb, cate, p.item_b, p.icl, ut, label,
+                                                                     lab_rows, gid_mul, gid_add, img, ntiles, per, rank);
   TLSAN_CHECK_LAUNCH("k_label_rank_tc");
   return TLSAN_OK;
+}
+
+// extern "C": full-catalogue label ranks against ONE row shard of the item tables (see k_label_rank_tc)
+extern "C" int tlsan_label_rank_shard(int32_t B, int64_t n_local, const float* item_emb_shard, const float* item_b_shard,
+                                      const int32_t* icl_shard, const float* cate_emb, const float* ut,
+                                      const int32_t* label_global, const float* lab_rows, int32_t gid_mul,
+                                      int32_t gid_add, int32_t* rank_partial, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  if (!item_emb_shard || !item_b_shard || !icl_shard || !cate_emb || !ut || !label_global || !lab_rows || !rank_partial ||
+      !workspace) {
+    tlsan_set_error("tlsan_label_rank_shard: NULL argument");
+    return TLSAN_E_NULL;
+  }
+  if (B <= 0 || n_local <= 0 || n_local >= (1ll << 31) || gid_mul <= 0 || gid_add < 0) {
+    tlsan_set_error("tlsan_label_rank_shard: bad dims");
+    return TLSAN_E_DIMS;
+  }
+  const size_t ntiles = ((size_t)n_local + RK_N - 1) / RK_N;
+  if (workspace_bytes < ntiles * RK_TILE + 256) {
+    tlsan_set_error("tlsan_label_rank_shard: workspace too small");
+    return TLSAN_E_WORKSPACE;
+  }
+  char* img = reinterpret_cast<char*>(tlsan_align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  return launch_rank_tc(B, (int)n_local, item_emb_shard, cate_emb, item_b_shard, icl_shard, ut, label_global, lab_rows,
+                        gid_mul, gid_add, rank_partial, img, (cudaStream_t)stream);
 }

@@ -63,9 +63,11 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_pack_grads(const float*
   const int c = (int)(g - k * 9);
   if (k >= n) return;
   const long long r = src ? src[k] : k;
-  float4 v;
-  if (c < 8) v = __ldg(reinterpret_cast<const float4*>(g_i + r * 64) + c);
-  else v = make_float4(__ldg(g_b + r), 0.f, 0.f, 0.f);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r >= 0) {
+    if (c < 8) v = __ldg(reinterpret_cast<const float4*>(g_i + r * 64) + c);
+    else v = make_float4(__ldg(g_b + r), 0.f, 0.f, 0.f);
+  }
   reinterpret_cast<float4*>(out + k * TLSAN_SHARD_ROW)[c] = v;
 }
 
@@ -121,10 +123,11 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_apply_grads(const float
 // Device-side routing of the distinct item ids of a batch (no torch.unique, no host round trip).
 // Every id has an owner-major POSITION p = owner * nloc + local (nloc = ceil(NI / W); cyclic partition: owner =
 // id % W, local = id / W; block partition: p = id).  A presence bitmap over the positions is the set of distinct ids;
-// an exclusive prefix of its word popcounts turns a position into its rank inside the owner's group, and the
-// COMPACT row of an id is owner * cap + rank -- a pure function of the batch, so the compact table, the category
-// CSR built on it and every summation order downstream are reproducible.  `cap` is a fixed per-owner capacity:
-// the all-to-alls run with equal splits; a group that does not fit raises the overflow flag.
+// a prefix of its word popcounts turns a position into its rank, and the COMPACT row of an id is its rank among all
+// requested ids in owner-major order -- a pure function of the batch, so the compact table, the category CSR built on
+// it and every summation order downstream are reproducible.  Request slot (owner o, k) = the k-th id of owner o's
+// group; `cap` slots per owner are exchanged (equal-split all-to-alls, padding marked -1); a group that does not
+// fit raises the overflow flag.
 struct RouteGeo { int W, nloc, mod, cap; long long NI; };
 __device__ __forceinline__ long long route_pos(const RouteGeo& g, int id) {
   return g.mod ? (long long)(id % g.W) * g.nloc + id / g.W : (long long)id;
@@ -138,7 +141,8 @@ __global__ void __launch_bounds__(256) k_route_mark(const RouteFields f, const R
       const int id = __ldg(f.src[q] + e);
       if (id < 0 || id >= g.NI) continue;                      // validated on the host; never fault here
       const long long p = route_pos(g, id);
-      atomicOr(bits + (p >> 5), 1u << (p & 31));
+      const unsigned int m = 1u << (p & 31);
+      if (!(*reinterpret_cast<volatile unsigned int*>(bits + (p >> 5)) & m)) atomicOr(bits + (p >> 5), m);   // padding zeros: one hot word
     }
 }
 __global__ void __launch_bounds__(256) k_route_popc(const unsigned int* __restrict__ bits, long long nwords,
@@ -155,7 +159,8 @@ __device__ __forceinline__ int route_rank(const unsigned int* __restrict__ bits,
 // per owner: its request list (owner-local row ids, ascending, padded with -1 to cap) and its count
 __global__ void __launch_bounds__(256) k_route_emit(const unsigned int* __restrict__ bits, const int* __restrict__ incl,
                                                     long long nwords, const RouteGeo g, int* __restrict__ send_ids,
-                                                    int* __restrict__ counts, int* __restrict__ overflow) {
+                                                    int* __restrict__ slot_row, int* __restrict__ counts,
+                                                    int* __restrict__ overflow) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < g.W) {                                                // (first W threads also publish the group sizes)
     const int lo = route_rank(bits, incl, (long long)w * g.nloc);
@@ -174,11 +179,14 @@ __global__ void __launch_bounds__(256) k_route_emit(const unsigned int* __restri
     const int o = (int)(p / g.nloc);
     const int local = (int)(p - (long long)o * g.nloc);
     const int rank = before - route_rank(bits, incl, (long long)o * g.nloc);
-    if (rank < g.cap) send_ids[(long long)o * g.cap + rank] = local;
+    if (rank < g.cap) {
+      send_ids[(long long)o * g.cap + rank] = local;
+      slot_row[(long long)o * g.cap + rank] = before;           // dense compact row = rank among ALL requested ids
+    }
     ++before;
   }
 }
-// id fields of the packed batch -> compact rows owner * cap + rank
+// id fields of the packed batch -> dense compact rows (rank of the id among all requested ids, owner-major order)
 __global__ void __launch_bounds__(256) k_route_rewrite(const RouteFields f, const RouteGeo g,
                                                        const unsigned int* __restrict__ bits, const int* __restrict__ incl) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -186,12 +194,7 @@ __global__ void __launch_bounds__(256) k_route_rewrite(const RouteFields f, cons
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < f.n[q]; e += stride) {
       const int id = __ldg(f.src[q] + e);
       int out = 0;
-      if (id >= 0 && id < g.NI) {
-        const long long p = route_pos(g, id);
-        const int o = (int)(p / g.nloc);
-        const int rank = route_rank(bits, incl, p) - route_rank(bits, incl, (long long)o * g.nloc);
-        out = o * g.cap + min(rank, g.cap - 1);
-      }
+      if (id >= 0 && id < g.NI) out = route_rank(bits, incl, route_pos(g, id));
       f.dst[q][e] = out;
     }
 }
@@ -328,8 +331,9 @@ int tlsan_route_bitmap_words(int64_t NI, int32_t world, int64_t* words) {
 
 int tlsan_route_ids(const int32_t* const* src, int32_t* const* dst, const int64_t* n, int32_t nfields, int64_t NI,
                     int32_t world, int32_t cyclic, int32_t cap, uint32_t* bitmap, int32_t* word_prefix,
-                    int32_t* send_ids, int32_t* counts, int32_t* overflow, int32_t phase, void* stream) {
-  SHARD_REQUIRE(src && dst && n && bitmap && word_prefix && send_ids && counts && overflow, TLSAN_E_NULL,
+                    int32_t* send_ids, int32_t* slot_row, int32_t* counts, int32_t* overflow, int32_t phase,
+                    void* stream) {
+  SHARD_REQUIRE(src && dst && n && bitmap && word_prefix && send_ids && slot_row && counts && overflow, TLSAN_E_NULL,
                 "tlsan_route_ids: NULL argument");
   SHARD_REQUIRE(nfields >= 1 && nfields <= 4 && NI > 0 && world > 0 && cap > 0, TLSAN_E_DIMS, "tlsan_route_ids: bad dims");
   cudaStream_t st = (cudaStream_t)stream;
@@ -357,7 +361,9 @@ int tlsan_route_ids(const int32_t* const* src, int32_t* const* dst, const int64_
   }
   // phase 1: request lists + compact batch
   TLSAN_CHECK_CUDA(cudaMemsetAsync(send_ids, 0xff, (size_t)world * cap * 4, st));
-  k_route_emit<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(bitmap, word_prefix, nwords, g, send_ids, counts, overflow);
+  TLSAN_CHECK_CUDA(cudaMemsetAsync(slot_row, 0xff, (size_t)world * cap * 4, st));
+  k_route_emit<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(bitmap, word_prefix, nwords, g, send_ids, slot_row, counts,
+                                                                 overflow);
   TLSAN_CHECK_LAUNCH("k_route_emit");
   k_route_rewrite<<<(unsigned)blocks, 256, 0, st>>>(f, g, bitmap, word_prefix);
   TLSAN_CHECK_LAUNCH("k_route_rewrite");

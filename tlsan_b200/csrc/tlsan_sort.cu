@@ -157,15 +157,19 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
   }
 }
 
-// seg_off[r] = first sorted position with key >= r, r in [0, NR]
+// seg_off[r] = first sorted position with key >= r, r in [0, NR]: one thread per ROW, binary search over the sorted
+// keys (a per-key thread that fills the rows between two keys serialises on long runs of untouched rows -- the compact
+// table of the row-sharded configuration has runs of 10^5)
 __global__ void k_seg_bounds(const int* __restrict__ keys, const int* __restrict__ nvalid, int NR,
                              int* __restrict__ seg_off) {
-  const int n = *nvalid;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  const int prev = i > 0 ? keys[i - 1] : -1;
-  const int cur = i < n ? keys[i] : NR;
-  for (int r = prev + 1; r <= cur; ++r) seg_off[r] = i;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > NR) return;
+  int lo = 0, hi = *nvalid;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(keys + mid) < r) lo = mid + 1; else hi = mid;
+  }
+  seg_off[r] = lo;
 }
 
 // which ping-pong buffer holds the sorted occurrence ids after the last pass (pass k writes b, a, b, ...)
@@ -215,7 +219,7 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }
   }
-  k_seg_bounds<<<(unsigned)((nocc + 1 + 255) / 256), 256, 0, st>>>(kin, nvalid, w.NR, seg_off);
+  k_seg_bounds<<<(unsigned)((w.NR + 1 + 255) / 256), 256, 0, st>>>(kin, nvalid, w.NR, seg_off);
   TLSAN_CHECK_LAUNCH("k_seg_bounds");
   *sorted_vals = vin;
   return TLSAN_OK;

@@ -37,7 +37,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import PART, SHARD_ROW, STAT, Batch, Dims, Params, check
-from .model import DENSE_LAYOUT, DeviceBatch, Model, _pack_offsets, pack_batch
+from .model import DENSE_LAYOUT, KS, DeviceBatch, Model, _pack_offsets, pack_batch
 
 NSQ = 256          # partial sums of squares per item shard
 
@@ -157,8 +157,10 @@ class ShardedModel(object):
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
         self._ws = None
         self._score_ws = None
+        self._rank_ws = None
         self._flat = None
         self._stage_cache = {}
+        self.reset_metrics()
         self.global_step = 0
         self.last_exchange_bytes = 0
         self.profile = None          # set to [] to collect (label, cuda event) marks per step (tools/bench_sharded.py)
@@ -278,8 +280,10 @@ class ShardedModel(object):
         dst = (C.c_void_p * 4)(*([cbuf.data_ptr() + 4 * db.offs[k] for k, _ in fields] + [None] * (4 - nf)))
         cnt = (C.c_int64 * 4)(*([n for _, n in fields] + [0] * (4 - nf)))
         send_ids = self._buf("send_ids", (W * cap,), torch.int32)
+        slot_row = self._buf("slot_row", (W * cap,), torch.int32)
         args = (src, dst, cnt, nf, self.NI, W, 1 if self.partition == "mod" else 0, cap, self._bits.data_ptr(),
-                self._wpref.data_ptr(), send_ids.data_ptr(), self._counts.data_ptr(), self._overflow.data_ptr())
+                self._wpref.data_ptr(), send_ids.data_ptr(), slot_row.data_ptr(), self._counts.data_ptr(),
+                self._overflow.data_ptr())
         check(lib.tlsan_route_ids(*args, 0, st))
         self._wpref.cumsum_(0)                                       # inclusive prefix of the word popcounts
         check(lib.tlsan_route_ids(*args, 1, st))
@@ -290,10 +294,11 @@ class ShardedModel(object):
                                         self.icl_shard.data_ptr(), recv_ids.data_ptr(), W * cap, self.n_local,
                                         rows_out.data_ptr(), self._bad.data_ptr(), st))
         rows_in = self._a2a("rows_in", rows_out)
-        check(lib.tlsan_shard_unpack_rows(rows_in.data_ptr(), None, W * cap, self.emb_c.data_ptr(),
+        check(lib.tlsan_shard_unpack_rows(rows_in.data_ptr(), slot_row.data_ptr(), W * cap, self.emb_c.data_ptr(),
                                           self.item_b_c.data_ptr(), self.icl_c.data_ptr(), st))
         cb = DeviceBatch(cbuf, db.B, db.L, db.S, db.offs, db.is_test)
         self.last_exchange_bytes = W * cap * (4 + 4 * SHARD_ROW)
+        self._n_u = self._wpref[-1:]                               # distinct ids of this batch (device scalar)
         return cb, recv_ids
 
     @property
@@ -303,9 +308,11 @@ class ShardedModel(object):
 
     def _compact_csr(self):
         """Items of the compact table grouped by category (stable), for the hierarchical category reduce."""
-        icl = self.icl_c[:self.cap]
+        # rows >= n_u hold stale data of earlier steps: they go to a dummy category NC behind the real ones
+        rows = torch.arange(self.cap, device=self.device, dtype=torch.int32)
+        icl = torch.where(rows < self._n_u, self.icl_c[:self.cap], self.NC)
         self.cate_items[:self.cap] = torch.sort(icl, stable=True).indices.to(torch.int32)
-        self.cate_off[1:] = torch.cumsum(torch.bincount(icl, minlength=self.NC), 0).to(torch.int32)
+        self.cate_off[1:] = torch.cumsum(torch.bincount(icl, minlength=self.NC + 1)[:self.NC], 0).to(torch.int32)
 
     # ------------------------------------------------------------------ training
     def train_staged(self, db, lr, global_batch=None):
@@ -343,7 +350,8 @@ class ShardedModel(object):
         self._mark("allreduce")
         # gradient rows of the requested ids -> owners (reverse of the row exchange, same equal splits)
         grads_out = self._buf("grads_out", (W * cap, SHARD_ROW))
-        check(lib.tlsan_shard_pack_grads(flat.data_ptr(), fp(f_gb), None, W * cap, grads_out.data_ptr(), st))
+        check(lib.tlsan_shard_pack_grads(flat.data_ptr(), fp(f_gb), self._xbuf["slot_row"].data_ptr(), W * cap,
+                                         grads_out.data_ptr(), st))
         grads_in = self._a2a("grads_in", grads_out)
         self._mark("return_grads")
         check(lib.tlsan_shard_apply_replicated(C.byref(dims), C.byref(self._params), fp(f_cate), fp(f_gu), fp(f_dgrad),
@@ -370,7 +378,7 @@ class ShardedModel(object):
         return float(stats[STAT["loss"]].item())
 
     # ------------------------------------------------------------------ scoring
-    def score_staged(self, db, ncand=1, want_ut=False):
+    def score_staged(self, db, ncand=1, want_ut=False, want_compact=False):
         cb, _ = self._fetch(db)
         dims = self._dims(db.B, db.S)
         logits = torch.empty(db.B, ncand, dtype=torch.float32, device=self.device)
@@ -387,7 +395,79 @@ class ShardedModel(object):
         else:
             check(self._lib.tlsan_score(C.byref(dims), C.byref(self._params), C.byref(cb.c), ncand,
                                         logits.data_ptr(), utp, self._stream()))
+        if want_compact:
+            return logits, ut, cb
         return (logits, ut) if want_ut else logits
+
+    # ------------------------------------------------------------------ full-catalogue P@k / R@k (model.py:140-156)
+    def _label_ranks(self, batch):
+        """rank of batch[1] among ALL items for this rank's rows: every rank scores its rows (u_t), the rows / labels
+        / label rows are all-gathered, every shard counts the items of ITS rows that beat each label on the tensor
+        cores (tlsan_label_rank_shard), and one integer all-reduce adds the shards up (last row)."""
+        db = self.stage_batch(batch, is_test=True)
+        _, ut, cb = self.score_staged(db, 1, want_ut=True, want_compact=True)
+        B = db.B
+        o = db.offs["i"]
+        lab = db.buf[o:o + B].contiguous()                                # global ids
+        ci = cb.buf[o:o + B].long()                                       # their compact rows
+        lab_rows = torch.zeros(B, 68, device=self.device)
+        lab_rows[:, :32] = self.emb_c[ci]
+        lab_rows[:, 32:64] = self.cate_emb[self.icl_c[ci].long()]
+        lab_rows[:, 64] = self.item_b_c[ci]
+        W = self.world
+        if W > 1:
+            nb = torch.tensor([B], device=self.device)
+            nbs = [torch.empty_like(nb) for _ in range(W)]
+            dist.all_gather(nbs, nb, group=self.pg)
+            nbs = [int(x.item()) for x in nbs]
+            Bm = max(nbs)
+
+            def gather(t):
+                pad = torch.zeros((Bm,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+                pad[:B] = t
+                out = [torch.empty_like(pad) for _ in range(W)]
+                dist.all_gather(out, pad, group=self.pg)
+                return torch.cat(out)
+            ut_all, lab_all, rows_all = gather(ut), gather(lab), gather(lab_rows)
+        else:
+            nbs, Bm, ut_all, lab_all, rows_all = [B], B, ut, lab, lab_rows
+        n_all = W * Bm
+        part = torch.zeros(n_all, dtype=torch.int32, device=self.device)
+        if self.n_local:
+            need = (-(-self.n_local // 128)) * 73728 + 512
+            if self._rank_ws is None or self._rank_ws.numel() < need:
+                self._rank_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            mul, add = (W, self.rank) if self.partition == "mod" else (1, self.rank * (-(-self.NI // W)))
+            check(self._lib.tlsan_label_rank_shard(n_all, self.n_local, self.item_emb_shard.data_ptr(),
+                                                   self.item_b_shard.data_ptr(), self.icl_shard.data_ptr(),
+                                                   self.cate_emb.data_ptr(), ut_all.data_ptr(), lab_all.data_ptr(),
+                                                   rows_all.data_ptr(), mul, add, part.data_ptr(),
+                                                   self._rank_ws.data_ptr(), self._rank_ws.numel(), self._stream()))
+        if W > 1:
+            dist.all_reduce(part, group=self.pg)
+        return part[self.rank * Bm:self.rank * Bm + B].cpu().numpy()
+
+    def eval_prec(self, sess, batch):
+        """Model.eval_prec (model.py:265-281) on this rank's rows; cumulative like the reference (reset_metrics)."""
+        rank = self._label_ranks(batch)
+        for n, k in enumerate(KS):
+            hit = float(np.sum(rank < k))
+            self._ptp[n] += hit
+            self._pfp[n] += len(rank) * k - hit
+        return [float(self._ptp[n] / (self._ptp[n] + self._pfp[n])) for n in range(len(KS))]
+
+    def eval_recall(self, sess, batch):
+        """Model.eval_recall (model.py:283-299) on this rank's rows."""
+        rank = self._label_ranks(batch)
+        for n, k in enumerate(KS):
+            hit = float(np.sum(rank < k))
+            self._rtp[n] += hit
+            self._rfn[n] += len(rank) - hit
+        return [float(self._rtp[n] / (self._rtp[n] + self._rfn[n])) for n in range(len(KS))]
+
+    def reset_metrics(self):
+        self._ptp = np.zeros(len(KS)); self._pfp = np.zeros(len(KS))
+        self._rtp = np.zeros(len(KS)); self._rfn = np.zeros(len(KS))
 
     def eval_auc(self, sess, batch):
         """Model.eval_auc (model.py:237-263) on this rank's rows."""
