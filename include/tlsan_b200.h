@@ -168,6 +168,28 @@ int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const fl
                      float lr, float reg, float clip_norm, void* workspace, size_t workspace_bytes,
                      float* stats, void* stream);
 
+/* The other optimisers of init_optimizer (model.py:188-193: adadelta / adam / rmsprop with the TF-1.8 defaults;
+ * GradientDescentOptimizer is the `else` branch and the path above).  tlsan_apply_flat_opt = tlsan_apply_flat with the
+ * update rule of `opt`: every element sees its aggregated, clipped gradient (sum of slices + reg * w) * scale, so TF's
+ * sparse apply ops reduce to the dense formulas (the L2 term puts every row into the IndexedSlices).  slot1 / slot2
+ * mirror the weight buffer, which must be ONE buffer emb | usert | item_b | dense (each padded to 16 B):
+ *   adam      slot1 = m, slot2 = v (zeros);  rmsprop  slot1 = ms (ONES), slot2 = momentum (zeros);
+ *   adadelta  slot1 = accum, slot2 = accum_update (zeros).  step = 1, 2, ... (adam's bias correction). */
+enum { TLSAN_OPT_SGD = 0, TLSAN_OPT_ADAM = 1, TLSAN_OPT_RMSPROP = 2, TLSAN_OPT_ADADELTA = 3 };
+typedef struct {
+  int32_t kind;
+  int32_t step;
+  float beta1, beta2;   /* adam: 0.9, 0.999 */
+  float rho;            /* rmsprop decay 0.9 ; adadelta rho 0.95 */
+  float momentum;       /* rmsprop: 0.0 */
+  float epsilon;        /* adam 1e-8, rmsprop 1e-10, adadelta 1e-8 */
+  float* slot1;
+  float* slot2;
+} tlsan_opt_t;
+int tlsan_apply_flat_opt(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
+                         float clip_norm, const tlsan_opt_t* opt, void* workspace, size_t workspace_bytes, float* stats,
+                         void* stream);
+
 /* Data-parallel exchange over NVLink peer memory, in place of NCCL all-reduce + tlsan_apply_flat: a
  * fused reduce-scatter + optimiser step + all-gather.  Every rank owns an ARENA that its peers map through CUDA
  * IPC and passes it to tlsan_step_grads as the `flat` gradient buffer; rank r then sums slice r of the weight index
@@ -291,6 +313,31 @@ typedef struct {
  * tlsan_pack_batch_host.  S must be >= the longest session among the rows (input.py uses the batch max). */
 int tlsan_collate(const tlsan_dataset_t* ds, const int32_t* idx, int32_t B, int32_t L, int32_t S, int32_t is_test,
                   int32_t* out, int64_t out_words, void* stream);
+
+/* Dataset builder on the GPU (TLSAN/build_dataset.py:25-73).  Input: the review table sorted by user then
+ * time (utils/2_remap_id.py:91) as three int32 columns, user_off[n_users + 1] = row range of every user.
+ *   tlsan_ds_plan     per user u: counts4[u] = {train PAIRS, has a test sample, sum of their history lengths, sum of
+ *                     their session lengths}, test2[u] = {first row (relative) and size of the test session}: session
+ *                     segmentation (runs of equal day, :38-46) + the split rule i + count < min(len, 90) - 1 (:55-72)
+ *   tlsan_ds_lengths  history / session length of every sample, unshuffled order (first_train[u] = index of user u's
+ *                     first train sample = 2 * exclusive prefix of the pairs; first_test likewise)
+ *   tlsan_ds_emit     writes every sample at its FINAL position (pos_train / pos_test: position after the reference's
+ *                     random.shuffle) into two tlsan_dataset_t images whose offset arrays the caller has filled:
+ *                     history, session, target, label / negative, u_cate (most frequent category, ties -> first seen,
+ *                     :54) and the weights float32(1/n), n = sum_j [d >= 2^j] (:16-21; lut13[n]); train_gap / test_gap
+ *                     (optional) receive the raw day gaps d.  neg[row] = sampled negative of every review row (:28-33),
+ *                     pick[u] = index chosen by random.choice inside the test session (:66): the host draws both from
+ *                     the Python random stream in the reference's call order. */
+int tlsan_ds_plan(const int32_t* day, const int64_t* user_off, int32_t n_users, int32_t* counts4, int32_t* test2,
+                  void* stream);
+int tlsan_ds_lengths(const int32_t* day, const int64_t* user_off, int32_t n_users, const int64_t* first_train,
+                     const int64_t* first_test, int32_t* len_pre_train, int32_t* len_new_train, int32_t* len_pre_test,
+                     int32_t* len_new_test, void* stream);
+int tlsan_ds_emit(const int32_t* reviewer, const int32_t* asin, const int32_t* day, const int32_t* item_cate,
+                  const int64_t* user_off, int32_t n_users, const int64_t* first_train, const int64_t* first_test,
+                  const int64_t* pos_train, const int64_t* pos_test, const int32_t* neg, const int32_t* pick,
+                  const float* lut13, const tlsan_dataset_t* train, const tlsan_dataset_t* test, int32_t* train_gap,
+                  int32_t* test_gap, void* stream);
 
 /* Row-sharded item tables (SURVEY 8e / BASELINE config 5, NI = 10 M; no counterpart in the reference, whose
  * tables live in one TF process).  item_emb / item_b / icl are split by row over the ranks.  Per step a rank

@@ -239,9 +239,55 @@ def bce_with_logits(x, y):
     return torch.clamp(x, min=0) - x * y + torch.log1p(torch.exp(-torch.abs(x)))
 
 
-def train_step(params, icl, batch, lr, config=None, dtype=torch.float32, clip_mode="tf"):
-    """One ``Model.train`` call (model.py:208-234): loss, tf.gradients, clip_by_global_norm,
-    GradientDescentOptimizer.  Returns dict(loss, bce, grads (dense, un-clipped, incl. reg),
+# tf.train.*Optimizer constructor defaults of TF 1.8 (model.py:188-193 passes learning_rate only)
+OPT_DEFAULTS = dict(adam=dict(beta1=0.9, beta2=0.999, epsilon=1e-8),
+                    rmsprop=dict(decay=0.9, momentum=0.0, epsilon=1e-10),
+                    adadelta=dict(rho=0.95, epsilon=1e-8))
+
+
+def init_opt_state(params, optimizer, dtype=torch.float64):
+    """Slot variables as TF 1.8 creates them: adam m, v = 0; rmsprop rms = ONES, momentum = 0; adadelta
+    accum, accum_update = 0.  ``t`` counts apply_gradients calls (adam's beta powers)."""
+    z = lambda v: torch.zeros(np.shape(v), dtype=dtype)
+    s1 = OrderedDict((k, torch.ones(np.shape(v), dtype=dtype) if optimizer == "rmsprop" else z(v))
+                     for k, v in params.items())
+    return dict(t=0, s1=s1, s2=OrderedDict((k, z(v)) for k, v in params.items()))
+
+
+def _opt_update(optimizer, w, g, lr, s1, s2, t, touched=None):
+    """One apply op.  g = the aggregated, clipped gradient.  Every table with an L2 term has a gradient whose
+    IndexedSlices cover all rows (tf.gradients concatenates the gather slices with the dense reg*W slice), and
+    Optimizer._apply_sparse_duplicate_indices sums duplicates first, so its sparse apply equals the dense formula.
+    item_b (no L2 term) is truly sparse: ``touched`` = bool mask of the rows in its slices; TF's
+    sparse_apply_rms_prop / sparse_apply_adadelta update only those rows (weights and slots), while
+    AdamOptimizer._apply_sparse (non-lazy) decays m, v and steps every row."""
+    o = OPT_DEFAULTS[optimizer]
+    if optimizer == "adam":
+        b1, b2, eps = o["beta1"], o["beta2"], o["epsilon"]
+        m = b1 * s1 + (1 - b1) * g
+        v = b2 * s2 + (1 - b2) * g * g
+        lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        return w - lr_t * m / (torch.sqrt(v) + eps), m, v
+    if optimizer == "rmsprop":
+        rho, mom_c, eps = o["decay"], o["momentum"], o["epsilon"]
+        ms = rho * s1 + (1 - rho) * g * g
+        mom = mom_c * s2 + lr * g / torch.sqrt(ms + eps)
+        nw = w - mom
+    else:
+        rho, eps = o["rho"], o["epsilon"]
+        ms = rho * s1 + (1 - rho) * g * g
+        upd = torch.sqrt(s2 + eps) / torch.sqrt(ms + eps) * g
+        mom = rho * s2 + (1 - rho) * upd * upd
+        nw = w - lr * upd
+    if touched is not None:
+        nw, ms, mom = torch.where(touched, nw, w), torch.where(touched, ms, s1), torch.where(touched, mom, s2)
+    return nw, ms, mom
+
+
+def train_step(params, icl, batch, lr, config=None, dtype=torch.float32, clip_mode="tf", opt_state=None):
+    """One ``Model.train`` call (model.py:208-234): loss, tf.gradients, clip_by_global_norm, then the optimizer of
+    ``config['optimizer']`` (:188-195; default GradientDescentOptimizer; the others need ``opt_state`` from
+    ``init_opt_state``, updated in place).  Returns dict(loss, bce, grads (dense, un-clipped, incl. reg),
     occ (per-gather slice gradients), norm_tf, norm_agg, scale, new_params)."""
     config = config or {}
     reg = config.get("regulation_rate", 0.00005)
@@ -268,8 +314,21 @@ def train_step(params, icl, batch, lr, config=None, dtype=torch.float32, clip_mo
     one = torch.ones((), dtype=dtype)
     scale = clip * torch.minimum(one / norm, one / clip)                             # clip_ops.py
     new_params = OrderedDict()
+    optimizer = config.get("optimizer", "sgd")
+    if optimizer in OPT_DEFAULTS:
+        if opt_state is None:
+            raise ValueError("optimizer %r needs opt_state=init_opt_state(params, optimizer)" % optimizer)
+        opt_state["t"] += 1
+        touched = torch.zeros(P["item_b"].shape, dtype=torch.bool)
+        touched[torch.as_tensor(np.asarray(batch[1], dtype=np.int64))] = True        # i_b = gather(item_b, self.i), :87
     for k in PARAM_NAMES:                                                            # :204
-        new_params[k] = (P[k].detach() - lr * (grads[k] * scale)).numpy()
+        if optimizer in OPT_DEFAULTS:
+            w, s1, s2 = _opt_update(optimizer, P[k].detach(), grads[k] * scale, lr, opt_state["s1"][k].to(dtype),
+                                    opt_state["s2"][k].to(dtype), opt_state["t"], touched if k == "item_b" else None)
+            opt_state["s1"][k], opt_state["s2"][k] = s1, s2
+            new_params[k] = w.numpy()
+        else:
+            new_params[k] = (P[k].detach() - lr * (grads[k] * scale)).numpy()
     return dict(loss=float(loss.detach()), bce=float(bce.detach()), logits=logits.detach().numpy(),
                 grads=OrderedDict((k, v.numpy()) for k, v in grads.items()),
                 occ={k: v.numpy() for k, v in occ.items()},

@@ -76,7 +76,10 @@ def test_train_step_is_deterministic_and_consistent_with_scoring(setup):
         assert stats[3] == 1.0                                        # clip inactive
         # conservation through sort + segmented reduce: sum of item_b updates = -lr * sum_b dL/dlogit_b
         d_item_b = m.item_b.double().sum().item() - item_b0
-        assert abs(d_item_b + g_sum) <= 1e-4 * abs(g_sum) + 1e-7
+        # floor: g_sum is a cancelling sum (sigmoid - y over a balanced batch), while every one of the NI updated
+        # biases is rounded to fp32 on its own (0.5 ulp of |item_b| ~ 0.4 each, random walk over NI rows)
+        floor = 4 * 2.0 ** -24 * float(m.item_b.abs().max()) * cfg["item_count"] ** 0.5
+        assert abs(d_item_b + g_sum) <= 1e-4 * abs(g_sum) + floor
         m.train_staged(db, 1.0)
         outs.append(({k: v.numpy().copy() for k, v in m.state_dict().items()}, stats.copy()))
     assert np.array_equal(outs[0][1], outs[1][1])

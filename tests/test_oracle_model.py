@@ -3,6 +3,7 @@ TF-internal choices (clip norm definitions) documented in oracle/tlsan_oracle.py
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import tlsan_oracle as O
@@ -86,3 +87,30 @@ def test_streaming_topk_semantics():
     st = O.StreamingTopK()
     p, r = st.update(scores, [2, 3])
     assert p[0] == 0.0 and r[0] == 0.0 and r[1] == 1.0 and abs(p[1] - 2 / 20) < 1e-12
+
+
+@pytest.mark.parametrize("opt", ["adam", "rmsprop", "adadelta"])
+def test_oracle_optimizers_follow_the_tf18_apply_ops(opt):
+    """_opt_update against a scalar-loop restatement of TF 1.8's ApplyAdam / ApplyRMSProp / ApplyAdadelta functors
+    (training_ops.cc), and the sparse row rule for item_b."""
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal(7); g = rng.standard_normal(7); s1 = rng.random(7) + 0.5; s2 = rng.random(7) * 0.1
+    t, lr = 3, 0.01
+    tw, ts1, ts2 = O._opt_update(opt, torch.tensor(w), torch.tensor(g), lr, torch.tensor(s1), torch.tensor(s2), t)
+    for i in range(7):
+        if opt == "adam":
+            m = 0.9 * s1[i] + 0.1 * g[i]; v = 0.999 * s2[i] + 0.001 * g[i] ** 2
+            alpha = lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+            exp = (w[i] - alpha * m / (np.sqrt(v) + 1e-8), m, v)
+        elif opt == "rmsprop":
+            ms = s1[i] + (g[i] ** 2 - s1[i]) * (1 - 0.9); mom = 0.0 * s2[i] + lr * g[i] / np.sqrt(ms + 1e-10)
+            exp = (w[i] - mom, ms, mom)
+        else:
+            acc = 0.95 * s1[i] + 0.05 * g[i] ** 2
+            upd = np.sqrt(s2[i] + 1e-8) / np.sqrt(acc + 1e-8) * g[i]
+            exp = (w[i] - lr * upd, acc, 0.95 * s2[i] + 0.05 * upd ** 2)
+        assert np.allclose([float(tw[i]), float(ts1[i]), float(ts2[i])], exp, rtol=1e-12, atol=0)
+    if opt != "adam":          # rows outside the IndexedSlices: untouched
+        mask = torch.tensor([True, False] * 3 + [True])
+        tw, ts1, ts2 = O._opt_update(opt, torch.tensor(w), torch.tensor(g), lr, torch.tensor(s1), torch.tensor(s2), t, mask)
+        assert np.array_equal(tw.numpy()[1::2], w[1::2]) and np.array_equal(ts1.numpy()[1::2], s1[1::2])

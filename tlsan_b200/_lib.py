@@ -29,6 +29,14 @@ class Next(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class Opt(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("step", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("rho", C.c_float),
+                ("momentum", C.c_float), ("epsilon", C.c_float), ("slot1", C.c_void_p), ("slot2", C.c_void_p)]
+
+
+OPT_KIND = dict(sgd=0, adam=1, rmsprop=2, adadelta=3)
+
+
 class Dataset(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("uid", "pre_off", "pre_items", "pre_time", "new_off", "new_items", "cand",
                                           "second_i", "second_f", "ucate")] + [("n", C.c_int64)]
@@ -64,6 +72,8 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p]),
     "tlsan_apply_flat": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_float, C.c_float, C.c_float,
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "tlsan_apply_flat_opt": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                       C.POINTER(Opt), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "tlsan_dp_arena_bytes": (C.c_int, [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_size_t)]),
     "tlsan_dp_arena_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "tlsan_dp_arena_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
@@ -87,6 +97,10 @@ _SIGS = {
                                                                                   C.c_void_p]),
     "tlsan_collate": (C.c_int, [C.POINTER(Dataset), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int64, C.c_void_p]),
+    "tlsan_ds_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tlsan_ds_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
+    "tlsan_ds_emit": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] + [C.c_void_p] * 7 + [C.POINTER(Dataset), C.POINTER(Dataset),
+                                                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "tlsan_shard_pack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "tlsan_shard_unpack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("TLSAN_LIB") or os.path.join(HERE, "libtlsan_b200.so")    # TLSAN_LIB: A/B builds of the same sources
-SOURCES = ["tlsan_abi.cu", "tlsan_fwd_bwd.cu", "tlsan_fused_mma.cu", "tlsan_fused_async.cu", "tlsan_fused_pf.cu", "tlsan_sort.cu", "tlsan_update.cu", "tlsan_dataset.cu", "tlsan_shard.cu", "tlsan_rank_tc.cu", "tlsan_host.cpp"]
+SOURCES = ["tlsan_abi.cu", "tlsan_fwd_bwd.cu", "tlsan_fused_mma.cu", "tlsan_fused_async.cu", "tlsan_fused_pf.cu", "tlsan_sort.cu", "tlsan_update.cu", "tlsan_dataset.cu", "tlsan_shard.cu", "tlsan_builder.cu", "tlsan_rank_tc.cu", "tlsan_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "128"]
 

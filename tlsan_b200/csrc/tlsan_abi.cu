@@ -343,7 +343,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
 
 static int apply_flat_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
                            float clip_norm, void* workspace, size_t workspace_bytes, float* stats, bool have_tsq,
-                           void* stream) {
+                           void* stream, const tlsan_opt_t* opt = nullptr) {
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
@@ -353,8 +353,18 @@ static int apply_flat_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
           w.total + 256);
   char* ws = ws_base(workspace);
+  if (opt && opt->kind != TLSAN_OPT_SGD) {
+    REQUIRE(opt->kind >= TLSAN_OPT_ADAM && opt->kind <= TLSAN_OPT_ADADELTA, TLSAN_E_UNSUPPORTED, "unknown optimizer kind %d", opt->kind);
+    REQUIRE(opt->slot1 && opt->slot2 && opt->step >= 1, TLSAN_E_NULL, "optimizer slots are NULL or step < 1");
+    // the slots mirror ONE weight buffer: emb | usert | item_b | dense must be laid out like tlsan_dp_exchange needs
+    const long long NR = (long long)dims->NI + dims->NC + dims->NU;
+    const long long off_usert = NR * 32, off_itemb = off_usert + ((long long)dims->NU * dims->L + 3) / 4 * 4;
+    const long long off_dense = off_itemb + ((long long)dims->NI + 3) / 4 * 4;
+    REQUIRE(p->usert == p->emb + off_usert && p->item_b == p->emb + off_itemb && p->dense == p->emb + off_dense,
+            TLSAN_E_UNSUPPORTED, "adam / rmsprop / adadelta need emb | usert | item_b | dense in one buffer (see header)");
+  }
   rc = tlsan_launch_apply(*dims, *p, w, ws, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, flat + w.f_dgrad, lr,
-                          reg, clip_norm, have_tsq, stats, (cudaStream_t)stream);
+                          reg, clip_norm, have_tsq, stats, opt, (cudaStream_t)stream);
   tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
   return rc;
 }
@@ -369,6 +379,12 @@ int tlsan_step_grads(const tlsan_dims_t* dims, const tlsan_params_t* p, const tl
 int tlsan_apply_flat(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
                      float clip_norm, void* workspace, size_t workspace_bytes, float* stats, void* stream) {
   return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream);
+}
+
+int tlsan_apply_flat_opt(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
+                         float clip_norm, const tlsan_opt_t* opt, void* workspace, size_t workspace_bytes, float* stats,
+                         void* stream) {
+  return apply_flat_impl(dims, p, flat, lr, reg, clip_norm, workspace, workspace_bytes, stats, true, stream, opt);
 }
 
 int tlsan_step_grads_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,

@@ -137,7 +137,7 @@ int tlsan_launch_finalize1(const TlsanWs& w, char* ws, int grid_a, int grid_b, i
                            cudaStream_t st);
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                        const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
-                       float reg, float clip, bool have_tsq, float* stats, cudaStream_t st);
+                       float reg, float clip, bool have_tsq, float* stats, const tlsan_opt_t* opt, cudaStream_t st);
 int tlsan_launch_table_sumsq(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                              cudaStream_t st);
 int tlsan_launch_apply_replicated(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,

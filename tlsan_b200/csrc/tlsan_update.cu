@@ -5,6 +5,7 @@
 //   k_finalize2    global norm, clip scale, loss, SGD on the 4449 small parameters
 //   k_apply_rows / k_apply_cate   W <- W - lr * scale * (g_sparse + reg * W) for every table row
 //   k_label_rank   full-catalogue rank of the label item (model.py:140-156)
+#include <math.h>
 #include <stdlib.h>
 #include "tlsan_common.cuh"
 
@@ -160,6 +161,51 @@ __global__ void __launch_bounds__(256) k_table_sumsq(const float* __restrict__ e
   }
 }
 
+// ---- optimisers of init_optimizer (model.py:188-195).  Every trainable element sees its AGGREGATED, clipped gradient
+// g = (sum of its slices + reg * w) * scale each step: the L2 term makes the IndexedSlices of a table cover all of its
+// rows, so TF's sparse apply ops reduce to the dense formulas (tf.train.*Optimizer defaults of TF 1.8):
+//   sgd      w -= lr g
+//   adam     m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; w -= lr c1 m / (sqrt(v) + eps), c1 = sqrt(1-b2^t)/(1-b1^t)
+//   rmsprop  ms = rho ms + (1-rho) g^2 ; mom = momentum mom + lr g / sqrt(ms + eps) ; w -= mom      (ms starts at 1)
+//   adadelta acc = rho acc + (1-rho) g^2 ; u = sqrt(acc_u + eps) / sqrt(acc + eps) g ; acc_u = rho acc_u + (1-rho) u^2 ;
+//            w -= lr u
+// The two slot arrays mirror the weight buffer (element of w at wbase + i <-> s1[i], s2[i]).
+struct OptArgs { int kind; float a, b, eps, c1; float* s1; float* s2; const float* wbase; };
+__device__ __forceinline__ float opt_step(float w, float g, float lr, const OptArgs& o, const float* wp) {
+  if (o.kind == TLSAN_OPT_SGD) return w - lr * g;
+  const size_t i = (size_t)(wp - o.wbase);
+  if (o.kind == TLSAN_OPT_ADAM) {
+    const float m = o.a * o.s1[i] + (1.f - o.a) * g, v = o.b * o.s2[i] + (1.f - o.b) * g * g;
+    o.s1[i] = m; o.s2[i] = v;
+    return w - lr * o.c1 * m / (sqrtf(v) + o.eps);
+  }
+  if (o.kind == TLSAN_OPT_RMSPROP) {
+    const float ms = o.a * o.s1[i] + (1.f - o.a) * g * g;
+    const float mom = o.b * o.s2[i] + lr * g / sqrtf(ms + o.eps);
+    o.s1[i] = ms; o.s2[i] = mom;
+    return w - mom;
+  }
+  const float acc = o.a * o.s1[i] + (1.f - o.a) * g * g;             // adadelta
+  const float u = sqrtf(o.s2[i] + o.eps) / sqrtf(acc + o.eps) * g;
+  o.s1[i] = acc; o.s2[i] = o.a * o.s2[i] + (1.f - o.a) * u * u;
+  return w - lr * u;
+}
+static OptArgs opt_args(const tlsan_opt_t* opt, const float* wbase) {
+  OptArgs o;
+  o.kind = opt ? opt->kind : TLSAN_OPT_SGD; o.a = o.b = o.eps = o.c1 = 0.f; o.s1 = o.s2 = nullptr; o.wbase = wbase;
+  if (!opt || o.kind == TLSAN_OPT_SGD) return o;
+  o.s1 = opt->slot1; o.s2 = opt->slot2;
+  if (o.kind == TLSAN_OPT_ADAM) {
+    o.a = opt->beta1; o.b = opt->beta2; o.eps = opt->epsilon;
+    o.c1 = (float)(sqrt(1.0 - pow((double)opt->beta2, (double)opt->step)) / (1.0 - pow((double)opt->beta1, (double)opt->step)));
+  } else if (o.kind == TLSAN_OPT_RMSPROP) {
+    o.a = opt->rho; o.b = opt->momentum; o.eps = opt->epsilon;
+  } else {
+    o.a = opt->rho; o.eps = opt->epsilon;
+  }
+  return o;
+}
+
 // global norm (TF style: un-aggregated slices, see oracle header), clip scale, loss, dense SGD
 __device__ __forceinline__ double block_sum_1024d(double v, double* sh) {   // fixed order: lanes, then warps
 #pragma unroll
@@ -177,7 +223,8 @@ __device__ __forceinline__ double block_sum_1024d(double v, double* sh) {   // f
 __global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dgrad, const float* __restrict__ tsq,
                                                     int ntsq, const float* __restrict__ extra_sq, int n_extra,
                                                     float invB, float lr, float reg, float clip,
-                                                    float* __restrict__ dense, float* __restrict__ stats) {
+                                                    float* __restrict__ dense, float* __restrict__ stats,
+                                                    const OptArgs opt) {
   __shared__ double sh[32];
   float g[5];
   double s = 0.0;
@@ -208,7 +255,10 @@ __global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dg
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     const int e = threadIdx.x + 1024 * q;
-    if (e < TLSAN_DENSE_COUNT) dense[e] -= lr * (g[q] * scale);
+    if (e < TLSAN_DENSE_COUNT) {
+      if (opt.kind == TLSAN_OPT_SGD) dense[e] -= lr * (g[q] * scale);
+      else dense[e] = opt_step(dense[e], g[q] * scale, lr, opt, dense + e);
+    }
   }
 }
 
@@ -217,7 +267,7 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
                                                     float* __restrict__ usert, float* __restrict__ item_b,
                                                     const float* __restrict__ g_i, const float* __restrict__ g_b,
                                                     const float* __restrict__ g_u, float lr, float reg,
-                                                    const float* __restrict__ stats) {
+                                                    const float* __restrict__ stats, const OptArgs opt) {
   const float scale = stats[TLSAN_STAT_SCALE];
   // float4 units: item rows (8 per row), user rows (8 per row); then scalars: usert, item_b
   const long long v1 = (long long)NI * 8, v2 = v1 + (long long)NU * 8;
@@ -235,18 +285,30 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
         g = *reinterpret_cast<const float4*>(g_u + (x >> 3) * PU + (x & 7) * 4);
       }
       float4 w = *wp;
-      w.x -= lr * ((g.x + reg * w.x) * scale); w.y -= lr * ((g.y + reg * w.y) * scale);
-      w.z -= lr * ((g.z + reg * w.z) * scale); w.w -= lr * ((g.w + reg * w.w) * scale);
+      if (opt.kind == TLSAN_OPT_SGD) {
+        w.x -= lr * ((g.x + reg * w.x) * scale); w.y -= lr * ((g.y + reg * w.y) * scale);
+        w.z -= lr * ((g.z + reg * w.z) * scale); w.w -= lr * ((g.w + reg * w.w) * scale);
+      } else {
+        const float* f = reinterpret_cast<const float*>(wp);
+        w.x = opt_step(w.x, (g.x + reg * w.x) * scale, lr, opt, f); w.y = opt_step(w.y, (g.y + reg * w.y) * scale, lr, opt, f + 1);
+        w.z = opt_step(w.z, (g.z + reg * w.z) * scale, lr, opt, f + 2); w.w = opt_step(w.w, (g.w + reg * w.w) * scale, lr, opt, f + 3);
+      }
       *wp = w;
     } else {
       const long long x = e - v2;
       if (x < n3) {
         const long long u = x / L; const int t = (int)(x - u * L);
         const float w = usert[x];
-        usert[x] = w - lr * ((g_u[u * PU + 32 + t] + reg * w) * scale);
+        const float g = (g_u[u * PU + 32 + t] + reg * w) * scale;
+        usert[x] = opt.kind == TLSAN_OPT_SGD ? w - lr * g : opt_step(w, g, lr, opt, usert + x);
       } else {
         const long long y = x - n3;
-        item_b[y] = item_b[y] - lr * (g_b[y] * scale);
+        const float g = g_b[y] * scale;
+        // item_b has no L2 term: its gradient is a truly sparse IndexedSlices.  TF's sparse RMSProp / Adadelta kernels
+        // leave the rows outside the slices (weights AND slots) untouched; sparse Adam (non-lazy) decays every row,
+        // which is the dense formula with g = 0.  A row is "outside" when its summed gradient is exactly 0.
+        if (opt.kind == TLSAN_OPT_SGD) item_b[y] = item_b[y] - lr * g;
+        else if (opt.kind == TLSAN_OPT_ADAM || g != 0.f) item_b[y] = opt_step(item_b[y], g, lr, opt, item_b + y);
       }
     }
   }
@@ -256,7 +318,7 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
 __global__ void __launch_bounds__(256) k_apply_cate(int NI, float* __restrict__ emb, const float* __restrict__ g_i,
                                                     const int* __restrict__ cate_off,
                                                     const int* __restrict__ cate_items, float lr, float reg,
-                                                    const float* __restrict__ stats) {
+                                                    const float* __restrict__ stats, const OptArgs opt) {
   __shared__ float sh[8][32];
   const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lo = cate_off[k], hi = cate_off[k + 1];
@@ -272,7 +334,8 @@ __global__ void __launch_bounds__(256) k_apply_cate(int NI, float* __restrict__ 
     const float scale = stats[TLSAN_STAT_SCALE];
     float* wp = emb + (size_t)(NI + k) * 32 + lane;
     const float w = *wp;
-    *wp = w - lr * ((g + reg * w) * scale);
+    const float gg = (g + reg * w) * scale;
+    *wp = opt.kind == TLSAN_OPT_SGD ? w - lr * gg : opt_step(w, gg, lr, opt, wp);
   }
 }
 
@@ -364,7 +427,8 @@ int tlsan_launch_table_sumsq(const tlsan_dims_t& d, const tlsan_params_t& p, con
 
 int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                        const float* g_i, const float* g_b, const float* g_u, const float* dgrad, float lr,
-                       float reg, float clip, bool have_tsq, float* stats, cudaStream_t st) {
+                       float reg, float clip, bool have_tsq, float* stats, const tlsan_opt_t* optd, cudaStream_t st) {
+  const OptArgs opt = opt_args(optd, p.emb);
   float* tsq = reinterpret_cast<float*>(ws + w.tsq);
   const int ntsq = tsq_grid();
   if (!have_tsq) {
@@ -372,16 +436,16 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
     if (rc) return rc;
   }
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, nullptr, 0, invB, lr, reg, clip, p.dense, stats);
+  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, nullptr, 0, invB, lr, reg, clip, p.dense, stats, opt);
   TLSAN_CHECK_LAUNCH("k_finalize2");
   const long long n4 = (long long)d.NI * 8 + (long long)d.NU * 8 + (long long)d.NU * d.L + d.NI;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tlsan_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   k_apply_rows<<<(unsigned)blocks, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert, p.item_b, g_i, g_b,
-                                                 g_u, lr, reg, stats);
+                                                 g_u, lr, reg, stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_rows");
-  k_apply_cate<<<d.NC, 256, 0, st>>>(d.NI, p.emb, g_i, p.cate_off, p.cate_items, lr, reg, stats);
+  k_apply_cate<<<d.NC, 256, 0, st>>>(d.NI, p.emb, g_i, p.cate_off, p.cate_items, lr, reg, stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_cate");
   return TLSAN_OK;
 }
@@ -606,7 +670,7 @@ int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, con
   TLSAN_CHECK_LAUNCH("k_dp_dense_sum");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
   k_finalize2<<<1, 1024, 0, st>>>(dtot, reinterpret_cast<float*>(ws + w.tsq), tsq_grid(), nullptr, 0, invB, lr, reg,
-                                  clip, p.dense, stats);
+                                  clip, p.dense, stats, opt_args(nullptr, p.emb));
   TLSAN_CHECK_LAUNCH("k_finalize2");
   k_dp_apply_slice<<<tlsan_num_sms() * 4, 256, 0, st>>>(peers, y, rank, world, d.NI + d.NC, d.NU, d.L, w.PU,
                                                         (long long)w.f_gb, (long long)w.f_gu, p.emb, lr, reg, stats,
@@ -631,14 +695,15 @@ int tlsan_launch_apply_replicated(const tlsan_dims_t& d, const tlsan_params_t& p
                                       (long long)d.NU * d.L, tsq);
   TLSAN_CHECK_LAUNCH("k_table_sumsq");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, item_sumsq, n_item_sumsq, invB, lr, reg, clip, p.dense, stats);
+  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, item_sumsq, n_item_sumsq, invB, lr, reg, clip, p.dense, stats,
+                                  opt_args(nullptr, p.emb));
   TLSAN_CHECK_LAUNCH("k_finalize2");
   const long long n4 = (long long)d.NU * 8 + (long long)d.NU * d.L;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tlsan_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   k_apply_rows<<<(unsigned)blocks, 256, 0, st>>>(0, d.NC, d.NU, d.L, w.PU, tail, p.usert, nullptr, nullptr, nullptr,
-                                                 g_u, lr, reg, stats);
+                                                 g_u, lr, reg, stats, opt_args(nullptr, p.emb));
   TLSAN_CHECK_LAUNCH("k_apply_rows");
   return TLSAN_OK;
 }

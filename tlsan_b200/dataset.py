@@ -46,6 +46,31 @@ class DeviceDataset:
                               new_off=p("new_off"), new_items=p("new_items"), cand=p("cand"),
                               second_i=p("second_i"), second_f=p("second_f"), ucate=p("ucate"), n=self.n)
 
+    @classmethod
+    def from_device(cls, tensors, is_test, device=None):
+        """Wrap CSR arrays that are ALREADY in HBM (the GPU dataset builder's output): keys uid, pre_off, pre_items,
+        pre_time, new_off, new_items, cand, ucate and second_i (test) / second_f (train)."""
+        self = cls.__new__(cls)
+        self._lib = _lib.lib()
+        self.device = torch.device(device if device is not None else tensors["uid"].device)
+        self.is_test = bool(is_test)
+        self.n = int(tensors["uid"].numel())
+        self.new_len = (tensors["new_off"][1:] - tensors["new_off"][:-1]).cpu().numpy().astype(np.int64)
+        self.max_new_len = int(self.new_len.max()) if self.n else 1
+        self._t = dict(tensors)
+        p = lambda k: self._t[k].data_ptr() if k in self._t else None
+        self.c = _lib.Dataset(uid=p("uid"), pre_off=p("pre_off"), pre_items=p("pre_items"), pre_time=p("pre_time"),
+                              new_off=p("new_off"), new_items=p("new_items"), cand=p("cand"),
+                              second_i=p("second_i"), second_f=p("second_f"), ucate=p("ucate"), n=self.n)
+        return self
+
+    def to_csr(self):
+        """Host copy as a CsrDataset (tests, checkpoints)."""
+        from .input import CsrDataset
+        g = lambda k: self._t[k].cpu().numpy()
+        return CsrDataset(g("uid"), g("pre_off"), g("pre_items"), g("pre_time"), g("new_off"), g("new_items"), g("cand"),
+                          g("second_i") if self.is_test else g("second_f"), g("ucate"), self.is_test)
+
     def __len__(self):
         return self.n
 

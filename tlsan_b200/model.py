@@ -153,8 +153,6 @@ class Model(object):
             raise ValueError("kernels are built for hidden_units=64, num_heads=8, embedding sizes 32")
         if config.get("dropout", 0.0) != 0.0:
             raise ValueError("dropout > 0 is not supported (reference default 0.0, train.py:30)")
-        if config.get("optimizer", "sgd") != "sgd":
-            raise ValueError("only the reference default optimizer 'sgd' is implemented (train.py:40)")
 
     def __init__(self, config, item_cate_list, device=None, seed=1234, process_group=None, validate=True,
                  dp_mode=None):
@@ -237,6 +235,23 @@ class Model(object):
                               item_b=self.item_b.data_ptr(), dense=self.dense.data_ptr(),
                               icl=self.icl.data_ptr(), cate_off=self.cate_off.data_ptr(),
                               cate_items=self.cate_items.data_ptr())
+
+        # ---- optimizer (model.py:188-195): anything but adadelta / adam / rmsprop is GradientDescentOptimizer
+        opt = config.get("optimizer", "sgd")
+        self.optimizer = opt if opt in ("adadelta", "adam", "rmsprop") else "sgd"
+        self._slots = None
+        if self.optimizer != "sgd":
+            if self.world > 1 and self.dp_mode == "p2p":
+                raise ValueError("the peer-memory exchange (dp_mode='p2p') implements sgd only; use dp_mode='nccl'")
+            # slot variables mirror the weight buffer element for element; TF 1.8 initial values: adam m, v = 0;
+            # rmsprop rms = 1, momentum = 0; adadelta accum, accum_update = 0
+            self._slots = (torch.ones_like(self._wflat) if self.optimizer == "rmsprop" else torch.zeros_like(self._wflat),
+                           torch.zeros_like(self._wflat))
+            d = dict(adam=(0.9, 0.999, 0.0, 0.0, 1e-8), rmsprop=(0.0, 0.0, 0.9, 0.0, 1e-10),
+                     adadelta=(0.0, 0.0, 0.95, 0.0, 1e-8))[self.optimizer]
+            self._opt = _lib.Opt(kind=_lib.OPT_KIND[self.optimizer], step=0, beta1=d[0], beta2=d[1], rho=d[2],
+                                 momentum=d[3], epsilon=d[4], slot1=self._slots[0].data_ptr(),
+                                 slot2=self._slots[1].data_ptr())
 
         self._stats = torch.zeros(_lib.STAT_COUNT, device=dev)
         self._ws = [None, None]
@@ -346,7 +361,22 @@ class Model(object):
             nxt = Next(dims=C.pointer(ndims), batch=C.pointer(next_db.c), workspace=nws.data_ptr(),
                        workspace_bytes=nws.numel())
         nref = C.byref(nxt) if nxt is not None else None
-        if self.world == 1:
+        if self.optimizer != "sgd":
+            # gradients into the flat buffer (summed over the ranks when data parallel), then the fused
+            # L2 + clip + adam / rmsprop / adadelta update of every table row and small parameter
+            n = C.c_int64()
+            check(self._lib.tlsan_flat_count(C.byref(dims), C.byref(n)))
+            if self._flat is None or self._flat.numel() != n.value:
+                self._flat = torch.empty(int(n.value), dtype=torch.float32, device=self.device)
+            check(self._lib.tlsan_step_grads_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref,
+                                                       ws.data_ptr(), ws.numel(), self._flat.data_ptr(), st))
+            if self.world > 1:
+                torch.distributed.all_reduce(self._flat, group=self.pg)
+            self._opt.step += 1
+            check(self._lib.tlsan_apply_flat_opt(C.byref(dims), C.byref(self._params), self._flat.data_ptr(), lr,
+                                                 self.reg, self.clip, C.byref(self._opt), ws.data_ptr(), ws.numel(),
+                                                 self._stats.data_ptr(), st))
+        elif self.world == 1:
             check(self._lib.tlsan_train_step_pipelined(C.byref(dims), C.byref(self._params), C.byref(db.c), nref, lr,
                                                        self.reg, self.clip, ws.data_ptr(), ws.numel(),
                                                        self._stats.data_ptr(), st))
@@ -570,6 +600,27 @@ class Model(object):
         self._rtp = np.zeros(len(KS)); self._rfn = np.zeros(len(KS))
 
     # ------------------------------------------------------------------ state
+    def slot_views(self):
+        """Optimizer slot variables per TF variable name: {name: (slot1, slot2)} (adam m / v, rmsprop rms / momentum,
+        adadelta accum / accum_update); None for sgd."""
+        if self._slots is None:
+            return None
+        NR, up4 = self.NI + self.NC + self.NU, lambda n: (n + 3) // 4 * 4
+        o_usert = NR * 32; o_itemb = o_usert + up4(self.NU * self.L); o_dense = o_itemb + up4(self.NI)
+        out = OrderedDict()
+        for s_ in (0, 1):
+            f = self._slots[s_]
+            e = f[:o_usert].view(NR, 32)
+            t = dict(item_emb=e[:self.NI], cate_emb=e[self.NI:self.NI + self.NC], user_emb=e[self.NI + self.NC:],
+                     usert_emb=f[o_usert:o_usert + self.NU * self.L].view(self.NU, self.L),
+                     item_b=f[o_itemb:o_itemb + self.NI])
+            for name, (off, shape) in DENSE_LAYOUT.items():
+                n = int(np.prod(shape)) if shape else 1
+                t[name] = f[o_dense + off:o_dense + off + n].reshape(shape)
+            for k, v in t.items():
+                out.setdefault(k, [None, None])[s_] = v
+        return out
+
     def state_dict(self):
         """All trainable variables keyed by their TF names (model.py:56-81, scopes :328-364)."""
         sd = OrderedDict()
@@ -599,8 +650,13 @@ class Model(object):
         checkpoint_path = os.path.join(self.config["model_dir"], "TLSAN")
         step = self.global_step.eval()
         save_path = "%s-%d" % (checkpoint_path, step)
-        torch.save({"variables": OrderedDict(self.state_dict()), "global_step": int(step),
-                    "global_epoch_step": int(self.global_epoch_step.eval())}, save_path)
+        ck = {"variables": OrderedDict(self.state_dict()), "global_step": int(step),
+              "global_epoch_step": int(self.global_epoch_step.eval())}
+        if self._slots is not None:           # tf.train.Saver stores the optimizer's slot variables too
+            ck["optimizer"] = self.optimizer
+            ck["opt_step"] = int(self._opt.step)
+            ck["slot1"], ck["slot2"] = self._slots[0].cpu(), self._slots[1].cpu()
+        torch.save(ck, save_path)
         json.dump(dict(self.config), open("%s-%d.json" % (checkpoint_path, step), "w"), indent=2)
         print("model saved at %s" % save_path, flush=True)
         return save_path
@@ -611,4 +667,7 @@ class Model(object):
         self.load_state_dict(ck["variables"])
         self.global_step.value = int(ck["global_step"])
         self.global_epoch_step.value = int(ck["global_epoch_step"])
+        if self._slots is not None and ck.get("optimizer") == self.optimizer:
+            self._slots[0].copy_(ck["slot1"]); self._slots[1].copy_(ck["slot2"])
+            self._opt.step = int(ck["opt_step"])
         print("model restored from %s" % path, flush=True)

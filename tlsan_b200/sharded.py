@@ -100,6 +100,8 @@ class ShardedModel(object):
         if partition not in ("mod", "block"):
             raise ValueError("partition must be 'mod' or 'block'")
         Model._check_config(config)
+        if config.get("optimizer", "sgd") in ("adadelta", "adam", "rmsprop"):
+            raise ValueError("row-sharded tables implement the reference default optimizer 'sgd' only (train.py:40)")
         self._lib = _lib.lib()
         if not torch.cuda.is_available():
             raise _lib.TlsanError("tlsan_b200 needs a CUDA device (no CPU fallback)")
