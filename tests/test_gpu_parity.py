@@ -328,3 +328,29 @@ def test_score_workspace_path_matches_fused_path_and_oracle():
     r2, _ = O.forward_logits(params, icl, sub, 2, config=cfg)
     got = lg_ws.cpu().numpy()
     assert rel_err(got[rows, 0], r1) < TOL and rel_err(got[rows, 1], r2) < TOL
+
+
+def test_train_summary_writes_the_reference_tags(dm, tmp_path):
+    """Model.train(add_summary=True) with writers attached (model.py:174-183, 228-230): the eight summaries of
+    self.train_summary, histograms counted over every element of the variable / of u_t [B, 64]."""
+    import json
+    from tlsan_b200.summary import attach_writers
+    cfg = _cfg(*dm.counts)
+    cfg["model_dir"] = str(tmp_path)
+    params = _params(cfg)
+    model = attach_writers(model_from_params(params, dm.icl, cfg))
+    batch = O.collate_train(dm.train_set[:48], 10)
+    ref = O.train_step(params, dm.icl, batch, 1.0, cfg, dtype=torch.float64)
+    loss = model.train(None, batch, 1.0, add_summary=True)
+    model.train_writer.close()
+    scal = {r["tag"]: r["value"] for r in map(json.loads, open(model.train_writer.path))}
+    assert abs(scal["Training Loss"] - loss) < 1e-12
+    l2 = 0.5 * sum(float(np.sum(np.asarray(params[k], np.float64) ** 2)) for k in O.TABLE_NAMES)
+    assert abs(scal["L2_norm_user_item"] - l2) / l2 < 2e-3            # (loss - bce) / reg in fp32: ~1e-7 / 5e-5 relative
+    hist = {r["tag"]: r for r in map(json.loads, open(model.train_writer.hist_path))}
+    NU, NI, NC = dm.counts
+    want = {"gamma": 1, "embedding/1_item_emb": NI * 32, "embedding/2_user_emb": NU * 32, "embedding/3_cate_emb": NC * 32,
+            "embedding/4_usert_emb": NU * 10, "attention_output": 48 * 64}
+    assert {k: hist[k]["num"] for k in want} == want
+    new_item = ref["new_params"]["item_emb"]
+    assert abs(hist["embedding/1_item_emb"]["sum"] - float(np.sum(new_item))) < 1e-3 * float(np.sum(np.abs(new_item)))

@@ -24,3 +24,31 @@ def test_attach_writers_creates_train_and_eval_dirs(tmp_path):
     m.train_writer.flush()
     assert (tmp_path / "save_path" / "train" / "scalars.jsonl").exists()
     assert (tmp_path / "save_path" / "eval").is_dir()
+
+
+def test_histogram_proto_follows_tf_buckets(tmp_path):
+    """tf.summary.histogram (model.py:174-180): HistogramProto moments + counts over TF's exponential bucket limits."""
+    import numpy as np
+    import torch
+    from tlsan_b200.summary import histogram_proto, tf_bucket_limits
+    lim = tf_bucket_limits()
+    assert lim[len(lim) // 2] == 0.0 and abs(lim[len(lim) // 2 + 1] - 1e-12) < 1e-24 and np.all(np.diff(lim) > 0)
+    assert abs(lim[len(lim) // 2 + 2] / lim[len(lim) // 2 + 1] - 1.1) < 1e-12
+    rng = np.random.default_rng(0)
+    v = np.r_[rng.standard_normal(1000) * 0.3, 0.0, -1.0, 1.0]
+    for h in (histogram_proto(v), histogram_proto(torch.as_tensor(v))):
+        assert h["num"] == len(v) and sum(h["bucket"]) == len(v)
+        assert abs(h["sum"] - v.sum()) < 1e-9 and abs(h["sum_squares"] - (v * v).sum()) < 1e-9
+        assert h["min"] == v.min() and h["max"] == v.max()
+        # every value lies in the bucket (previous limit, limit]... TF's rule: bucket = first limit > value
+        edges = np.array(h["bucket_limit"])
+        assert np.all(np.diff(edges) > 0)
+        full = np.searchsorted(lim, v, side="right")
+        for limit, count in zip(h["bucket_limit"], h["bucket"]):
+            if count:
+                assert count == int(np.sum(lim[full] == limit))
+    w = JsonlSummaryWriter(str(tmp_path / "train"))
+    w.add_histogram("gamma", np.array([1.0]), 7)
+    w.close()
+    rec = json.loads(open(w.hist_path).readline())
+    assert rec["tag"] == "gamma" and rec["step"] == 7 and rec["num"] == 1 and rec["bucket"][-1] == 1

@@ -52,7 +52,7 @@ static bool use_mma() { return fused_impl() >= 1; }
 // The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
 // onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
 // events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
-struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
+struct SideStream { cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
 static SideStream* side_stream() {
   static SideStream per_dev[64];
   static int enabled = -1;
@@ -69,6 +69,7 @@ static SideStream* side_stream() {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, lo) != cudaSuccess ||   // presort: fills gaps
+        cudaStreamCreateWithPriority(&s.st3, cudaStreamNonBlocking, lo) != cudaSuccess ||   // its partition, beside it
         cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.part, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -83,7 +84,9 @@ static bool g_prof_overlap = false;   // the recorded steps ran the sort on the 
 
 // Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
 // one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
-struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr, ev_part = nullptr; bool valid = false; };
+// ev: ranks (inv) ready -- what the gradient-row writers wait for; ev_seg: segment bounds ready too (row reduce; the
+// last kernel of the presort); ev_part: balanced partition ready (long-term forward)
+struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr, ev_seg = nullptr, ev_part = nullptr; bool valid = false; };
 static Presort g_presort[32];
 static Presort* presort_slot(char* ws, bool create) {
   for (auto& e : g_presort) if (e.ws == ws) return &e;
@@ -91,6 +94,7 @@ static Presort* presort_slot(char* ws, bool create) {
   for (auto& e : g_presort)
     if (!e.valid) {
       if (!e.ev && (cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&e.ev_seg, cudaEventDisableTiming) != cudaSuccess ||
                     cudaEventCreateWithFlags(&e.ev_part, cudaEventDisableTiming) != cudaSuccess))
         return nullptr;
       e.ws = ws;
@@ -99,7 +103,7 @@ static Presort* presort_slot(char* ws, bool create) {
   // every slot holds an announced-but-never-consumed presort (callers that dropped their model): one whose
   // kernels have finished can no longer race with anything and may be recycled
   for (auto& e : g_presort)
-    if (cudaEventQuery(e.ev) == cudaSuccess) {
+    if (cudaEventQuery(e.ev_seg) == cudaSuccess && cudaEventQuery(e.ev_part) == cudaSuccess) {
       e.ws = ws;
       e.valid = false;
       return &e;
@@ -145,6 +149,24 @@ static int check_batch(const tlsan_batch_t* b, bool train, int ncand) {
   REQUIRE(b->hist_d == nullptr || fused_impl() == 1 || fused_impl() >= 3, TLSAN_E_UNSUPPORTED,
           "raw day gaps (batch.hist_d) need the mma / hybrid / pf kernels (TLSAN_FUSED_IMPL)");
   return TLSAN_OK;
+}
+
+// where in step k the presort of batch k+1 is released (see tlsan_launch_fwd_bwd_async): TLSAN_PRESORT_AT=1..5
+static int presort_at() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("TLSAN_PRESORT_AT"); v = e ? atoi(e) : 5; if (v < 1 || v > 5) v = 5; }
+  return v;
+}
+
+static int env_int(const char* name, int dflt) {      // A/B switches, read on every call (host side, cheap)
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+bool tlsan_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TLSAN_PDL"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
 }
 
 extern "C" {
@@ -247,7 +269,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   const int32_t* sorted_vals = nullptr;
   tlsan_profile_mark(-1, st);
   SideStream* side = use_mma() ? side_stream() : nullptr;
-  cudaEvent_t sorted = nullptr, part_ready = nullptr;
+  cudaEvent_t sorted = nullptr, part_ready = nullptr, seg_ready = nullptr;
   const bool pf = fused_impl() == 4;                            // kernels that take the balanced partition
   int long_ctas = 3;
   // bit 1 = "the previous *_pipelined call announced this batch": honoured only if that call really enqueued the
@@ -257,6 +279,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   if (presorted) {
     ps->valid = false;
     sorted = ps->ev;
+    seg_ready = ps->ev_seg;
     if (pf) part_ready = ps->ev_part;
     sorted_vals = tlsan_sorted_vals(w, ws);
     tlsan_profile_mark(TLSAN_PHASE_SORT, st);
@@ -272,7 +295,10 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     if (Presort* stale = presort_slot(ws, false)) {
       // a presort announced for this workspace was not consumed (the caller trained on another batch): its
       // kernels may still be writing the sort buffers we are about to reuse
-      if (stale->valid) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev, 0));
+      if (stale->valid) {
+        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev_seg, 0));
+        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev_part, 0));
+      }
       stale->valid = false;
     }
     long_ctas = tlsan_overlap_ctas();
@@ -281,7 +307,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
       TLSAN_CHECK_CUDA(cudaEventRecord(side->part, side->st));
       part_ready = side->part;
     }
-    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, side->st))) return rc;
+    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, nullptr, side->st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
     sorted = side->join;
@@ -290,7 +316,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, side->st))) return rc;
     g_prof_overlap = true;
   } else {
-    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, st))) return rc;
+    if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, nullptr, st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, st);
     if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, st))) return rc;
     g_prof_overlap = false;
@@ -298,7 +324,8 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
     rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() - 2, sorted,
-                                    part_ready, long_ctas, st);
+                                    part_ready, presorted, long_ctas, (next && side) ? side->fork2 : nullptr,
+                                    presort_at(), st);
   else if (fused_impl() == 1)
     rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, long_ctas, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
@@ -315,23 +342,32 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     Presort* ps = presort_slot(wsn, true);
     REQUIRE(ps != nullptr, TLSAN_E_UNSUPPORTED, "too many presorted workspaces in flight");
     const int32_t* unused = nullptr;
-    TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+    if (fused_impl() < 2) TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));   // else recorded inside the chain (presort_at)
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
     if (pf) {     // the consuming (presorted) step runs its forward kernel with 3 CTAs per SM
-      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, side->st2))) return rc;
-      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, side->st2));
+      // two small latency-bound kernels: on their own stream they do not lengthen the sort's chain of launches
+      cudaStream_t pst = env_int("TLSAN_PART_STREAM", 2) == 3 ? side->st3 : side->st2;
+      if (pst != side->st2) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, side->fork2, 0));
+      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, pst))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, pst));
     }
-    if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, side->st2))) return rc;
-    TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev, side->st2));
+    // ps->ev is recorded inside, before the segment-bounds kernel
+    if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, ps->ev, side->st2))) return rc;
+    TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_seg, side->st2));
     ps->valid = true;
   }
   if (side) {
     // the fixed-order sum of the per-CTA partials and the segmented row reduce are independent: side by side
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
-    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, side->st))) return rc;
+    // TLSAN_RR_HI=1: the row reduce takes the HIGH-priority side stream (its CTAs win over the next batch's presort,
+    // which runs at the caller stream's priority), the small partial-sum kernel the caller's
+    const bool rr_hi = env_int("TLSAN_RR_HI", 0) != 0;
+    cudaStream_t s_fin = rr_hi ? st : side->st, s_red = rr_hi ? side->st : st;
+    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, s_fin))) return rc;
+    if (seg_ready) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(s_red, seg_ready, 0));
+    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, s_red);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
-    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   } else {
     if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;

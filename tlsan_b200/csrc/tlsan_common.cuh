@@ -43,6 +43,29 @@ void tlsan_profile_mark(int phase_done, cudaStream_t st);   // phase_done = -1: 
 
 static inline size_t tlsan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL): the kernels of the step's main stream are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of kernel N+1 become resident while kernel N drains and
+// run their prologue (weight images, partition bounds -- nothing kernel N writes) up to pdl_wait(), which returns
+// once kernel N has completed and flushed.  Every such kernel calls pdl_trigger() only AFTER its own pdl_wait(): when
+// kernel N+1 starts, kernel N-1 and everything before it are complete, so the pre-wait region may read whatever
+// kernels <= N-1 wrote.  Launched without the attribute both instructions are no-ops.   TLSAN_PDL=0 switches it off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool tlsan_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tlsan_launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = tlsan_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Workspace carve-up (byte offsets from a 256-B aligned base).
 struct TlsanWs {
   int SLOTS;  // occurrence slots per sample: L long, S short, candidate, u_cate, user
@@ -54,7 +77,7 @@ struct TlsanWs {
   int nchunks;
   size_t keys_a, keys_b, vals_a, vals_b, inv, hist, nvalid, seg_off;
   size_t rows_i, rows_u, gscal, scratch, meta, smeta, sscal, part;
-  size_t part_a, part_b, part_c, tsq, flat;
+  size_t part_a, part_b, part_c, tsq, rpart, flat;
   // flat gradient buffer (float offsets): [g_i (NI+NC)x64 | g_b NIpad | g_u NUxPU | dgrad PART]
   size_t f_gi, f_gb, f_gu, f_dgrad, flat_count;
   size_t total;
@@ -95,6 +118,7 @@ static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   w.part_b = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.part_c = take((size_t)TLSAN_MAX_GRID * TLSAN_PART * 4);
   w.tsq = take((size_t)TLSAN_MAX_GRID * 4 * 4);
+  w.rpart = take((size_t)2 * TLSAN_MAX_GRID * 8 * 72 * 4);   // head / tail partial rows of the balanced segmented reduce
   w.f_gi = 0;
   w.f_gb = (size_t)(d.NI + d.NC) * 64;
   w.f_gu = w.f_gb + tlsan_align_up(d.NI, 4);
@@ -116,7 +140,7 @@ int tlsan_launch_gather(const tlsan_dims_t& d, const tlsan_params_t& p, const in
 int tlsan_launch_bucket(const int32_t* dd, const float* lut, float* out, int32_t* bucket, int64_t n,
                         cudaStream_t st);
 int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
-                      char* ws, const int32_t** sorted_vals, cudaStream_t st);
+                      char* ws, const int32_t** sorted_vals, cudaEvent_t ranks_ready, cudaStream_t st);
 const int32_t* tlsan_sorted_vals(const TlsanWs& w, char* ws);
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st);
@@ -127,7 +151,8 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
                              int long_ctas, cudaStream_t st);
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
-                               cudaEvent_t sorted, cudaEvent_t part_ready, int long_ctas, cudaStream_t st);
+                               cudaEvent_t sorted, cudaEvent_t part_ready, bool part_early, int long_ctas,
+                               cudaEvent_t fork_ev, int fork_at, cudaStream_t st);
 int tlsan_launch_partition_batch(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int fwd_ctas,
                                  void* part, cudaStream_t st);
 int tlsan_overlap_ctas();

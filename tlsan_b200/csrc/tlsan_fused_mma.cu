@@ -438,6 +438,8 @@ __global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restric
     }
   }
   if (threadIdx.x < 64) sbd[threadIdx.x] = dense[TLSAN_OFF_BD + threadIdx.x];
+  pdl_wait();                                      // o_long of the long-term forward
+  pdl_trigger();
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int half = warp & 1;                       // output columns 32*half .. +31
@@ -501,6 +503,8 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) accw[nt][0] = accw[nt][1] = accw[nt][2] = accw[nt][3] = 0.f;
   float bsum = 0.f;                                 // threads < 64: dbd[threadIdx.x]
+  pdl_wait();                                       // dz of the short-term kernel
+  pdl_trigger();
   for (int tile = t_lo; tile < t_hi; ++tile) {
     __syncthreads();                                // previous tile fully consumed (and sb written)
     for (int e = threadIdx.x; e < 16 * 16; e += 128) {
@@ -590,7 +594,7 @@ int tlsan_launch_dense_fwd(const float* dense, float* scratch, int B, cudaStream
   const int ntile16 = (B + 15) / 16;
   int gg = (ntile16 + 3) / 4;
   if (gg > tlsan_num_sms() * 2) gg = tlsan_num_sms() * 2;   // one resident wave: the B image is built once per CTA
-  k_dense_fwd_mma<<<gg, 256, 0, st>>>(dense, scratch, B);
+  tlsan_launch_k(k_dense_fwd_mma, dim3(gg), dim3(256), 0, st, dense, scratch, B);
   TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
   return TLSAN_OK;
 }
@@ -599,7 +603,7 @@ int tlsan_launch_dense_bwd(const float* dense, float* scratch, int B, float* par
   const int ntile16 = (B + 15) / 16;
   const int gc = ntile16 < tlsan_num_sms() * 4 ? ntile16 : tlsan_num_sms() * 4;
   *grid_c = gc;
-  k_dense_bwd_mma<<<gc, 128, 0, st>>>(dense, scratch, B, part);
+  tlsan_launch_k(k_dense_bwd_mma, dim3(gc), dim3(128), 0, st, dense, scratch, B, part);
   TLSAN_CHECK_LAUNCH("k_dense_bwd_mma");
   return TLSAN_OK;
 }

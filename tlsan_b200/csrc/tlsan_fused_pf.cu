@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restri
                                                    int4* __restrict__ sscal) {
   const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nlong = (long long)a.B * a.L;
+  pdl_wait();                                                   // usert / item_b: the previous step's update
+  pdl_trigger();
   if (gidx < nlong) {
     const int b = (int)(gidx / a.L), t = (int)(gidx - (long long)b * a.L);
     int4 m = make_int4(0, 0, 0, 0);
@@ -415,6 +417,9 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
   int eN = ell_of(nextb(it0.b));                                // length of the sample after the newest iterator's
   it1 = advance(it0, eN);
   if (it1.r0 == 0) eN = ell_of(nextb(it1.b));
+  const FwaWT wlt = BWD ? load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t) : FwaWT();
+  pdl_wait();                                                   // meta (k_long_meta) / scratch, ranks (backward)
+  pdl_trigger();
   issue_meta(it0, ring(0));
   issue_meta(it1, ring(1));
   cp_commit();
@@ -425,7 +430,6 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
 
   // per-kernel state
   SoftL2 st; st.init();
-  const FwaWT wlt = BWD ? load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t) : FwaWT();
   FwaGrad G;
   if (BWD) G.init();
   float ggamma = 0.f, sq_acc = 0.f;
@@ -617,6 +621,8 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
   };
 
   int b0 = bBeg;
+  pdl_wait();                                                   // z (k_dense_fwd_mma), smeta / sscal, ranks
+  pdl_trigger();
   issue_meta(b0, ring(0));
   issue_meta(b0 + 1, ring(1));
   cp_commit();
@@ -740,8 +746,8 @@ size_t tlsan_long_meta_bytes(int B, int L) { return (size_t)B * L * sizeof(int4)
 // smeta / sscal may be NULL (scoring: long-term part only)
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st) {
   const long long n = (long long)a.B * a.L + (smeta ? a.B : 0);
-  k_long_meta<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<int4*>(meta), reinterpret_cast<int2*>(smeta),
-                                                          reinterpret_cast<int4*>(sscal));
+  tlsan_launch_k(k_long_meta, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, reinterpret_cast<int4*>(meta),
+                 reinterpret_cast<int2*>(smeta), reinterpret_cast<int4*>(sscal));
   TLSAN_CHECK_LAUNCH("k_long_meta");
   return TLSAN_OK;
 }
@@ -809,7 +815,7 @@ static int launch_pf_long(const FArgs& a, const void* meta, const void* part, in
   }
   const int gr = pf_grid(a.B, ctas_per_sm);
   if (grid_out) *grid_out = gr;
-  k_pf_long<KIND><<<gr, PF_THREADS, A.g.total, st>>>(A);
+  tlsan_launch_k(k_pf_long<KIND>, dim3(gr), dim3(PF_THREADS), (size_t)A.g.total, st, A);
   TLSAN_CHECK_LAUNCH(KIND == 1 ? "k_pf_long<fwd>" : "k_pf_long<bwd>");
   return TLSAN_OK;
 }
@@ -836,7 +842,7 @@ int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, 
   }
   const int gr = pf_grid(a.B, 2);
   if (grid_a) *grid_a = gr;
-  k_pf_short<<<gr, PF_THREADS, smem, st>>>(A);
+  tlsan_launch_k(k_pf_short, dim3(gr), dim3(PF_THREADS), (size_t)smem, st, A);
   TLSAN_CHECK_LAUNCH("k_pf_short");
   return TLSAN_OK;
 }

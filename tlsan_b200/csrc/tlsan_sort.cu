@@ -181,7 +181,7 @@ const int32_t* tlsan_sorted_vals(const TlsanWs& w, char* ws) {
 }
 
 int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, const TlsanWs& w,
-                      char* ws, const int32_t** sorted_vals, cudaStream_t st) {
+                      char* ws, const int32_t** sorted_vals, cudaEvent_t ranks_ready, cudaStream_t st) {
   int* keys_a = reinterpret_cast<int*>(ws + w.keys_a);
   int* keys_b = reinterpret_cast<int*>(ws + w.keys_b);
   int* vals_a = reinterpret_cast<int*>(ws + w.vals_a);
@@ -219,6 +219,9 @@ int tlsan_launch_sort(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsa
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }
   }
+  // the sorted ranks (inv) are complete here: the gradient-row writers need nothing more, only the row reduce reads
+  // the segment bounds
+  if (ranks_ready) TLSAN_CHECK_CUDA(cudaEventRecord(ranks_ready, st));
   k_seg_bounds<<<(unsigned)((w.NR + 1 + 255) / 256), 256, 0, st>>>(kin, nvalid, w.NR, seg_off);
   TLSAN_CHECK_LAUNCH("k_seg_bounds");
   *sorted_vals = vin;

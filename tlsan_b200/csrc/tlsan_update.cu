@@ -7,6 +7,7 @@
 //   k_label_rank   full-catalogue rank of the label item (model.py:140-156)
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "tlsan_common.cuh"
 
 // ------------------------------------------------------------------ segmented reduce
@@ -31,6 +32,8 @@ __global__ void __launch_bounds__(256, 4) k_row_reduce(int NI, int NC, int NU, i
   int2 seg_c = r < NR ? make_int2(seg_off[r], seg_off[r + 1]) : make_int2(0, 0);
   int2 seg_n = r + W < NR ? make_int2(seg_off[r + W], seg_off[r + W + 1]) : make_int2(0, 0);
   int mine_c = seg_c.x + lane < seg_c.y ? vals[seg_c.x + lane] : 0;
+  pdl_wait();                                       // gradient rows of the backward kernels (the sort finished long ago)
+  pdl_trigger();
   for (; r < NR; r += W) {
     const int2 seg_nn = r + 2 * W < NR ? make_int2(seg_off[r + 2 * W], seg_off[r + 2 * W + 1]) : make_int2(0, 0);
     const int mine_n = seg_n.x + lane < seg_n.y ? vals[seg_n.x + lane] : 0;
@@ -87,6 +90,141 @@ __global__ void __launch_bounds__(256, 4) k_row_reduce(int NI, int NC, int NU, i
     }
     seg_c = seg_n; seg_n = seg_nn; mine_c = mine_n;
   }
+}
+
+// ------------------------------------------------------------------ balanced segmented reduce (default)
+// The per-row kernel above gives one warp one ROW: with Zipf item popularity (and 15 categories on the Movies-TV shape)
+// a few warps own segments of thousands of occurrences while the rest idle -- ncu: long_scoreboard 74 % at 41 % of the
+// warps active, 3.1 TB/s.  Here the SORTED OCCURRENCE LIST is what is divided: warp w sums positions
+// [w R, (w+1) R) of the item / category part (R = ceil(T / #warps) rounded up to 16, T = seg_off[NI + NC]), 16 rows
+// (4 KB) in flight per warp, walking the segment ends it meets:
+//   * a segment that lies inside the range is written straight to g_i / g_b;
+//   * the range's first segment, if it began in an earlier range, goes to head[w]; its last one, if it continues in
+//     the next range, to tail[w] (a range inside ONE long segment is a head only);
+//   * k_row_fix (one warp per row) then writes  g[r] = tail[w_a] + head[w_a + 1] + ... + head[w_b]  for the rows whose
+//     segment spans ranges w_a < w_b, and zeros for the rows without occurrences.
+// Ranges, walk order and the order of the fix-up sum are functions of the batch and the grid only: bit-reproducible.
+// The user rows (short segments, payload indexed by sample) keep the row-per-warp loop.
+#define RR_PSTRIDE 72          // floats per partial: 64 + item_b gradient + pad
+__device__ __forceinline__ int rr_range(int T, int NW) {
+  const int r = ((T + NW - 1) / NW + 15) & ~15;
+  return r < 16 ? 16 : r;
+}
+__global__ void __launch_bounds__(256, 4) k_row_reduce_bal(int NI, int NC, int NU, int L, int S, int spsh, int PU,
+                                                        const int* __restrict__ seg_off, const int* __restrict__ keys,
+                                                        const int* __restrict__ vals,
+                                                        const float* __restrict__ rows_i,
+                                                        const float* __restrict__ rows_u,
+                                                        const float* __restrict__ gscal, float* __restrict__ g_i,
+                                                        float* __restrict__ g_b, float* __restrict__ g_u,
+                                                        float* __restrict__ head, float* __restrict__ tail) {
+  const int lane = threadIdx.x & 31;
+  const int NW = gridDim.x * 8;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int smask = (1 << spsh) - 1;
+  const int T = seg_off[NI + NC];
+  const int R = rr_range(T, NW);
+  const int p0 = min(gw * R, T), p1 = min(p0 + R, T);
+  pdl_wait();                                       // gradient rows of the backward kernels (the sort finished long ago)
+  pdl_trigger();
+  if (p0 < p1) {
+    // lane j of a batch at position p holds the key of position p - 1 + j (j = 0..17): the neighbours decide whether
+    // the first / last segment of the range is shared with the adjacent ranges
+    auto key_at = [&](int p, int j) { const int q = p - 1 + j; return (j < 18 && q >= 0 && q < T) ? __ldg(keys + q) : -1; };
+    auto occ_at = [&](int p, int j) { const int q = p - 1 + j; return (j >= 1 && j < 17 && q < p1) ? __ldg(vals + q) : 0; };
+    int key_n = key_at(p0, lane), occ_n = occ_at(p0, lane);
+    float2 acc = make_float2(0.f, 0.f);
+    float accb = 0.f;
+    bool first = true;                              // still inside the first segment of the range
+    const bool head_shared = __shfl_sync(0xffffffffu, key_n, 0) == __shfl_sync(0xffffffffu, key_n, 1);   // key[p0 - 1] == key[p0]
+    for (int p = p0; p < p1; p += 16) {
+      const int cnt = min(16, p1 - p);
+      const int key = key_n, occ = occ_n;
+      float2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        v[i] = i < cnt ? __ldcs(reinterpret_cast<const float2*>(rows_i + (size_t)(p + i) * 64) + lane) : make_float2(0.f, 0.f);
+      if (p + 16 < p1) { key_n = key_at(p + 16, lane); occ_n = occ_at(p + 16, lane); }
+      // item_b gradient: the candidate slot (j == L + S) of sample b contributes gscal[b]
+      const bool is_cand = lane >= 1 && lane <= cnt && (occ & smask) == L + S;
+      const float gb = is_cand ? __ldg(gscal + (occ >> spsh)) : 0.f;
+      const unsigned candmask = __ballot_sync(0xffffffffu, is_cand) >> 1;
+      const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+      // bit i: position p + i is the last of its segment as far as this range can tell
+      const bool last_batch = p + 16 >= p1;             // the range's last position always closes a (partial) segment
+      const unsigned endmask = (__ballot_sync(0xffffffffu, lane >= 1 && (key != knext || (last_batch && lane == cnt))) >> 1) & 0xffffu;
+      const bool tail_shared = last_batch && __shfl_sync(0xffffffffu, key, cnt) == __shfl_sync(0xffffffffu, key, cnt + 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < cnt) {
+          acc.x += v[i].x; acc.y += v[i].y;
+          if (candmask & (1u << i)) accb += __shfl_sync(0xffffffffu, gb, i + 1);
+          if (endmask & (1u << i)) {
+            const int k = __shfl_sync(0xffffffffu, key, i + 1);
+            const bool to_head = first && head_shared;
+            const bool to_tail = !to_head && tail_shared && i == cnt - 1;
+            float* dst = to_head ? head + (size_t)gw * RR_PSTRIDE : to_tail ? tail + (size_t)gw * RR_PSTRIDE : g_i + (size_t)k * 64;
+            reinterpret_cast<float2*>(dst)[lane] = acc;
+            if (lane == 0) {
+              if (to_head || to_tail) dst[64] = accb;
+              else if (k < NI) g_b[k] = accb;
+            }
+            acc = make_float2(0.f, 0.f); accb = 0.f; first = false;
+          }
+        }
+      }
+    }
+  }
+  // ---- user rows: payload rows_u[sample], one warp per row
+  const int NR = NI + NC + NU;
+  for (int r = NI + NC + gw; r < NR; r += NW) {
+    const int lo = __ldg(seg_off + r), hi = __ldg(seg_off + r + 1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = lo; base < hi; base += 32) {
+      const int mine = base + lane < hi ? __ldg(vals + base + lane) : 0;
+      const int cnt = min(32, hi - base);
+      for (int k = 0; k < cnt; ++k) {
+        const int b = __shfl_sync(0xffffffffu, mine, k) >> spsh;
+        const float* src = rows_u + (size_t)b * PU;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          if (lane + 32 * qq < PU) acc[qq] += __ldg(src + lane + 32 * qq);
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq)
+      if (lane + 32 * qq < PU) g_u[(size_t)(r - NI - NC) * PU + lane + 32 * qq] = acc[qq];
+  }
+}
+
+// rows whose segment spans several ranges: tail of the first range + heads of the others, in range order; rows
+// without occurrences: zeros.  NW = the warp count of k_row_reduce_bal.
+__global__ void __launch_bounds__(256) k_row_fix(int NI, int NC, int NW, const int* __restrict__ seg_off,
+                                                 const float* __restrict__ head, const float* __restrict__ tail,
+                                                 float* __restrict__ g_i, float* __restrict__ g_b) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= NI + NC) return;
+  const int lo = __ldg(seg_off + r), hi = __ldg(seg_off + r + 1);
+  const int R = rr_range(__ldg(seg_off + NI + NC), NW);
+  const int wa = lo / R, wb = (hi - 1) / R;
+  const bool empty = lo >= hi;
+  if (!empty && wa == wb) return;                   // written directly by its range (independent of k_row_reduce_bal)
+  pdl_wait();
+  pdl_trigger();
+  float2 acc = make_float2(0.f, 0.f);
+  float accb = 0.f;
+  if (!empty) {
+    acc = reinterpret_cast<const float2*>(tail + (size_t)wa * RR_PSTRIDE)[lane];
+    accb = tail[(size_t)wa * RR_PSTRIDE + 64];
+    for (int w = wa + 1; w <= wb; ++w) {
+      const float2 h = reinterpret_cast<const float2*>(head + (size_t)w * RR_PSTRIDE)[lane];
+      acc.x += h.x; acc.y += h.y;
+      accb += head[(size_t)w * RR_PSTRIDE + 64];
+    }
+  }
+  reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
+  if (r < NI && lane == 0) g_b[r] = accb;
 }
 
 // ------------------------------------------------------------------ dense partials
@@ -228,6 +366,8 @@ __global__ void __launch_bounds__(1024) k_finalize2(const float* __restrict__ dg
   __shared__ double sh[32];
   float g[5];
   double s = 0.0;
+  pdl_wait();
+  pdl_trigger();
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     const int e = threadIdx.x + 1024 * q;
@@ -268,6 +408,8 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
                                                     const float* __restrict__ g_i, const float* __restrict__ g_b,
                                                     const float* __restrict__ g_u, float lr, float reg,
                                                     const float* __restrict__ stats, const OptArgs opt) {
+  pdl_wait();                                       // the clip scale of k_finalize2
+  pdl_trigger();
   const float scale = stats[TLSAN_STAT_SCALE];
   // float4 units: item rows (8 per row), user rows (8 per row); then scalars: usert, item_b
   const long long v1 = (long long)NI * 8, v2 = v1 + (long long)NU * 8;
@@ -337,6 +479,11 @@ __global__ void __launch_bounds__(256) k_apply_cate(int NI, float* __restrict__ 
     const float gg = (g + reg * w) * scale;
     *wp = opt.kind == TLSAN_OPT_SGD ? w - lr * gg : opt_step(w, gg, lr, opt, wp);
   }
+  // launched as the programmatic dependent of k_apply_rows: everything above needs only what k_finalize2 and the
+  // kernels before it wrote (category rows are nobody else's), so it ran BESIDE k_apply_rows; waiting for it here
+  // keeps the chain's invariant (a kernel finishes only after its predecessor)
+  pdl_wait();
+  pdl_trigger();
 }
 
 // rank[b] = #{ j : s_j > s_label  or  (s_j == s_label and j < label) },  s = u_t . all_emb^T + item_b
@@ -386,15 +533,37 @@ __global__ void __launch_bounds__(256) k_label_rank(int NI, const float* __restr
 }
 
 // ------------------------------------------------------------------ launchers
+static bool row_reduce_balanced() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TLSAN_ROW_REDUCE"); v = !(e && !strcmp(e, "row")); }
+  return v != 0;
+}
+
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st) {
   int rgrid = (w.NR + 7) / 8;
   if (rgrid > tlsan_num_sms() * 4) rgrid = tlsan_num_sms() * 4;
-  k_row_reduce<<<rgrid, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU,
-                                               reinterpret_cast<const int*>(ws + w.seg_off), sorted_vals,
-                                               reinterpret_cast<const float*>(ws + w.rows_i),
-                                               reinterpret_cast<const float*>(ws + w.rows_u),
-                                               reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b, g_u);
+  const int* seg_off = reinterpret_cast<const int*>(ws + w.seg_off);
+  if (row_reduce_balanced()) {
+    rgrid = tlsan_num_sms() * 4;
+    // the sorted keys sit in the ping-pong buffer of the same parity as the sorted occurrence ids
+    const int* keys = reinterpret_cast<const int*>(ws + (sorted_vals == reinterpret_cast<const int32_t*>(ws + w.vals_b) ? w.keys_b : w.keys_a));
+    float* head = reinterpret_cast<float*>(ws + w.rpart);
+    float* tail = head + (size_t)TLSAN_MAX_GRID * 8 * RR_PSTRIDE;
+    tlsan_launch_k(k_row_reduce_bal, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off, keys,
+                   (const int*)sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
+                   reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
+                   g_u, head, tail);
+    TLSAN_CHECK_LAUNCH("k_row_reduce_bal");
+    tlsan_launch_k(k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
+                   (const float*)head, (const float*)tail, g_i, g_b);
+    TLSAN_CHECK_LAUNCH("k_row_fix");
+    return TLSAN_OK;
+  }
+  tlsan_launch_k(k_row_reduce, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off,
+                 sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
+                 reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
+                 g_u);
   TLSAN_CHECK_LAUNCH("k_row_reduce");
   return TLSAN_OK;
 }
@@ -436,16 +605,18 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
     if (rc) return rc;
   }
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 1024, 0, st>>>(dgrad, tsq, ntsq, nullptr, 0, invB, lr, reg, clip, p.dense, stats, opt);
+  tlsan_launch_k(k_finalize2, dim3(1), dim3(1024), 0, st, dgrad, (const float*)tsq, ntsq, (const float*)nullptr, 0, invB,
+                 lr, reg, clip, p.dense, stats, opt);
   TLSAN_CHECK_LAUNCH("k_finalize2");
   const long long n4 = (long long)d.NI * 8 + (long long)d.NU * 8 + (long long)d.NU * d.L + d.NI;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tlsan_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  k_apply_rows<<<(unsigned)blocks, 256, 0, st>>>(d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert, p.item_b, g_i, g_b,
-                                                 g_u, lr, reg, stats, opt);
+  tlsan_launch_k(k_apply_rows, dim3((unsigned)blocks), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert,
+                 p.item_b, g_i, g_b, g_u, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_rows");
-  k_apply_cate<<<d.NC, 256, 0, st>>>(d.NI, p.emb, g_i, p.cate_off, p.cate_items, lr, reg, stats, opt);
+  tlsan_launch_k(k_apply_cate, dim3(d.NC), dim3(256), 0, st, d.NI, p.emb, g_i, (const int*)p.cate_off,
+                 (const int*)p.cate_items, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_cate");
   return TLSAN_OK;
 }

@@ -513,8 +513,25 @@ class Model(object):
         loss = float(stats[STAT["loss"]].item())
         self.last_d2h_bytes = 4
         if add_summary and self.train_writer is not None:
-            self.train_writer.add_scalar("Training Loss", loss, self.global_step.eval())
+            self._write_train_summary(db, loss, stats)
         return loss
+
+    def _write_train_summary(self, db, loss, stats):
+        """self.train_summary of model.py:174-183,228-230: five variable histograms, the histogram of the batch's
+        attention output u_t, 'L2_norm_user_item' (the l2_norm sum, :164-169) and 'Training Loss'."""
+        w, step = self.train_writer, self.global_step.eval()
+        w.add_scalar("Training Loss", loss, step)
+        bce = float(stats[STAT["bce"]].item())
+        if self.reg > 0:
+            w.add_scalar("L2_norm_user_item", (loss - bce) / self.reg, step)
+        if hasattr(w, "add_histogram"):
+            w.add_histogram("gamma", self.dense[OFF["GAMMA"]:OFF["GAMMA"] + 1], step)
+            w.add_histogram("embedding/1_item_emb", self.item_emb, step)
+            w.add_histogram("embedding/2_user_emb", self.user_emb, step)
+            w.add_histogram("embedding/3_cate_emb", self.cate_emb, step)
+            w.add_histogram("embedding/4_usert_emb", self.usert_emb, step)
+            _, ut = self.score_staged(db, 1, want_ut=True)
+            w.add_histogram("attention_output", ut, step)
 
     # ------------------------------------------------------------------ scoring
     def score_staged(self, db, ncand=1, want_ut=False):
