@@ -277,6 +277,14 @@ int tlsan_stage_batch_host(const tlsan_dims_t* dims, const int64_t* u, const int
                            const int64_t* sl, const int64_t* sl_new, const int64_t* c, int32_t* pinned, int32_t* dev,
                            int64_t words, int32_t validate, int32_t nthreads, void* stream);
 
+/* The packed feed: a batch that ALREADY sits in page-locked host memory in the staging layout of tlsan_stage_batch_host
+ * (tlsan_b200/input.py, DataInput(..., packed=True), writes its arrays straight into such a buffer; tlsan_stage_batch_host
+ * with dev == NULL packs a 9-tuple into one without copying).  Two host->device copies + the session expansion, no host
+ * pass; n_new = number of valid session items (sum of sl_new clipped to S).  Ids are NOT range checked here: the
+ * producer vouches for them (PackedBatch carries the id maxima of its dataset, Model compares them with its tables). */
+int tlsan_stage_packed(const tlsan_dims_t* dims, const int32_t* pinned, int32_t* dev, int64_t words, int64_t n_new,
+                       void* stream);
+
 /* The same two helpers for batches whose integer fields are already int32 (no narrowing pass; tlsan_b200/input.py
  * emits such batches): half the host memory traffic of the feed, same range checks. */
 int tlsan_pack_batch_host_i32(const tlsan_dims_t* dims, const int32_t* u, const int32_t* i, const int32_t* i2,

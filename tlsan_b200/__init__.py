@@ -1,8 +1,8 @@
 """tlsan_b200: B200-native (sm_100a) TLSAN train / scoring hot path behind the reference
 ``Model`` surface (TLSAN/model.py) and ``input.py`` batch layout.  See DESIGN.md."""
-from .input import CsrDataset, DataInput, DataInputTest  # noqa: F401
+from .input import CsrDataset, DataInput, DataInputTest, PackedBatch  # noqa: F401
 
-__all__ = ["Model", "DataInput", "DataInputTest", "CsrDataset"]
+__all__ = ["Model", "DataInput", "DataInputTest", "CsrDataset", "PackedBatch"]
 
 
 def __getattr__(name):

@@ -95,6 +95,7 @@ _SIGS = {
     "tlsan_stage_words": (C.c_int, [C.POINTER(Dims), C.POINTER(C.c_int64)]),
     "tlsan_stage_batch_host": (C.c_int, [C.POINTER(Dims)] + [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32,
                                                                                   C.c_void_p]),
+    "tlsan_stage_packed": (C.c_int, [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "tlsan_collate": (C.c_int, [C.POINTER(Dataset), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int64, C.c_void_p]),
     "tlsan_ds_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

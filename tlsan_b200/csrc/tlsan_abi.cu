@@ -88,11 +88,13 @@ static bool g_prof_overlap = false;   // the recorded steps ran the sort on the 
 // last kernel of the presort); ev_part: balanced partition ready (long-term forward)
 struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr, ev_seg = nullptr, ev_part = nullptr; bool valid = false; };
 static Presort g_presort[32];
-static Presort* presort_slot(char* ws, bool create) {
+// `avoid`: the entry the calling step is consuming -- its events are still to be waited on by kernels that step
+// enqueues later (row reduce -> ev_seg), so it must not be handed to another workspace and re-recorded
+static Presort* presort_slot(char* ws, bool create, const Presort* avoid = nullptr) {
   for (auto& e : g_presort) if (e.ws == ws) return &e;
   if (!create) return nullptr;
   for (auto& e : g_presort)
-    if (!e.valid) {
+    if (!e.valid && &e != avoid) {
       if (!e.ev && (cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess ||
                     cudaEventCreateWithFlags(&e.ev_seg, cudaEventDisableTiming) != cudaSuccess ||
                     cudaEventCreateWithFlags(&e.ev_part, cudaEventDisableTiming) != cudaSuccess))
@@ -103,7 +105,7 @@ static Presort* presort_slot(char* ws, bool create) {
   // every slot holds an announced-but-never-consumed presort (callers that dropped their model): one whose
   // kernels have finished can no longer race with anything and may be recycled
   for (auto& e : g_presort)
-    if (cudaEventQuery(e.ev_seg) == cudaSuccess && cudaEventQuery(e.ev_part) == cudaSuccess) {
+    if (&e != avoid && cudaEventQuery(e.ev_seg) == cudaSuccess && cudaEventQuery(e.ev_part) == cudaSuccess) {
       e.ws = ws;
       e.valid = false;
       return &e;
@@ -163,10 +165,10 @@ static int env_int(const char* name, int dflt) {      // A/B switches, read on e
   return e ? atoi(e) : dflt;
 }
 
-bool tlsan_pdl_enabled() {
+int tlsan_pdl_level() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TLSAN_PDL"); v = e ? (atoi(e) != 0) : 1; }
-  return v != 0;
+  if (v < 0) { const char* e = getenv("TLSAN_PDL"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 extern "C" {
@@ -339,7 +341,8 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     REQUIRE(next->workspace_bytes >= wn.total + 256, TLSAN_E_WORKSPACE, "next workspace too small");
     char* wsn = ws_base(next->workspace);
     REQUIRE(wsn != ws, TLSAN_E_UNSUPPORTED, "the next batch needs its own workspace");
-    Presort* ps = presort_slot(wsn, true);
+    Presort* consumed = ps;
+    Presort* ps = presort_slot(wsn, true, consumed);
     REQUIRE(ps != nullptr, TLSAN_E_UNSUPPORTED, "too many presorted workspaces in flight");
     const int32_t* unused = nullptr;
     if (fused_impl() < 2) TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));   // else recorded inside the chain (presort_at)

@@ -53,17 +53,22 @@ static inline size_t tlsan_align_up(size_t x, size_t a) { return (x + a - 1) / a
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
-bool tlsan_pdl_enabled();
+int tlsan_pdl_level();     // TLSAN_PDL: 0 off, 1 = the update-phase kernels (reduce, fix-up, finalize, apply), 2 = every kernel of the step
 template <typename... KArgs, typename... Args>
-static inline cudaError_t tlsan_launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                         Args... args) {
+static inline cudaError_t tlsan_launch_kl(int level, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                          cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = tlsan_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = tlsan_pdl_level() >= level ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tlsan_launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+  return tlsan_launch_kl(2, kern, grid, block, smem, st, args...);
 }
 
 // Workspace carve-up (byte offsets from a 256-B aligned base).

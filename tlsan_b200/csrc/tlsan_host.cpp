@@ -207,7 +207,7 @@ int stage_compact_impl(const tlsan_dims_t* d, const IdT* u, const IdT* i, const 
                        const IdT* hist_i, const IdT* hist_i_new, const float* hist_t, const IdT* sl,
                        const IdT* sl_new, const IdT* c, int32_t* out, int32_t* dev, int64_t words,
                        int32_t validate, int32_t nthreads, cudaStream_t st) {
-  if (!d || !u || !i || !hist_i || !hist_i_new || !hist_t || !sl || !sl_new || !c || !out || !dev || (!i2 && !y)) {
+  if (!d || !u || !i || !hist_i || !hist_i_new || !hist_t || !sl || !sl_new || !c || !out || (!i2 && !y)) {
     tlsan_set_error("tlsan_stage_batch_host: NULL argument");
     return TLSAN_E_NULL;
   }
@@ -228,7 +228,7 @@ int stage_compact_impl(const tlsan_dims_t* d, const IdT* u, const IdT* i, const 
   cudaError_t cerr = cudaSuccess;
   int64_t total_new = 0;
   auto copy_words = [&](int64_t lo, int64_t hi) {
-    if (hi > lo && cerr == cudaSuccess)
+    if (dev && hi > lo && cerr == cudaSuccess)          // dev == NULL: pack only (tlsan_stage_packed copies later)
       cerr = cudaMemcpyAsync(dev + lo, out + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, st);
   };
   auto arrive = [&](int ph) { phase_done[ph].fetch_add(1, std::memory_order_release); };
@@ -287,8 +287,10 @@ int stage_compact_impl(const tlsan_dims_t* d, const IdT* u, const IdT* i, const 
     return TLSAN_E_CUDA;
   }
   // hist_i_new [B][S] <- (sl_new, offsets, items), zero padded like input.py:50-51
-  int rc = tlsan_launch_expand_sessions(dev + Y.o_sn, dev + o_off, dev + o_rag, dev + Y.o_hn, (int)B, (int)S, st);
-  if (rc) return rc;
+  if (dev) {
+    int rc = tlsan_launch_expand_sessions(dev + Y.o_sn, dev + o_off, dev + o_rag, dev + Y.o_hn, (int)B, (int)S, st);
+    if (rc) return rc;
+  }
   if (validate) {
     PerThread A;
     for (int t = 0; t < T; ++t) {
@@ -320,6 +322,33 @@ extern "C" int tlsan_stage_words(const tlsan_dims_t* d, int64_t* words) {
   const Layout Y = layout_of(d);
   *words = Y.total + up4(Y.B) + up4(Y.B * Y.S);
   return TLSAN_OK;
+}
+
+// A batch that already sits in page-locked memory in the staging layout (the packed feed of tlsan_b200.input: the
+// batcher writes its arrays straight into that buffer): two host->device copies -- everything in front of the padded
+// session matrix, everything behind it up to the last ragged item -- and the session expansion.  No host pass at all.
+extern "C" int tlsan_stage_packed(const tlsan_dims_t* d, const int32_t* pinned, int32_t* dev, int64_t words,
+                                  int64_t n_new, void* stream) {
+  if (!d || !pinned || !dev) {
+    tlsan_set_error("tlsan_stage_packed: NULL argument");
+    return TLSAN_E_NULL;
+  }
+  const Layout Y = layout_of(d);
+  const int64_t o_off = Y.total, o_rag = o_off + up4(Y.B), need = o_rag + up4(Y.B * Y.S);
+  if (words < need || n_new < 0 || n_new > Y.B * Y.S) {
+    tlsan_set_error("tlsan_stage_packed: buffers hold %lld words, need %lld; n_new %lld", (long long)words,
+                    (long long)need, (long long)n_new);
+    return TLSAN_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(dev, pinned, (size_t)Y.o_hn * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(dev + Y.o_ht, pinned + Y.o_ht, (size_t)(o_rag + n_new - Y.o_ht) * 4, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    tlsan_set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    return TLSAN_E_CUDA;
+  }
+  return tlsan_launch_expand_sessions(dev + Y.o_sn, dev + o_off, dev + o_rag, dev + Y.o_hn, (int)Y.B, (int)Y.S, st);
 }
 
 extern "C" int tlsan_pack_batch_host(const tlsan_dims_t* d, const int64_t* u, const int64_t* i, const int64_t* i2,

@@ -550,17 +550,17 @@ int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, c
     const int* keys = reinterpret_cast<const int*>(ws + (sorted_vals == reinterpret_cast<const int32_t*>(ws + w.vals_b) ? w.keys_b : w.keys_a));
     float* head = reinterpret_cast<float*>(ws + w.rpart);
     float* tail = head + (size_t)TLSAN_MAX_GRID * 8 * RR_PSTRIDE;
-    tlsan_launch_k(k_row_reduce_bal, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off, keys,
+    tlsan_launch_kl(1, k_row_reduce_bal, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off, keys,
                    (const int*)sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
                    reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
                    g_u, head, tail);
     TLSAN_CHECK_LAUNCH("k_row_reduce_bal");
-    tlsan_launch_k(k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
+    tlsan_launch_kl(1, k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
                    (const float*)head, (const float*)tail, g_i, g_b);
     TLSAN_CHECK_LAUNCH("k_row_fix");
     return TLSAN_OK;
   }
-  tlsan_launch_k(k_row_reduce, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off,
+  tlsan_launch_kl(1, k_row_reduce, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off,
                  sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
                  reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
                  g_u);
@@ -605,17 +605,17 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
     if (rc) return rc;
   }
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  tlsan_launch_k(k_finalize2, dim3(1), dim3(1024), 0, st, dgrad, (const float*)tsq, ntsq, (const float*)nullptr, 0, invB,
+  tlsan_launch_kl(1, k_finalize2, dim3(1), dim3(1024), 0, st, dgrad, (const float*)tsq, ntsq, (const float*)nullptr, 0, invB,
                  lr, reg, clip, p.dense, stats, opt);
   TLSAN_CHECK_LAUNCH("k_finalize2");
   const long long n4 = (long long)d.NI * 8 + (long long)d.NU * 8 + (long long)d.NU * d.L + d.NI;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tlsan_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  tlsan_launch_k(k_apply_rows, dim3((unsigned)blocks), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert,
+  tlsan_launch_kl(1, k_apply_rows, dim3((unsigned)blocks), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert,
                  p.item_b, g_i, g_b, g_u, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_rows");
-  tlsan_launch_k(k_apply_cate, dim3(d.NC), dim3(256), 0, st, d.NI, p.emb, g_i, (const int*)p.cate_off,
+  tlsan_launch_kl(1, k_apply_cate, dim3(d.NC), dim3(256), 0, st, d.NI, p.emb, g_i, (const int*)p.cate_off,
                  (const int*)p.cate_items, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_cate");
   return TLSAN_OK;

@@ -26,6 +26,7 @@ import torch
 
 from . import _lib
 from ._lib import OFF, STAT, Batch, Dims, Next, Params, check
+from .input import PackedBatch
 
 _L = "all/long_term/num_blocks0_0/long_term_layer/feature_wise_attention1/"
 _S = "all/short_term/num_blocks1_0/short_term_layer/feature_wise_attention2/"
@@ -305,6 +306,8 @@ class Model(object):
         """Pack the input.py 9-tuple into pinned memory (tlsan_pack_batch_host: multi-threaded
         int64->int32 cast + id range checks) and copy it to the device (one H2D).  `out` (optional): a device
         int32 tensor to stage into instead of a fresh allocation (the double-buffered feed of `prefetch`)."""
+        if isinstance(batch, PackedBatch):
+            return self._stage_packed(batch, is_test, out)
         B = len(batch[0])
         S = max(int(np.shape(batch[4])[1]), 1)
         if np.shape(batch[3])[1] != self.L:
@@ -330,6 +333,30 @@ class Model(object):
         self.last_h2d_bytes = 4 * (total - (B * S + 3) // 4 * 4 + B + n_new)
         return DeviceBatch(dev, B, self.L, S, offs, is_test,
                            raw_gaps=np.issubdtype(np.asarray(batch[5]).dtype, np.integer))
+
+    def _stage_packed(self, pb, is_test, out=None):
+        """The packed feed (tlsan_b200.input.PackedBatch): the batch already sits in page-locked memory in the staging
+        layout, so the feed is two DMA copies and the session expansion (tlsan_stage_packed) -- no cast, no pack.  The
+        range checks of the feed (tf.gather's InvalidArgumentError) compare the id maxima the producer vouches for with
+        this model's tables."""
+        if pb.L != self.L:
+            raise ValueError("batch was built with Ls=%d but the model with Ls=%d" % (pb.L, self.L))
+        if pb.is_test != bool(is_test):
+            raise ValueError("PackedBatch.is_test does not match the call (train batches carry labels, test batches a second item)")
+        if self.validate:
+            for name, mx, n in (("u", pb.id_max[0], self.NU), ("item ids", pb.id_max[1], self.NI), ("c", pb.id_max[2], self.NC)):
+                if mx >= n:
+                    raise IndexError("batch field %s out of range [0, %d): the producer's largest id is %d" % (name, n, mx))
+        dims = self._dims(pb.B, pb.S)
+        words = pb.words
+        dev = out[:words] if out is not None else torch.empty(words, dtype=torch.int32, device=self.device)
+        check(self._lib.tlsan_stage_packed(C.byref(dims), pb.buf.ctypes.data, dev.data_ptr(), words, pb.n_new, self._stream()))
+        pb.copied = torch.cuda.Event()
+        pb.copied.record(torch.cuda.current_stream(self.device))
+        o = pb.offs
+        self.last_h2d_bytes = 4 * (o["hist_i_new"] + o["new_items"] + pb.n_new - o["hist_t"])
+        offs, _ = _pack_offsets(pb.B, self.L, pb.S)
+        return DeviceBatch(dev, pb.B, self.L, pb.S, offs, is_test)
 
     # ------------------------------------------------------------------ training
     def train_staged(self, db, lr, global_batch=None, next_db=None):
@@ -467,7 +494,10 @@ class Model(object):
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
             self._feed_ring, self._feed_i = [], 0
-        B, S = len(batch[0]), max(int(np.shape(batch[4])[1]), 1)
+        if isinstance(batch, PackedBatch):
+            B, S = batch.B, batch.S
+        else:
+            B, S = len(batch[0]), max(int(np.shape(batch[4])[1]), 1)
         words = C.c_int64()
         check(self._lib.tlsan_stage_words(C.byref(self._dims(B, S)), C.byref(words)))
         words = int(words.value)
