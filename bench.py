@@ -524,46 +524,44 @@ def main():
                  "unit": "samples/s", "clocks": clk_sus}
 
     # ---------------- end to end through Model.train with host batches (batch k+1 staged while step k runs)
-    for w in range(3):
-        model.train(None, host_batches[w % nres], 1.0, global_batch=Bg)
-    ctx.barrier()
     e2e_steps = max(200, args.steps)
-    t0 = time.perf_counter()
-    model.prefetch(host_batches[0])
-    for k in range(e2e_steps):
-        model.train(None, host_batches[k % nres], 1.0, global_batch=Bg, prefetch=host_batches[(k + 1) % nres])
-    torch.cuda.synchronize()
-    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
-    model.drop_prefetch()
+
+    def e2e_loop(batches, lazy):
+        """K calls of Model.train(sess, batch, lr, prefetch=next batch); every step's loss is read back (D2H) inside the
+        timed region -- right after the call (lazy=False), or after the NEXT call has been enqueued (lazy=True)."""
+        for w in range(3):
+            model.train(None, batches[w % nres], 1.0, global_batch=Bg)
+        model.drop_prefetch()
+        torch.cuda.synchronize()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        model.prefetch(batches[0])
+        total, pending = 0.0, None
+        for k in range(e2e_steps):
+            cur = model.train(None, batches[k % nres], 1.0, global_batch=Bg, prefetch=batches[(k + 1) % nres], lazy_loss=lazy)
+            if pending is not None:
+                total += float(pending)
+            pending = cur
+        total += float(pending)
+        torch.cuda.synchronize()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        model.drop_prefetch()
+        assert np.isfinite(total)
+        return dt
+
+    e2e_s = e2e_loop(host_batches, False)
     h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
     # the same loop fed with int32 batches (tlsan_b200.input index_dtype=np.int32): no 64 -> 32 bit narrowing pass
     hb32 = [tuple(np.ascontiguousarray(f, dtype=np.int32) if n not in (2, 5) else f for n, f in enumerate(b))
             for b in host_batches]
-    for w in range(2):
-        model.train(None, hb32[w % nres], 1.0, global_batch=Bg)
-    ctx.barrier()
-    t0 = time.perf_counter()
-    model.prefetch(hb32[0])
-    for k in range(e2e_steps):
-        model.train(None, hb32[k % nres], 1.0, global_batch=Bg, prefetch=hb32[(k + 1) % nres])
-    torch.cuda.synchronize()
-    e2e32_s = ctx.max_over_ranks(time.perf_counter() - t0)
-    model.drop_prefetch()
+    e2e32_s = e2e_loop(hb32, False)
     del hb32
     # the packed feed: batches as DataInput(..., packed=True) yields them -- already in page-locked memory in the
     # staging layout -- so the timed region holds the H2D copy from pinned memory, the step and the loss read-back
     from tlsan_b200.input import PackedBatch
     pk = [PackedBatch.from_tuple(b) for b in host_batches]
-    for w in range(3):
-        model.train(None, pk[w % nres], 1.0, global_batch=Bg)
-    ctx.barrier()
-    t0 = time.perf_counter()
-    model.prefetch(pk[0])
-    for k in range(e2e_steps):
-        model.train(None, pk[k % nres], 1.0, global_batch=Bg, prefetch=pk[(k + 1) % nres])
-    torch.cuda.synchronize()
-    e2ep_s = ctx.max_over_ranks(time.perf_counter() - t0)
-    model.drop_prefetch()
+    e2ep_sync_s = e2e_loop(pk, False)
+    e2ep_s = e2e_loop(pk, True)
     h2d_p = model.last_h2d_bytes
     del pk
 
@@ -688,13 +686,17 @@ def main():
         "config": workload_config(args, B),
         "e2e": {"value": e2e_steps * Bg / e2ep_s, "unit": "samples/s", "h2d_bytes_per_step": h2d_p,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2ep_s / e2e_steps,
-                "how": "Model.train(sess, batch, lr, prefetch=next batch) with the batches tlsan_b200.input.DataInput("
-                       "..., packed=True) yields: PackedBatch = the reference 9-tuple's fields in ONE page-locked int32 "
-                       "buffer in the staging layout; per step: H2D from pinned memory (batch k+1's copy overlaps step "
-                       "k) + session expansion + train step + loss read-back",
+                "how": "Model.train(sess, batch, lr, prefetch=next batch, lazy_loss=True) with the batches "
+                       "tlsan_b200.input.DataInput(..., packed=True) yields: PackedBatch = the reference 9-tuple's fields "
+                       "in ONE page-locked int32 buffer in the staging layout; per step: H2D from pinned memory (batch "
+                       "k+1's copy and occurrence sort overlap step k) + session expansion + train step + 4-byte loss "
+                       "read-back, every loss read by the host one call later (double-buffered loop)",
+                "sync_loss": {"value": e2e_steps * Bg / e2ep_sync_s, "ms_per_step": 1e3 * e2ep_sync_s / e2e_steps,
+                              "what": "same packed feed, loss read synchronously inside every call (the reference's "
+                                      "`loss = model.train(...)`): the GPU idles while the host enqueues the next step"},
                 "tuple_int64_feed": {"value": e2e_steps * Bg / e2e_s, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                                      "h2d_bytes_per_step": h2d,
-                                     "what": "same loop fed with the reference's own 9-tuples of int64 numpy arrays "
+                                     "what": "synchronous loop fed with the reference's own 9-tuples of int64 numpy arrays "
                                              "(TLSAN/input.py:54): adds the multi-threaded int64->int32 cast + range "
                                              "checks + pack into pinned memory per step (host-memory-bound)"},
                 "int32_feed": {"value": e2e_steps * Bg / e2e32_s, "ms_per_step": 1e3 * e2e32_s / e2e_steps,

@@ -223,6 +223,8 @@ typedef struct {
   const tlsan_batch_t* batch;
   void* workspace;
   size_t workspace_bytes;
+  void* ready_event;   /* optional cudaEvent_t: the next batch's buffer is complete once it fires (its H2D copy on another
+                        * stream); the presort waits for it, the current step does not.  NULL: the batch is ready */
 } tlsan_next_t;
 int tlsan_train_step_pipelined(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b,
                                const tlsan_next_t* next, float lr, float reg, float clip_norm, void* workspace,

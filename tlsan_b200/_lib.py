@@ -26,7 +26,7 @@ class Batch(C.Structure):
 
 class Next(C.Structure):
     _fields_ = [("dims", C.POINTER(Dims)), ("batch", C.POINTER(Batch)), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t)]
+                ("workspace_bytes", C.c_size_t), ("ready_event", C.c_void_p)]
 
 
 class Opt(C.Structure):

@@ -347,10 +347,14 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     const int32_t* unused = nullptr;
     if (fused_impl() < 2) TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));   // else recorded inside the chain (presort_at)
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
+    if (next->ready_event) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, (cudaEvent_t)next->ready_event, 0));
     if (pf) {     // the consuming (presorted) step runs its forward kernel with 3 CTAs per SM
       // two small latency-bound kernels: on their own stream they do not lengthen the sort's chain of launches
       cudaStream_t pst = env_int("TLSAN_PART_STREAM", 2) == 3 ? side->st3 : side->st2;
-      if (pst != side->st2) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, side->fork2, 0));
+      if (pst != side->st2) {
+        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, side->fork2, 0));
+        if (next->ready_event) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, (cudaEvent_t)next->ready_event, 0));
+      }
       if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, pst))) return rc;
       TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, pst));
     }

@@ -76,6 +76,25 @@ class _IncrOp:
         return self._var.value
 
 
+class LazyLoss(object):
+    """Loss of a step whose read-back is still in flight; ``float(x)`` waits for it.  (At most 8 may be pending.)"""
+
+    def __init__(self, host, ev):
+        self._host, self._ev, self._v = host, ev, None
+
+    def __float__(self):
+        if self._v is None:
+            self._ev.synchronize()
+            self._v = float(self._host[0])
+        return self._v
+
+    def __radd__(self, other):
+        return other + float(self)
+
+    def __add__(self, other):
+        return float(self) + other
+
+
 class DeviceBatch:
     """A batch resident in HBM: one packed int32 buffer + the C struct pointing into it."""
 
@@ -359,7 +378,7 @@ class Model(object):
         return DeviceBatch(dev, pb.B, self.L, pb.S, offs, is_test)
 
     # ------------------------------------------------------------------ training
-    def train_staged(self, db, lr, global_batch=None, next_db=None):
+    def train_staged(self, db, lr, global_batch=None, next_db=None, next_ready=None):
         """One optimiser step on a device-resident batch; returns the device stats tensor
         (index with ``tlsan_b200._lib.STAT``) without synchronising.  ``next_db`` (optional) is the batch the
         NEXT call will train on: its occurrence sort is then enqueued behind this step's backward kernels
@@ -385,8 +404,10 @@ class Model(object):
         if next_db is not None:
             ndims = self._dims(next_db.B, next_db.S, nBg)
             nws = self._workspace(ndims, 1 - slot)
+            # next_ready: torch.cuda.Event after which next_db's buffer is complete (its H2D copy runs on another stream)
             nxt = Next(dims=C.pointer(ndims), batch=C.pointer(next_db.c), workspace=nws.data_ptr(),
-                       workspace_bytes=nws.numel())
+                       workspace_bytes=nws.numel(),
+                       ready_event=next_ready.cuda_event if next_ready is not None else None)
         nref = C.byref(nxt) if nxt is not None else None
         if self.optimizer != "sgd":
             # gradients into the flat buffer (summed over the ranks when data parallel), then the fused
@@ -528,23 +549,48 @@ class Model(object):
             return pf[2], pf[4]
         return self.stage_batch(batch, is_test=is_test), None
 
-    def train(self, sess, batch, lr, add_summary=False, global_batch=None, prefetch=None):
+    def train(self, sess, batch, lr, add_summary=False, global_batch=None, prefetch=None, lazy_loss=False):
         """Reference Model.train (model.py:208-234): feed the 9-tuple, run [loss, train_op].
         Data parallel: `batch` is this rank's block of the global batch; `global_batch` = its total row count
         (found with one small all_reduce when omitted).  `prefetch` (optional) = the batch of the NEXT call: it is
-        packed and copied to the device while this step's kernels run (double-buffered feed)."""
+        staged on the copy stream while this step's kernels run (double-buffered feed) and its occurrence sort is
+        enqueued behind this step's backward kernels.  `lazy_loss=True` returns a ``LazyLoss`` (the 4-byte read-back is
+        enqueued, ``float()`` waits for it): a loop that reads loss k after calling train for batch k+1 keeps the GPU
+        busy across the read-back."""
         db, slot = self._staged(batch, False)
-        stats = self.train_staged(db, float(lr), global_batch=global_batch)
+        nxt_db = nxt_ev = None
+        # a PackedBatch costs the host two memcpy calls: stage it FIRST, so that this step can name it and its
+        # occurrence sort runs behind this step's backward kernels.  A 9-tuple costs a ~1 ms host pass: enqueue this
+        # step first and pack while the GPU works.
+        early = prefetch is not None and isinstance(prefetch, PackedBatch)
+        if early:
+            self.prefetch(prefetch)
+            if not (self.world > 1 and global_batch is None):   # (the next step's global row count must be known)
+                nxt_db, nxt_ev = self._prefetched[2], self._prefetched[3]
+        stats = self.train_staged(db, float(lr), global_batch=global_batch, next_db=nxt_db, next_ready=nxt_ev)
         if slot is not None:                  # its staging buffer may be refilled once this step has run
             slot[1] = torch.cuda.Event()
             slot[1].record(torch.cuda.current_stream(self.device))
-        if prefetch is not None:
+        if prefetch is not None and not early:
             self.prefetch(prefetch)
-        loss = float(stats[STAT["loss"]].item())
         self.last_d2h_bytes = 4
+        if lazy_loss and not (add_summary and self.train_writer is not None):
+            return self._lazy(stats)
+        loss = float(stats[STAT["loss"]].item())
         if add_summary and self.train_writer is not None:
             self._write_train_summary(db, loss, stats)
         return loss
+
+    def _lazy(self, stats):
+        if not hasattr(self, "_loss_ring"):
+            self._loss_ring = [torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(8)]
+            self._loss_i = 0
+        host = self._loss_ring[self._loss_i % 8]
+        self._loss_i += 1
+        host.copy_(stats[STAT["loss"]:STAT["loss"] + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return LazyLoss(host, ev)
 
     def _write_train_summary(self, db, loss, stats):
         """self.train_summary of model.py:174-183,228-230: five variable histograms, the histogram of the batch's
