@@ -128,7 +128,7 @@ EXPORTS = tuple(_SIGS)
 PHASES = ("sort", "long_fwd", "dense_fwd", "short", "dense_bwd", "bwd_long", "reduce", "apply")
 # kernel that dominates each phase (names as ncu prints them, default `pf` formulation)
 PHASE_KERNEL = {"long_fwd": "k_pf_long<1>", "short": "k_pf_short", "bwd_long": "k_pf_long<3>",
-                "dense_fwd": "k_dense_fwd_mma", "dense_bwd": "k_dense_bwd_mma", "reduce": "k_row_reduce"}
+                "dense_fwd": "k_dense_fwd_mma", "dense_bwd": "k_dense_bwd_mma", "reduce": "k_row_reduce_bal"}
 
 
 def _drain():

@@ -52,7 +52,7 @@ static bool use_mma() { return fused_impl() >= 1; }
 // The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
 // onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
 // events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
-struct SideStream { cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
+struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
 static SideStream* side_stream() {
   static SideStream per_dev[64];
   static int enabled = -1;
@@ -69,7 +69,6 @@ static SideStream* side_stream() {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, lo) != cudaSuccess ||   // presort: fills gaps
-        cudaStreamCreateWithPriority(&s.st3, cudaStreamNonBlocking, lo) != cudaSuccess ||   // its partition, beside it
         cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.part, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -153,21 +152,9 @@ static int check_batch(const tlsan_batch_t* b, bool train, int ncand) {
   return TLSAN_OK;
 }
 
-// where in step k the presort of batch k+1 is released (see tlsan_launch_fwd_bwd_async): TLSAN_PRESORT_AT=1..5
-static int presort_at() {
-  static int v = 0;
-  if (!v) { const char* e = getenv("TLSAN_PRESORT_AT"); v = e ? atoi(e) : 5; if (v < 1 || v > 5) v = 5; }
-  return v;
-}
-
-static int env_int(const char* name, int dflt) {      // A/B switches, read on every call (host side, cheap)
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 int tlsan_pdl_level() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TLSAN_PDL"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char* e = getenv("TLSAN_PDL"); v = e ? atoi(e) : 1; }
   return v;
 }
 
@@ -326,8 +313,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
   int grid_a = 0, grid_b = 0, grid_c = 0;
   if (fused_impl() >= 2)
     rc = tlsan_launch_fwd_bwd_async(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, fused_impl() - 2, sorted,
-                                    part_ready, presorted, long_ctas, (next && side) ? side->fork2 : nullptr,
-                                    presort_at(), st);
+                                    part_ready, presorted, long_ctas, st);
   else if (fused_impl() == 1)
     rc = tlsan_launch_fwd_bwd_mma(*dims, *p, *b, w, ws, &grid_a, &grid_b, &grid_c, sorted, long_ctas, st);
   else rc = tlsan_launch_fwd_bwd(*dims, *p, *b, w, ws, &grid_a, &grid_b, st);
@@ -345,18 +331,14 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     Presort* ps = presort_slot(wsn, true, consumed);
     REQUIRE(ps != nullptr, TLSAN_E_UNSUPPORTED, "too many presorted workspaces in flight");
     const int32_t* unused = nullptr;
-    if (fused_impl() < 2) TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));   // else recorded inside the chain (presort_at)
+    // released here, behind the long-term backward: measured best of the five possible points of the chain (an
+    // earlier release only moves the sort's SM time from the reduce / update phase into the backward kernels)
+    TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
     if (next->ready_event) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, (cudaEvent_t)next->ready_event, 0));
     if (pf) {     // the consuming (presorted) step runs its forward kernel with 3 CTAs per SM
-      // two small latency-bound kernels: on their own stream they do not lengthen the sort's chain of launches
-      cudaStream_t pst = env_int("TLSAN_PART_STREAM", 2) == 3 ? side->st3 : side->st2;
-      if (pst != side->st2) {
-        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, side->fork2, 0));
-        if (next->ready_event) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(pst, (cudaEvent_t)next->ready_event, 0));
-      }
-      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, pst))) return rc;
-      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, pst));
+      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, side->st2))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, side->st2));
     }
     // ps->ev is recorded inside, before the segment-bounds kernel
     if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, ps->ev, side->st2))) return rc;
@@ -367,14 +349,10 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     // the fixed-order sum of the per-CTA partials and the segmented row reduce are independent: side by side
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
-    // TLSAN_RR_HI=1: the row reduce takes the HIGH-priority side stream (its CTAs win over the next batch's presort,
-    // which runs at the caller stream's priority), the small partial-sum kernel the caller's
-    const bool rr_hi = env_int("TLSAN_RR_HI", 0) != 0;
-    cudaStream_t s_fin = rr_hi ? st : side->st, s_red = rr_hi ? side->st : st;
-    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, s_fin))) return rc;
-    if (seg_ready) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(s_red, seg_ready, 0));
-    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, s_red);
+    if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, side->st))) return rc;
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
+    if (seg_ready) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, seg_ready, 0));
+    rc = tlsan_launch_row_reduce(*dims, w, ws, sorted_vals, flat + w.f_gi, flat + w.f_gb, flat + w.f_gu, st);
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   } else {
     if ((rc = tlsan_launch_finalize1(w, ws, grid_a, grid_b, grid_c, flat + w.f_dgrad, st))) return rc;

@@ -157,7 +157,7 @@ int tlsan_launch_fwd_bwd_mma(const tlsan_dims_t& d, const tlsan_params_t& p, con
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
                                cudaEvent_t sorted, cudaEvent_t part_ready, bool part_early, int long_ctas,
-                               cudaEvent_t fork_ev, int fork_at, cudaStream_t st);
+                               cudaStream_t st);
 int tlsan_launch_partition_batch(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b, int fwd_ctas,
                                  void* part, cudaStream_t st);
 int tlsan_overlap_ctas();

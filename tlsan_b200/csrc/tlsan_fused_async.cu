@@ -407,10 +407,7 @@ int tlsan_launch_bwd_long_pf(const FArgs& a, const void* meta, const void* part,
 int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, const tlsan_batch_t& b,
                                const TlsanWs& w, char* ws, int* grid_a, int* grid_b, int* grid_c, int variant,
                                cudaEvent_t sorted, cudaEvent_t part_ready, bool part_early, int long_ctas,
-                               cudaEvent_t fork_ev, int fork_at, cudaStream_t st) {
-  // fork_ev (optional) is recorded after kernel number fork_at of the chain (1 long forward, 2 dense forward,
-  // 3 short-term, 4 dense backward, 5 long backward): the point the NEXT batch's presort is released at
-  auto fork = [&](int at) { if (fork_ev && fork_at == at) cudaEventRecord(fork_ev, st); };
+                               cudaStream_t st) {
   const bool hybrid = variant == 1;
   FArgs a = tlsan_make_fargs(d, p, b);
   a.rows_i = reinterpret_cast<float*>(ws + w.rows_i);
@@ -435,24 +432,19 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
                          : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_LONG_FWD, st);
-  fork(1);
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
-  fork(2);
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
   if ((rc = variant == 2 ? tlsan_launch_short_pf(a, smeta, sscal, part, grid_a, st) : launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);
-  fork(3);
   if ((rc = tlsan_launch_dense_bwd(p.dense, a.scratch, d.B, reinterpret_cast<float*>(ws + w.part_c), grid_c, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_DENSE_BWD, st);
-  fork(4);
   a.part = reinterpret_cast<float*>(ws + w.part_b);
   if ((rc = variant == 2 ? tlsan_launch_bwd_long_pf(a, meta, part, grid_b, st)
                          : hybrid ? tlsan_launch_bwd_long_mma(a, grid_b, st) : launch_async<3>(a, grid_b, st)))
     return rc;
   tlsan_profile_mark(TLSAN_PHASE_BWD_LONG, st);
-  fork(5);
   return TLSAN_OK;
 }

@@ -10,90 +10,8 @@
 #include <string.h>
 #include "tlsan_common.cuh"
 
-// ------------------------------------------------------------------ segmented reduce
-// Persistent warps stride over the rows of the unified row space; the occurrences of a row are
-// visited in sorted (stable) order.  Item / category rows: each half-warp reads one 256-B
-// gradient row per step (16 lanes x float4), even occurrences in lanes 0-15, odd ones in lanes
-// 16-31, 8 steps (16 rows) in flight; the two half-sums are combined at the end -- a fixed
-// order, independent of timing.  The segment bounds of the row after next and the occurrence
-// list of the next row are fetched while the current row is being summed.
-__global__ void __launch_bounds__(256, 4) k_row_reduce(int NI, int NC, int NU, int L, int S, int spsh, int PU,
-                                                    const int* __restrict__ seg_off, const int* __restrict__ vals,
-                                                    const float* __restrict__ rows_i,
-                                                    const float* __restrict__ rows_u,
-                                                    const float* __restrict__ gscal, float* __restrict__ g_i,
-                                                    float* __restrict__ g_b, float* __restrict__ g_u) {
-  const int lane = threadIdx.x & 31;
-  const int NR = NI + NC + NU;
-  const int W = gridDim.x * 8;
-  const int smask = (1 << spsh) - 1;
-  const int hw = lane >> 4, q = lane & 15;
-  int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  int2 seg_c = r < NR ? make_int2(seg_off[r], seg_off[r + 1]) : make_int2(0, 0);
-  int2 seg_n = r + W < NR ? make_int2(seg_off[r + W], seg_off[r + W + 1]) : make_int2(0, 0);
-  int mine_c = seg_c.x + lane < seg_c.y ? vals[seg_c.x + lane] : 0;
-  pdl_wait();                                       // gradient rows of the backward kernels (the sort finished long ago)
-  pdl_trigger();
-  for (; r < NR; r += W) {
-    const int2 seg_nn = r + 2 * W < NR ? make_int2(seg_off[r + 2 * W], seg_off[r + 2 * W + 1]) : make_int2(0, 0);
-    const int mine_n = seg_n.x + lane < seg_n.y ? vals[seg_n.x + lane] : 0;
-    const int lo = seg_c.x, hi = seg_c.y;
-    if (r < NI + NC) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float accb = 0.f;
-      for (int base = lo; base < hi; base += 32) {
-        const int mine = base == lo ? mine_c : (base + lane < hi ? vals[base + lane] : 0);
-        const int cnt = min(32, hi - base);
-        for (int k0 = 0; k0 < cnt; k0 += 16) {
-          float4 v[8];
-          float gb[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int kk = k0 + 2 * k + hw;
-            const int occ = __shfl_sync(0xffffffffu, mine, kk & 31);
-            const int b = occ >> spsh, j = occ & smask;
-            const bool on = kk < cnt;
-            v[k] = on ? __ldg(reinterpret_cast<const float4*>(rows_i + (size_t)(base + kk) * 64) + q)   // sorted rows
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            gb[k] = (on && j == L + S && q == 0) ? __ldg(gscal + b) : 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
-            accb += gb[k];
-          }
-        }
-      }
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-      accb += __shfl_xor_sync(0xffffffffu, accb, 16);
-      if (hw == 0) reinterpret_cast<float4*>(g_i + (size_t)r * 64)[q] = acc;
-      if (r < NI && lane == 0) g_b[r] = accb;
-    } else {
-      const int u = r - NI - NC;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int base = lo; base < hi; base += 32) {
-        const int mine = base == lo ? mine_c : (base + lane < hi ? vals[base + lane] : 0);
-        const int cnt = min(32, hi - base);
-        for (int k = 0; k < cnt; ++k) {
-          const int occ = __shfl_sync(0xffffffffu, mine, k);
-          const int b = occ >> spsh;
-          const float* src = rows_u + (size_t)b * PU;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-            if (lane + 32 * qq < PU) acc[qq] += __ldg(src + lane + 32 * qq);
-        }
-      }
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
-        if (lane + 32 * qq < PU) g_u[(size_t)u * PU + lane + 32 * qq] = acc[qq];
-    }
-    seg_c = seg_n; seg_n = seg_nn; mine_c = mine_n;
-  }
-}
-
-// ------------------------------------------------------------------ balanced segmented reduce (default)
-// The per-row kernel above gives one warp one ROW: with Zipf item popularity (and 15 categories on the Movies-TV shape)
+// ------------------------------------------------------------------ balanced segmented reduce
+// Giving one warp one ROW (round 1) fails on Zipf item popularity (and 15 categories on the Movies-TV shape)
 // a few warps own segments of thousands of occurrences while the rest idle -- ncu: long_scoreboard 74 % at 41 % of the
 // warps active, 3.1 TB/s.  Here the SORTED OCCURRENCE LIST is what is divided: warp w sums positions
 // [w R, (w+1) R) of the item / category part (R = ceil(T / #warps) rounded up to 16, T = seg_off[NI + NC]), 16 rows
@@ -533,38 +451,23 @@ __global__ void __launch_bounds__(256) k_label_rank(int NI, const float* __restr
 }
 
 // ------------------------------------------------------------------ launchers
-static bool row_reduce_balanced() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TLSAN_ROW_REDUCE"); v = !(e && !strcmp(e, "row")); }
-  return v != 0;
-}
-
 int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, const int32_t* sorted_vals,
                             float* g_i, float* g_b, float* g_u, cudaStream_t st) {
-  int rgrid = (w.NR + 7) / 8;
-  if (rgrid > tlsan_num_sms() * 4) rgrid = tlsan_num_sms() * 4;
   const int* seg_off = reinterpret_cast<const int*>(ws + w.seg_off);
-  if (row_reduce_balanced()) {
-    rgrid = tlsan_num_sms() * 4;
-    // the sorted keys sit in the ping-pong buffer of the same parity as the sorted occurrence ids
-    const int* keys = reinterpret_cast<const int*>(ws + (sorted_vals == reinterpret_cast<const int32_t*>(ws + w.vals_b) ? w.keys_b : w.keys_a));
-    float* head = reinterpret_cast<float*>(ws + w.rpart);
-    float* tail = head + (size_t)TLSAN_MAX_GRID * 8 * RR_PSTRIDE;
-    tlsan_launch_kl(1, k_row_reduce_bal, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off, keys,
-                   (const int*)sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
-                   reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
-                   g_u, head, tail);
-    TLSAN_CHECK_LAUNCH("k_row_reduce_bal");
-    tlsan_launch_kl(1, k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
-                   (const float*)head, (const float*)tail, g_i, g_b);
-    TLSAN_CHECK_LAUNCH("k_row_fix");
-    return TLSAN_OK;
-  }
-  tlsan_launch_kl(1, k_row_reduce, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off,
-                 sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
-                 reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
-                 g_u);
-  TLSAN_CHECK_LAUNCH("k_row_reduce");
+  const int rgrid = tlsan_num_sms() * 4;
+  // the sorted keys sit in the ping-pong buffer of the same parity as the sorted occurrence ids
+  const int* keys = reinterpret_cast<const int*>(
+      ws + (sorted_vals == reinterpret_cast<const int32_t*>(ws + w.vals_b) ? w.keys_b : w.keys_a));
+  float* head = reinterpret_cast<float*>(ws + w.rpart);
+  float* tail = head + (size_t)TLSAN_MAX_GRID * 8 * RR_PSTRIDE;
+  tlsan_launch_kl(1, k_row_reduce_bal, dim3(rgrid), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, d.S, w.SPSH, w.PU, seg_off,
+                  keys, (const int*)sorted_vals, reinterpret_cast<const float*>(ws + w.rows_i),
+                  reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
+                  g_u, head, tail);
+  TLSAN_CHECK_LAUNCH("k_row_reduce_bal");
+  tlsan_launch_kl(1, k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
+                  (const float*)head, (const float*)tail, g_i, g_b);
+  TLSAN_CHECK_LAUNCH("k_row_fix");
   return TLSAN_OK;
 }
 
