@@ -199,16 +199,32 @@ __global__ void __launch_bounds__(256) k_part_bounds(const PartArgs p, const uns
                                                      const unsigned int* __restrict__ tot, int nchunk, int cpc) {
   extern __shared__ unsigned int pre[];                          // [2][nchunk + 1] global exclusive chunk prefixes
   __shared__ unsigned int cbase[2][PART_CTAS + 1];
+  __shared__ unsigned int ctot[2 * PART_CTAS];
   const int tid = threadIdx.x;
-  if (tid < 2) {
+  // exclusive scan of the 64 CTA totals of each kind: one load per thread, then every thread sums its predecessors
+  // out of shared memory (a serial loop of dependent global loads here used to be most of this kernel's 20 us)
+  if (tid < 2 * PART_CTAS) ctot[tid] = __ldg(tot + tid);
+  __syncthreads();
+  if (tid < 2 * PART_CTAS) {
+    const int kind = tid / PART_CTAS, c = tid - kind * PART_CTAS;
     unsigned int run = 0;
-    for (int c = 0; c < PART_CTAS; ++c) { cbase[tid][c] = run; run += __ldg(tot + tid * PART_CTAS + c); }
-    cbase[tid][PART_CTAS] = run;
+    for (int q = 0; q < c; ++q) run += ctot[kind * PART_CTAS + q];
+    cbase[kind][c] = run;
+    if (c == PART_CTAS - 1) cbase[kind][PART_CTAS] = run + ctot[tid];
   }
   __syncthreads();
-  for (int e = tid; e < 2 * nchunk; e += 256) {
-    const int kind = e >= nchunk, c = e - kind * nchunk;
-    pre[kind * (nchunk + 1) + c] = cbase[kind][c / cpc] + __ldg(scan + e);
+  for (int e0 = tid; e0 < 2 * nchunk; e0 += 256 * 8) {          // 8 independent loads in flight per thread
+    unsigned int v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int e = e0 + 256 * q; v[q] = e < 2 * nchunk ? __ldg(scan + e) : 0u; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = e0 + 256 * q;
+      if (e < 2 * nchunk) {
+        const int kind = e >= nchunk, c = e - kind * nchunk;
+        pre[kind * (nchunk + 1) + c] = cbase[kind][c / cpc] + v[q];
+      }
+    }
   }
   if (tid < 2) pre[tid * (nchunk + 1) + nchunk] = cbase[tid][PART_CTAS];
   __syncthreads();

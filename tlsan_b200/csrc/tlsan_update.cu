@@ -117,32 +117,56 @@ __global__ void __launch_bounds__(256, 4) k_row_reduce_bal(int NI, int NC, int N
 
 // rows whose segment spans several ranges: tail of the first range + heads of the others, in range order; rows
 // without occurrences: zeros.  NW = the warp count of k_row_reduce_bal.
+// One THREAD classifies one row (coalesced segment bounds, 256 rows per CTA); the rows that need work -- a few
+// hundred of 22 721 on the Electronics shape, none of the ~600 000 of a row-sharded compact table -- are then taken
+// by the CTA's warps in row order.
 __global__ void __launch_bounds__(256) k_row_fix(int NI, int NC, int NW, const int* __restrict__ seg_off,
                                                  const float* __restrict__ head, const float* __restrict__ tail,
                                                  float* __restrict__ g_i, float* __restrict__ g_b) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= NI + NC) return;
-  const int lo = __ldg(seg_off + r), hi = __ldg(seg_off + r + 1);
+  __shared__ int todo[256];
+  __shared__ int ntodo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 256 + threadIdx.x;
   const int R = rr_range(__ldg(seg_off + NI + NC), NW);
-  const int wa = lo / R, wb = (hi - 1) / R;
-  const bool empty = lo >= hi;
-  if (!empty && wa == wb) return;                   // written directly by its range (independent of k_row_reduce_bal)
+  if (threadIdx.x == 0) ntodo = 0;
+  __syncthreads();
+  bool need = false;
+  if (r0 < NI + NC) {
+    const int lo = __ldg(seg_off + r0), hi = __ldg(seg_off + r0 + 1);
+    need = lo >= hi || lo / R != (hi - 1) / R;      // else: written directly by its range
+  }
+  // compact the flagged rows in row order: warp w's rows precede warp w+1's
+  const unsigned m = __ballot_sync(0xffffffffu, need);
+  __shared__ int wcnt[8];
+  if (lane == 0) wcnt[warp] = __popc(m);
+  __syncthreads();
+  int base = 0;
+  for (int q = 0; q < warp; ++q) base += wcnt[q];
+  if (need) todo[base + __popc(m & ((1u << lane) - 1))] = r0;
+  if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += wcnt[q]; ntodo = t; }
+  __syncthreads();
+  // EVERY thread waits, also those with nothing to fix: a grid that finished without waiting would let the next
+  // kernel of the chain start while k_row_reduce_bal is still writing
   pdl_wait();
   pdl_trigger();
-  float2 acc = make_float2(0.f, 0.f);
-  float accb = 0.f;
-  if (!empty) {
-    acc = reinterpret_cast<const float2*>(tail + (size_t)wa * RR_PSTRIDE)[lane];
-    accb = tail[(size_t)wa * RR_PSTRIDE + 64];
-    for (int w = wa + 1; w <= wb; ++w) {
-      const float2 h = reinterpret_cast<const float2*>(head + (size_t)w * RR_PSTRIDE)[lane];
-      acc.x += h.x; acc.y += h.y;
-      accb += head[(size_t)w * RR_PSTRIDE + 64];
+  for (int k = warp; k < ntodo; k += 8) {
+    const int r = todo[k];
+    const int lo = __ldg(seg_off + r), hi = __ldg(seg_off + r + 1);
+    float2 acc = make_float2(0.f, 0.f);
+    float accb = 0.f;
+    if (lo < hi) {
+      const int wa = lo / R, wb = (hi - 1) / R;
+      acc = reinterpret_cast<const float2*>(tail + (size_t)wa * RR_PSTRIDE)[lane];
+      accb = tail[(size_t)wa * RR_PSTRIDE + 64];
+      for (int w = wa + 1; w <= wb; ++w) {
+        const float2 h = reinterpret_cast<const float2*>(head + (size_t)w * RR_PSTRIDE)[lane];
+        acc.x += h.x; acc.y += h.y;
+        accb += head[(size_t)w * RR_PSTRIDE + 64];
+      }
     }
+    reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
+    if (r < NI && lane == 0) g_b[r] = accb;
   }
-  reinterpret_cast<float2*>(g_i + (size_t)r * 64)[lane] = acc;
-  if (r < NI && lane == 0) g_b[r] = accb;
 }
 
 // ------------------------------------------------------------------ dense partials
@@ -465,7 +489,7 @@ int tlsan_launch_row_reduce(const tlsan_dims_t& d, const TlsanWs& w, char* ws, c
                   reinterpret_cast<const float*>(ws + w.rows_u), reinterpret_cast<const float*>(ws + w.gscal), g_i, g_b,
                   g_u, head, tail);
   TLSAN_CHECK_LAUNCH("k_row_reduce_bal");
-  tlsan_launch_kl(1, k_row_fix, dim3((d.NI + d.NC + 7) / 8), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
+  tlsan_launch_kl(1, k_row_fix, dim3((d.NI + d.NC + 255) / 256), dim3(256), 0, st, d.NI, d.NC, rgrid * 8, seg_off,
                   (const float*)head, (const float*)tail, g_i, g_b);
   TLSAN_CHECK_LAUNCH("k_row_fix");
   return TLSAN_OK;
