@@ -481,9 +481,10 @@ __global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restric
 #define TILE_LD 72
 __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
                                                        int B, float* __restrict__ part) {
-  __shared__ SmemGemm sb;                          // Wd^T: image[j][f] = Wd[f][j]
-  __shared__ __align__(16) float so[16 * TILE_LD];
-  __shared__ __align__(16) float sz[16 * TILE_LD];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];   // 55 KB: over the static limit, opted in by the launcher
+  SmemGemm& sb = *reinterpret_cast<SmemGemm*>(dyn_smem);      // Wd^T: image[j][f] = Wd[f][j]
+  float (*so2)[16 * TILE_LD] = reinterpret_cast<float (*)[16 * TILE_LD]>(dyn_smem + sizeof(SmemGemm));   // double-buffered
+  float (*sz2)[16 * TILE_LD] = so2 + 2;                       // tiles of o_long / dz (cp.async)
   for (int e4 = threadIdx.x; e4 < 64 * 16; e4 += 128) {       // float4 loads: 8 independent per thread
     const float4 w4 = *reinterpret_cast<const float4*>(dense + TLSAN_OFF_WD + 4 * e4);
     const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -505,20 +506,31 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
   float bsum = 0.f;                                 // threads < 64: dbd[threadIdx.x]
   pdl_wait();                                       // dz of the short-term kernel
   pdl_trigger();
-  for (int tile = t_lo; tile < t_hi; ++tile) {
-    __syncthreads();                                // previous tile fully consumed (and sb written)
+  // the 16 rows (o_long | dz) of a tile: 2 x 16-byte cp.async per thread and matrix, rows past B zero-filled
+  auto issue = [&](int tile, int buf) {
     for (int e = threadIdx.x; e < 16 * 16; e += 128) {
       const int r = e >> 4, q = e & 15, row = tile * 16 + r;
-      float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vz = vo;
+      float* po = so2[buf] + r * TILE_LD + 4 * q;
+      float* pz = sz2[buf] + r * TILE_LD + 4 * q;
       if (row < B) {
         const float* sc = scratch + (size_t)row * (TLSAN_SCR * 64);
-        vo = *reinterpret_cast<const float4*>(sc + 64 + 4 * q);
-        vz = *reinterpret_cast<const float4*>(sc + 256 + 4 * q);
+        cp16_async(po, sc + 64 + 4 * q);
+        cp16_async(pz, sc + 256 + 4 * q);
+      } else {
+        *reinterpret_cast<float4*>(po) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(pz) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      *reinterpret_cast<float4*>(so + r * TILE_LD + 4 * q) = vo;
-      *reinterpret_cast<float4*>(sz + r * TILE_LD + 4 * q) = vz;
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (t_lo < t_hi) issue(t_lo, 0);
+  for (int tile = t_lo; tile < t_hi; ++tile) {
+    const int buf = (tile - t_lo) & 1;
+    cp_async_wait_all();
+    __syncthreads();                                // this tile has landed (and sb is written); the previous one is consumed
+    if (tile + 1 < t_hi) issue(tile + 1, buf ^ 1);  // in flight while this tile is multiplied
+    const float* so = so2[buf];
+    const float* sz = sz2[buf];
     // (a) d o_long = dZ Wd^T : this warp computes output columns 16*warp .. +15 for the 16 rows
     {
       float acc[2][4];
@@ -603,7 +615,13 @@ int tlsan_launch_dense_bwd(const float* dense, float* scratch, int B, float* par
   const int ntile16 = (B + 15) / 16;
   const int gc = ntile16 < tlsan_num_sms() * 4 ? ntile16 : tlsan_num_sms() * 4;
   *grid_c = gc;
-  tlsan_launch_k(k_dense_bwd_mma, dim3(gc), dim3(128), 0, st, dense, scratch, B, part);
+  const size_t smem = sizeof(SmemGemm) + 4 * 16 * TILE_LD * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_dense_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tlsan_launch_k(k_dense_bwd_mma, dim3(gc), dim3(128), smem, st, dense, scratch, B, part);
   TLSAN_CHECK_LAUNCH("k_dense_bwd_mma");
   return TLSAN_OK;
 }

@@ -399,22 +399,30 @@ __global__ void __launch_bounds__(256) k_apply_rows(int NI, int NC, int NU, int 
 }
 
 // one CTA per category: sum the cate halves of its items' reduced rows in CSR order
-__global__ void __launch_bounds__(256) k_apply_cate(int NI, float* __restrict__ emb, const float* __restrict__ g_i,
-                                                    const int* __restrict__ cate_off,
-                                                    const int* __restrict__ cate_items, float lr, float reg,
-                                                    const float* __restrict__ stats, const OptArgs opt) {
-  __shared__ float sh[8][32];
-  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// blockDim = 256, or 1024 when categories are few and large (Movies-TV: 15 categories of ~1 900 items): warp w adds
+// items lo + w, lo + w + nw, ... in that order, the warp sums are added in warp order -- fixed for a given shape
+__global__ void __launch_bounds__(1024) k_apply_cate(int NI, float* __restrict__ emb, const float* __restrict__ g_i,
+                                                     const int* __restrict__ cate_off,
+                                                     const int* __restrict__ cate_items, float lr, float reg,
+                                                     const float* __restrict__ stats, const OptArgs opt) {
+  __shared__ float sh[32][32];
+  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int lo = cate_off[k], hi = cate_off[k + 1];
   float acc = 0.f;
-#pragma unroll 4
-  for (int n = lo + warp; n < hi; n += 8) acc += __ldg(g_i + (size_t)__ldg(cate_items + n) * 64 + 32 + lane);
+  int n = lo + warp;
+  for (; n + 7 * nw < hi; n += 8 * nw) {            // 8 independent row loads in flight per lane
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(g_i + (size_t)__ldg(cate_items + n + q * nw) * 64 + 32 + lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += v[q];
+  }
+  for (; n < hi; n += nw) acc += __ldg(g_i + (size_t)__ldg(cate_items + n) * 64 + 32 + lane);
   sh[warp][lane] = acc;
   __syncthreads();
   if (warp == 0) {
     float g = g_i[(size_t)(NI + k) * 64 + 32 + lane];   // direct u_cate occurrences
-#pragma unroll
-    for (int w = 0; w < 8; ++w) g += sh[w][lane];
+    for (int w = 0; w < nw; ++w) g += sh[w][lane];
     const float scale = stats[TLSAN_STAT_SCALE];
     float* wp = emb + (size_t)(NI + k) * 32 + lane;
     const float w = *wp;
@@ -542,7 +550,7 @@ int tlsan_launch_apply(const tlsan_dims_t& d, const tlsan_params_t& p, const Tls
   tlsan_launch_kl(1, k_apply_rows, dim3((unsigned)blocks), dim3(256), 0, st, d.NI, d.NC, d.NU, d.L, w.PU, p.emb, p.usert,
                  p.item_b, g_i, g_b, g_u, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_rows");
-  tlsan_launch_kl(1, k_apply_cate, dim3(d.NC), dim3(256), 0, st, d.NI, p.emb, g_i, (const int*)p.cate_off,
+  tlsan_launch_kl(1, k_apply_cate, dim3(d.NC), dim3(d.NI / d.NC > 256 ? 1024 : 256), 0, st, d.NI, p.emb, g_i, (const int*)p.cate_off,
                  (const int*)p.cate_items, lr, reg, (const float*)stats, opt);
   TLSAN_CHECK_LAUNCH("k_apply_cate");
   return TLSAN_OK;
