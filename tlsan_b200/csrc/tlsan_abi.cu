@@ -284,23 +284,26 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     if (Presort* stale = presort_slot(ws, false)) {
       // a presort announced for this workspace was not consumed (the caller trained on another batch): its
       // kernels may still be writing the sort buffers we are about to reuse
+      // -- and, laid out for ANOTHER batch size, any other part of this workspace (the metadata pre-pass and the
+      // forward's work counter are written by the main stream right away): both streams wait for it
       if (stale->valid) {
         TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev_seg, 0));
         TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st, stale->ev_part, 0));
+        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, stale->ev_seg, 0));
+        TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, stale->ev_part, 0));
       }
       stale->valid = false;
     }
-    long_ctas = tlsan_overlap_ctas();
-    if (pf) {                                                   // balanced partition: first thing on the side stream
-      if ((rc = tlsan_launch_partition_batch(*dims, *p, *b, long_ctas, ws + w.part, side->st))) return rc;
-      TLSAN_CHECK_CUDA(cudaEventRecord(side->part, side->st));
-      part_ready = side->part;
-    }
+    if (!pf) long_ctas = tlsan_overlap_ctas();  // statically partitioned forward kernels leave room for the sort's CTAs
     if ((rc = tlsan_launch_sort(*dims, *p, *b, w, ws, &sorted_vals, nullptr, side->st))) return rc;
     tlsan_profile_mark(TLSAN_PHASE_SORT, side->st);
     TLSAN_CHECK_CUDA(cudaEventRecord(side->join, side->st));
     sorted = side->join;
-    long_ctas = tlsan_overlap_ctas();
+    if (pf) {                    // balanced partition of the short-term / backward kernels: behind the sort, same stream
+      if ((rc = tlsan_launch_partition_batch(*dims, *p, *b, long_ctas, ws + w.part, side->st))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(side->part, side->st));
+      part_ready = side->part;
+    }
     // ||W||^2 of the tables needs only the (still unchanged) weights: off the critical path too
     if (with_tsq && (rc = tlsan_launch_table_sumsq(*dims, *p, w, ws, side->st))) return rc;
     g_prof_overlap = true;
@@ -336,13 +339,13 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
     TLSAN_CHECK_CUDA(cudaEventRecord(side->fork2, st));
     TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, side->fork2, 0));
     if (next->ready_event) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(side->st2, (cudaEvent_t)next->ready_event, 0));
-    if (pf) {     // the consuming (presorted) step runs its forward kernel with 3 CTAs per SM
-      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, side->st2))) return rc;
-      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, side->st2));
-    }
     // ps->ev is recorded inside, before the segment-bounds kernel
     if ((rc = tlsan_launch_sort(*next->dims, *p, *next->batch, wn, wsn, &unused, ps->ev, side->st2))) return rc;
     TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_seg, side->st2));
+    if (pf) {     // partition of the short-term / backward kernels: needed later than the ranks, so behind the sort
+      if ((rc = tlsan_launch_partition_batch(*next->dims, *p, *next->batch, 3, wsn + wn.part, side->st2))) return rc;
+      TLSAN_CHECK_CUDA(cudaEventRecord(ps->ev_part, side->st2));
+    }
     ps->valid = true;
   }
   if (side) {

@@ -390,7 +390,8 @@ static int launch_async(const FArgs& a, int* grid_out, cudaStream_t st) {
 int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
-int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st);   // tlsan_fused_pf.cu
+int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
+                           cudaStream_t st);                                                     // tlsan_fused_pf.cu
 int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int* grid_a,
                           cudaStream_t st);
 int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
@@ -420,14 +421,11 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   void* smeta = ws + w.smeta;
   void* sscal = ws + w.sscal;
   void* part = ws + w.part;
-  // the balanced partition depends on the batch only: the caller computed it beside the sort (part_ready), or asks
-  // for it here (no side stream)
+  // the balanced partition (short-term and backward kernels; the long-term forward claims its samples dynamically)
+  // depends on the batch only: the caller computed it behind the sort (part_ready), or asks for it here (no side stream)
+  (void)part_early;
   if (variant == 2 && !part_ready && (rc = tlsan_launch_partition(a, long_ctas, true, part, st))) return rc;
-  // a partition made by the previous step's presort is long finished: joining it BEFORE the metadata pre-pass keeps
-  // k_long_meta -> k_pf_long<1> adjacent in the stream (programmatic dependent launch)
-  if (variant == 2 && part_ready && part_early) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, part_ready, 0));
-  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, st))) return rc;
-  if (variant == 2 && part_ready && !part_early) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, part_ready, 0));
+  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, part, long_ctas, st))) return rc;
   if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, part, long_ctas, st)
                          : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
     return rc;
@@ -435,6 +433,7 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   if ((rc = tlsan_launch_dense_fwd(p.dense, a.scratch, d.B, st))) return rc;
   a.part = reinterpret_cast<float*>(ws + w.part_a);
   if (sorted) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, sorted, 0));   // gradient rows are written at sorted rank
+  if (variant == 2 && part_ready) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, part_ready, 0));
   tlsan_profile_mark(TLSAN_PHASE_DENSE_FWD, st);                       // (phase includes the join with the sort stream)
   if ((rc = variant == 2 ? tlsan_launch_short_pf(a, smeta, sscal, part, grid_a, st) : launch_async<2>(a, grid_a, st))) return rc;
   tlsan_profile_mark(TLSAN_PHASE_SHORT, st);

@@ -675,7 +675,8 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
   return TLSAN_OK;
 }
 
-int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st);   // tlsan_fused_pf.cu
+int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
+                           cudaStream_t st);                                                     // tlsan_fused_pf.cu
 int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st);
 int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
 size_t tlsan_partition_bytes();
@@ -690,8 +691,7 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
   if (use_ws < 0) { const char* e = getenv("TLSAN_FUSED_IMPL"); use_ws = (e && *e && strcmp(e, "pf") != 0) ? 0 : 1; }
   void* meta = reinterpret_cast<char*>(scratch) + tlsan_align_up((size_t)d.B * TLSAN_SCR * 64 * sizeof(float), 256);
   void* part = reinterpret_cast<char*>(meta) + tlsan_align_up((size_t)d.B * d.L * 16, 256);
-  if (use_ws && (rc = tlsan_launch_partition(a, 3, false, part, st))) return rc;
-  if (use_ws && (rc = tlsan_launch_long_meta(a, meta, nullptr, nullptr, st))) return rc;
+  if (use_ws && (rc = tlsan_launch_long_meta(a, meta, nullptr, nullptr, part, 3, st))) return rc;
   if ((rc = use_ws ? tlsan_launch_long_fwd_pf(a, meta, part, 3, st) : tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
   if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
   k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);

@@ -63,7 +63,9 @@ static PfGeo pf_geo(int L, bool bwd) {
 struct PfArgs {
   FArgs a;
   const int4* meta;         // [B][L] {item row, category row, P*hist_t, hist_t}
-  const int* starts;        // [#warps + 1] balanced partition (k_partition)
+  const int* starts;        // [#warps + 1] balanced partition (k_partition): backward only
+  int* counter;             // forward: next unclaimed sample (k_long_meta resets it to #warps * chunk)
+  int chunk;                // forward: samples per claim
   PfGeo g;
 };
 
@@ -102,11 +104,12 @@ __device__ __forceinline__ FwaW load_fwa_log2(const float* __restrict__ dense, i
 // [2 + j] = session item j, each {row of the item / user half, row of the category half};
 // sscal[b] = {sl_new, candidate, y, item_b[candidate]}
 __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta, int2* __restrict__ smeta,
-                                                   int4* __restrict__ sscal) {
+                                                   int4* __restrict__ sscal, int* __restrict__ counter, int counter0) {
   const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nlong = (long long)a.B * a.L;
   pdl_wait();                                                   // usert / item_b: the previous step's update
   pdl_trigger();
+  if (gidx == 0 && counter) *counter = counter0;                // work counter of the long-term forward (k_pf_long<1>)
   if (gidx < nlong) {
     const int b = (int)(gidx / a.L), t = (int)(gidx - (long long)b * a.L);
     int4 m = make_int4(0, 0, 0, 0);
@@ -149,15 +152,16 @@ __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restri
 // starts[w] = min { b : P(b) >= floor(w * total / NW) }, P = exclusive prefix of cost.  The partition is a pure
 // function of the batch and the grid, so the per-warp summation order -- and every result bit -- stays reproducible.
 //   cost_long(b) = 2 ceil(sl / 2) + 2          cost_short(b) = 2 ceil((sl_new + 1) / 2) + 3        (tiles + overhead)
-struct PartArgs { const int* sl; const int* sl_new; int B; int nw[3]; int* starts[3]; };   // [0] fwd, [1] bwd, [2] short
+struct PartArgs { const int* sl; const int* sl_new; int B; int nw[3]; int* starts[3]; };   // [0] unused (the forward
+                                                    // claims samples dynamically, see k_pf_long), [1] bwd, [2] short
 
 // Two small kernels.  k_part_scan (PART_CTAS CTAs): CTA c owns samples [c * per, (c+1) * per) -- per-chunk (8 samples)
-// exclusive prefixes LOCAL to the CTA and the CTA's total, for both cost kinds.  k_part_bounds: every CTA stages the
-// global chunk prefixes in shared memory (CTA totals are scanned on the fly), each thread places one boundary by
-// binary search over the chunks and a walk of at most 8 samples; comparisons are w * total <= P * nw + nw - 1
-// (no division).
+// exclusive prefixes LOCAL to the CTA and the CTA's total, for both cost kinds.  k_part_bounds: every CTA scans the 64
+// CTA totals in shared memory, each thread places one boundary by binary search -- over the CTA bases first, then over
+// one CTA's chunk prefixes in global memory -- and a walk of at most 8 samples; comparisons are
+// w * total <= P * nw + nw - 1 (no division).
 #define PART_CTAS 64
-#define PART_MAXB (200 * 1024)                                   // chunk prefixes of both kinds must fit one CTA's smem
+#define PART_MAXB (200 * 1024)                                   // sizes the chunk-prefix scratch (tlsan_partition_bytes)
 __device__ __forceinline__ int part_cost_of(int kind, int v) {
   return kind == 0 ? 2 * ((min(max(v, 0), 120) + 1) / 2) + 2 : 2 * ((min(max(v, 0), 120) + 2) / 2) + 3;
 }
@@ -197,12 +201,11 @@ __global__ void __launch_bounds__(256) k_part_scan(const PartArgs p, unsigned in
 
 __global__ void __launch_bounds__(256) k_part_bounds(const PartArgs p, const unsigned int* __restrict__ scan,
                                                      const unsigned int* __restrict__ tot, int nchunk, int cpc) {
-  extern __shared__ unsigned int pre[];                          // [2][nchunk + 1] global exclusive chunk prefixes
-  __shared__ unsigned int cbase[2][PART_CTAS + 1];
+  __shared__ unsigned int cbase[2][PART_CTAS + 1];               // global prefix at the first chunk of every scan CTA
   __shared__ unsigned int ctot[2 * PART_CTAS];
   const int tid = threadIdx.x;
   // exclusive scan of the 64 CTA totals of each kind: one load per thread, then every thread sums its predecessors
-  // out of shared memory (a serial loop of dependent global loads here used to be most of this kernel's 20 us)
+  // out of shared memory
   if (tid < 2 * PART_CTAS) ctot[tid] = __ldg(tot + tid);
   __syncthreads();
   if (tid < 2 * PART_CTAS) {
@@ -213,42 +216,36 @@ __global__ void __launch_bounds__(256) k_part_bounds(const PartArgs p, const uns
     if (c == PART_CTAS - 1) cbase[kind][PART_CTAS] = run + ctot[tid];
   }
   __syncthreads();
-  for (int e0 = tid; e0 < 2 * nchunk; e0 += 256 * 8) {          // 8 independent loads in flight per thread
-    unsigned int v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { const int e = e0 + 256 * q; v[q] = e < 2 * nchunk ? __ldg(scan + e) : 0u; }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int e = e0 + 256 * q;
-      if (e < 2 * nchunk) {
-        const int kind = e >= nchunk, c = e - kind * nchunk;
-        pre[kind * (nchunk + 1) + c] = cbase[kind][c / cpc] + v[q];
-      }
-    }
-  }
-  if (tid < 2) pre[tid * (nchunk + 1) + nchunk] = cbase[tid][PART_CTAS];
-  __syncthreads();
   const int stride = TLSAN_MAX_GRID * PF_WARPS + 1;
   const int idx = blockIdx.x * 256 + tid;
   const int t = idx / stride, w = idx - t * stride;
   if (t >= 3 || p.nw[t] <= 0 || w > p.nw[t]) return;
   const int nw = p.nw[t], kind = t == 2 ? 1 : 0;
-  const unsigned int* P = pre + kind * (nchunk + 1);
   const int* src = kind == 0 ? p.sl : p.sl_new;
+  // global exclusive prefix of chunk c (c == nchunk: the total); the CTA bases sit in shared memory, the CTA-local
+  // prefixes stay in global memory (an earlier version staged all of them in every CTA's shared memory: 20 us)
+  auto P = [&](int c) -> unsigned int {
+    return c >= nchunk ? cbase[kind][PART_CTAS] : cbase[kind][c / cpc] + __ldg(scan + (size_t)kind * nchunk + c);
+  };
   int out = p.B;
   if (w < nw) {
-    const unsigned long long total = P[nchunk] > 0 ? P[nchunk] : 1;
+    const unsigned long long total = cbase[kind][PART_CTAS] > 0 ? cbase[kind][PART_CTAS] : 1;
     const unsigned long long lhs = (unsigned long long)w * total;
     auto ge = [&](unsigned int x) { return lhs <= (unsigned long long)x * nw + (nw - 1); };
-    int lo = 0, hi = nchunk;                                     // first chunk whose prefix satisfies ge (hi: none)
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ge(P[mid])) hi = mid; else lo = mid + 1; }
+    // first chunk whose prefix satisfies ge (nchunk: none) -- first among the 65 CTA bases (shared memory), then
+    // inside one scan CTA's chunks (<= 8 dependent global loads)
+    int qlo = 0, qhi = PART_CTAS + 1;
+    while (qlo < qhi) { const int mid = (qlo + qhi) >> 1; if (ge(cbase[kind][mid])) qhi = mid; else qlo = mid + 1; }
+    int lo = qlo == 0 ? 0 : (int)min((long long)(qlo - 1) * cpc + 1, (long long)nchunk);
+    int hi = qlo == 0 ? 0 : (int)min((long long)qlo * cpc, (long long)nchunk);
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ge(P(mid))) hi = mid; else lo = mid + 1; }
     int b = lo * 8;                                              // inside chunk lo - 1 (after its first sample) or at chunk lo
     if (lo > 0) {
       const int base = (lo - 1) * 8;
       int v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = base + i < p.B ? __ldg(src + base + i) : 0;
-      unsigned int x = P[lo - 1];
+      unsigned int x = P(lo - 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         x += base + i < p.B ? part_cost_of(kind, v[i]) : 0;
@@ -377,20 +374,45 @@ struct PfIter { int b, r0, ell; };
 template <int KIND>
 __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const PfArgs A) {
   constexpr bool BWD = KIND == 3;
+  // Work assignment.  Backward: the balanced static partition (its per-warp partial sums must be accumulated in a
+  // fixed order).  Forward: every output is per sample, so the order samples are processed in cannot change a bit of
+  // the result -- warps CLAIM chunks of A.chunk samples from a global counter instead.  A CTA that becomes resident
+  // late (the occurrence sort of the next batch shares the SMs: a third CTA per SM often has to wait for a sort CTA
+  // to retire) then simply claims less, where the static partition made the whole kernel wait for it
+  // (long-term forward 52 us alone, 100 us beside the sort).
+  constexpr bool DYN = KIND == 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const FArgs& a = A.a;
   const PfGeo& g = A.g;
   LaneGeo L; L.init();
   const int warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * PF_WARPS + warp;
-  const int bBeg = __ldg(A.starts + gw), bEnd = __ldg(A.starts + gw + 1);     // this warp's contiguous samples
+  int bBeg, bEnd;                                               // static: this warp's contiguous samples
+  if (DYN) { bBeg = min(gw * A.chunk, a.B); bEnd = min(bBeg + A.chunk, a.B); }   // first chunk: no claim needed
+  else { bBeg = __ldg(A.starts + gw); bEnd = __ldg(A.starts + gw + 1); }
   const int h = L.lane >> 4, c16 = L.lane & 15;
   unsigned char* mine = smem + (size_t)warp * g.per_warp;
   const FwaW wl = load_fwa_log2(a.dense, TLSAN_OFF_W1L, L.g, L.t);
 
   const float gamma = a.dense[TLSAN_OFF_GAMMA];
-  auto ell_of = [&](int b) { return b < bEnd ? __ldg(a.sl + b) : -1; };
-  auto nextb = [&](int b) { return b + 1 < bEnd ? b + 1 : a.B; };        // a.B: end marker
+  int curEnd = bEnd, nxt = a.B;                                 // dynamic: end of the newest chunk, first sample of the claimed one
+  auto claim = [&]() -> int {
+    int v = 0;
+    if (L.lane == 0) v = atomicAdd(A.counter, A.chunk);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  auto ell_of = [&](int b) { return b < a.B ? __ldg(a.sl + b) : -1; };
+  // the sample after b in this warp's sequence; a.B: end marker.  Called exactly once per sample (stateful when DYN).
+  auto succ = [&](int b) -> int {
+    if (b >= a.B) return a.B;
+    if (b + 1 < curEnd) return b + 1;
+    if (!DYN) return a.B;
+    const int nb = nxt;
+    if (nb >= a.B) return a.B;
+    curEnd = min(nb + A.chunk, a.B);
+    nxt = claim();                                              // needed a whole chunk from now
+    return nb;
+  };
   auto ring = [&](int n) { return mine + g.o_ring + (n % 3) * g.ring; };
   // copy the metadata of a round into ring slot `dst`: lane t < 16 serves token r0 + t
   auto issue_meta = [&](const PfIter& it, unsigned char* dst) {
@@ -420,22 +442,30 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
       cp16_s(smem_addr(buf + g.o_stats) + 512 + L.lane * 16, sc + 128 + L.lane * 4);
     }
   };
-  auto advance = [&](const PfIter& it, int ell_next) {
+  auto advance = [&](const PfIter& it, int b_next, int ell_next) {
     PfIter n;
     if (it.r0 + PF_R < it.ell) { n.b = it.b; n.r0 = it.r0 + PF_R; n.ell = it.ell; }
-    else { n.b = nextb(it.b); n.r0 = 0; n.ell = ell_next; }
+    else { n.b = b_next; n.r0 = 0; n.ell = ell_next; }
     return n;
   };
 
   // ---- pipeline prologue: metadata of rounds 0 and 1, then the rows of round 0
-  PfIter it0, it1, it2;
-  it0.b = bBeg < bEnd ? bBeg : a.B; it0.r0 = 0; it0.ell = ell_of(it0.b);
-  int eN = ell_of(nextb(it0.b));                                // length of the sample after the newest iterator's
-  it1 = advance(it0, eN);
-  if (it1.r0 == 0) eN = ell_of(nextb(it1.b));
   const FwaWT wlt = BWD ? load_fwa_t(a.dense, TLSAN_OFF_W1L, L.g, L.t) : FwaWT();
-  pdl_wait();                                                   // meta (k_long_meta) / scratch, ranks (backward)
+  PfIter it0, it1, it2;
+  int bN = a.B, eN = -1;                                        // the sample after the newest iterator's, its length
+  auto first_rounds = [&]() {
+    it0.b = bBeg < bEnd ? bBeg : a.B; it0.r0 = 0; it0.ell = ell_of(it0.b);
+    bN = succ(it0.b); eN = ell_of(bN);
+    it1 = advance(it0, bN, eN);
+    if (it1.r0 == 0) { bN = succ(it1.b); eN = ell_of(bN); }
+  };
+  if (!DYN) first_rounds();                                     // batch data only: overlaps the previous kernel's tail
+  pdl_wait();                                                   // meta, work counter (k_long_meta) / scratch, ranks (backward)
   pdl_trigger();
+  if (DYN) {
+    if (bBeg < a.B) nxt = claim();
+    first_rounds();
+  }
   issue_meta(it0, ring(0));
   issue_meta(it1, ring(1));
   cp_commit();
@@ -457,8 +487,8 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
     __syncwarp();
     // ---- next round's rows, the metadata of the round after it
     issue_round(it1, ring(n + 1), mine + (size_t)((n + 1) & 1) * g.buf);
-    it2 = advance(it1, eN);
-    if (it2.r0 == 0) eN = ell_of(nextb(it2.b));
+    it2 = advance(it1, bN, eN);
+    if (it2.r0 == 0) { bN = succ(it2.b); eN = ell_of(bN); }
     issue_meta(it2, ring(n + 2));
     cp_commit();
 
@@ -760,14 +790,31 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
 size_t tlsan_long_meta_bytes(int B, int L) { return (size_t)B * L * sizeof(int4); }
 
 // smeta / sscal may be NULL (scoring: long-term part only)
-int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, cudaStream_t st) {
+// `part`: the partition block of the workspace; its last 16 bytes hold the work counter of the long-term forward, reset
+// here for the kernel launched with `fwd_ctas` CTAs per SM
+static int* pf_counter(const void* part);
+static int pf_chunk();
+static int pf_grid(int B, int ctas_per_sm);
+int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
+                           cudaStream_t st) {
   const long long n = (long long)a.B * a.L + (smeta ? a.B : 0);
   tlsan_launch_k(k_long_meta, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, reinterpret_cast<int4*>(meta),
-                 reinterpret_cast<int2*>(smeta), reinterpret_cast<int4*>(sscal));
+                 reinterpret_cast<int2*>(smeta), reinterpret_cast<int4*>(sscal), pf_counter(part),
+                 pf_grid(a.B, fwd_ctas) * PF_WARPS * pf_chunk());
   TLSAN_CHECK_LAUNCH("k_long_meta");
   return TLSAN_OK;
 }
 
+// samples a forward warp claims at a time: small enough that the last claims end together (a sample is ~2.8 us of one
+// warp), large enough that the claims (one atomic on one address each) stay far below the L2's same-address rate
+static int pf_chunk() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("TLSAN_PF_CHUNK"); v = e ? atoi(e) : 4; if (v < 1 || v > 1024) v = 4; }
+  return v;
+}
+static int* pf_counter(const void* part) {
+  return reinterpret_cast<int*>(reinterpret_cast<char*>(const_cast<void*>(part)) + tlsan_partition_bytes() - 16);
+}
 // grids of the three pipelined kernels (the partition is computed for exactly these)
 static int pf_grid(int B, int ctas_per_sm) {
   const int need = (B + PF_WARPS - 1) / PF_WARPS, cap = tlsan_num_sms() * ctas_per_sm;
@@ -783,7 +830,9 @@ int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part,
   p.sl = a.sl; p.sl_new = a.sl_new; p.B = a.B;
   int* base = reinterpret_cast<int*>(part);
   for (int t = 0; t < 3; ++t) p.starts[t] = base + (size_t)t * (TLSAN_MAX_GRID * PF_WARPS + 4);
-  p.nw[0] = pf_grid(a.B, fwd_ctas) * PF_WARPS;
+  (void)fwd_ctas;                                                // the forward claims its samples dynamically
+  if (!train) return TLSAN_OK;                                   // scoring: nothing to partition
+  p.nw[0] = 0;
   p.nw[1] = train ? pf_grid(a.B, 2) * PF_WARPS : 0;
   p.nw[2] = train ? pf_grid(a.B, 2) * PF_WARPS : 0;
   const int nchunk = (a.B + 7) / 8;
@@ -798,13 +847,7 @@ int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part,
   const int cpc = (nchunk + PART_CTAS - 1) / PART_CTAS;          // chunks per CTA
   k_part_scan<<<PART_CTAS, 256, 0, st>>>(p, scan, tot, nchunk, cpc);
   TLSAN_CHECK_LAUNCH("k_part_scan");
-  const int smem = 2 * (nchunk + 1) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_part_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    attr_set = true;
-  }
-  k_part_bounds<<<(3 * (TLSAN_MAX_GRID * PF_WARPS + 1) + 255) / 256, 256, smem, st>>>(p, scan, tot, nchunk, cpc);
+  k_part_bounds<<<(3 * (TLSAN_MAX_GRID * PF_WARPS + 1) + 255) / 256, 256, 0, st>>>(p, scan, tot, nchunk, cpc);
   TLSAN_CHECK_LAUNCH("k_part_bounds");
   return TLSAN_OK;
 }
@@ -823,7 +866,8 @@ static int launch_pf_long(const FArgs& a, const void* meta, const void* part, in
                           cudaStream_t st) {
   PfArgs A;
   A.a = a; A.meta = reinterpret_cast<const int4*>(meta); A.g = pf_geo(a.L, KIND == 3);
-  A.starts = part_starts(part, KIND == 1 ? 0 : 1);
+  A.starts = part_starts(part, 1);
+  A.counter = pf_counter(part); A.chunk = pf_chunk();
   static bool attr_set = false;
   if (!attr_set) {
     TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_long<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));

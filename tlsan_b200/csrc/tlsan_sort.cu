@@ -21,12 +21,17 @@ struct KeySrc {
 };
 __device__ __forceinline__ int occ_key(const KeySrc& k, long long g) {
   const int b = (int)(g >> k.spsh), j = (int)(g & ((1 << k.spsh) - 1));
+  const int LS = k.L + k.S;
   int key = TLSAN_INVALID_KEY;                      // also the padding slots j >= L+S+3
-  if (j < k.L) { if (j < __ldg(k.sl + b)) key = __ldg(k.hist_i + (size_t)b * k.L + j); }
-  else if (j < k.L + k.S) { if ((j - k.L) < __ldg(k.sl_new + b)) key = __ldg(k.hist_i_new + (size_t)b * k.S + (j - k.L)); }
-  else if (j == k.L + k.S) key = __ldg(k.cand + b);
-  else if (j == k.L + k.S + 1) key = k.NI + __ldg(k.c + b);
-  else if (j == k.L + k.S + 2) key = k.NI + k.NC + __ldg(k.u + b);
+  if (j < LS) {                                     // a history slot: one length load (warp-uniform when SP >= 32), one id
+    const bool lng = j < k.L;
+    const int jj = lng ? j : j - k.L;
+    if (jj < __ldg((lng ? k.sl : k.sl_new) + b))
+      key = __ldg((lng ? k.hist_i + (size_t)b * k.L : k.hist_i_new + (size_t)b * k.S) + jj);
+  } else if (j <= LS + 2) {                         // candidate | u_cate | user
+    const int q = j - LS;
+    key = __ldg((q == 0 ? k.cand : q == 1 ? k.c : k.u) + b) + (q == 0 ? 0 : q == 1 ? k.NI : k.NI + k.NC);
+  }
   // ids are range-checked when a batch is staged; a batch buffer that was freed and reused while a presort
   // announced for it was still queued must not turn into out-of-range segment writes either
   if ((unsigned)key >= (unsigned)k.NR) key = TLSAN_INVALID_KEY;
@@ -90,8 +95,15 @@ __global__ void __launch_bounds__(256) k_radix_scan_rows(int* __restrict__ hist,
   if (lane == 0) tot[d] = run;
 }
 
+// One pass = count + rank in ONE sweep over the warp's keys: in index order a key's rank among the warp's keys of the
+// same digit is (matching keys seen in earlier iterations) + (matching lower lanes of this iteration); the running
+// count per digit lives in the warp's shared-memory row and ends up as the warp's digit histogram.  The CTA then
+// turns the 16 histograms into start offsets (digit base + this CTA's base inside the digit + lower warps) and every
+// lane scatters its 8 keys from registers with nothing but one shared-memory read in between -- all stores of a lane
+// are in flight together.  (The first version counted with shared-memory atomics, ranked in a second sweep with a
+// dependent read-modify-write per iteration and loaded the values inside that loop: 34 / 24 us per pass.)
 template <bool FROM_BATCH>
-__global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
+__global__ void __launch_bounds__(32 * SORT_WARPS, FROM_BATCH ? 3 : 2) k_radix_scatter(
     const int* __restrict__ keys_in, const KeySrc src, const int* __restrict__ vals_in, long long ncap,
     const int* __restrict__ nvalid, int* __restrict__ nvalid_out, int shift, int nblk, const int* __restrict__ hist,
     const int* __restrict__ tot, int* __restrict__ keys_out, int* __restrict__ vals_out,
@@ -100,32 +112,61 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
   __shared__ int dbase[256];
   __shared__ int wtot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = lane; d < 256; d += 32) off[warp][d] = 0;
-  __syncwarp();
   const long long n = nvalid ? (long long)*nvalid : ncap;
+  // a CTA past the valid keys (later passes run on the compacted list) has nothing to rank or write
+  if (blockIdx.x > 0 && (long long)blockIdx.x * SORT_WARPS * SORT_KPW >= n) return;
+  for (int d = lane; d < 256; d += 32) off[warp][d] = 0;
   const long long wbase = ((long long)blockIdx.x * SORT_WARPS + warp) * SORT_KPW;
-  int k[SORT_KPL];
+  int k[SORT_KPL], v[FROM_BATCH ? 1 : SORT_KPL], rk[SORT_KPL];   // pass 0 (from the batch): value = occurrence id = index
   load_keys<FROM_BATCH>(keys_in, src, n, wbase, lane, k);
+  if (!FROM_BATCH) {
 #pragma unroll
-  for (int it = 0; it < SORT_KPL; ++it)
-    if (k[it] != TLSAN_INVALID_KEY) atomicAdd(&off[warp][(k[it] >> shift) & 255], 1);
+    for (int it = 0; it < SORT_KPL; ++it) {
+      const long long idx = wbase + it * 32 + lane;
+      v[it] = (vals_in && k[it] != TLSAN_INVALID_KEY) ? vals_in[idx] : (int)idx;
+    }
+  }
+  // digit totals: loaded early, scanned below
+  const int my_tot = threadIdx.x < 256 ? tot[threadIdx.x] : 0;
+  const int my_hist = threadIdx.x < 256 ? hist[(size_t)threadIdx.x * nblk + blockIdx.x] : 0;
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < SORT_KPL; ++it) {      // in index order: the pass is stable
+    const bool act = k[it] != TLSAN_INVALID_KEY;
+    const int digit = (k[it] >> shift) & 255;
+    // lanes holding the same digit: eight ballots, one per digit bit (match.any is far slower than that on sm_100a:
+    // the pass was bound by it -- ~150 cycles each, one at a time per SM)
+    unsigned m = __ballot_sync(0xffffffffu, act);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+      const bool one = (digit >> bit) & 1;
+      const unsigned bal = __ballot_sync(0xffffffffu, one);
+      m &= one ? bal : ~bal;
+    }
+    const int below = __popc(m & lt);
+    const int seen = act ? off[warp][digit] : 0;
+    rk[it] = seen + below;
+    __syncwarp();
+    if (act && below == 0) off[warp][digit] = seen + __popc(m);
+    __syncwarp();
+  }
   if (threadIdx.x < 256) {  // exclusive scan of the 256 digit totals (8 warps x 32)
-    const int v = tot[threadIdx.x];
-    int x = v;
+    int x = my_tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
     if (lane == 31) wtot[warp] = x;
-    dbase[threadIdx.x] = x - v;
+    dbase[threadIdx.x] = x - my_tot;
   }
   __syncthreads();
   if (threadIdx.x < 256) {  // counts -> start offsets: digit base + CTA base in the digit + lower warps
     int pre = 0;
     for (int w = 0; w < warp; ++w) pre += wtot[w];
-    if (blockIdx.x == 0 && threadIdx.x == 255) *nvalid_out = pre + dbase[255] + tot[255];
-    int run = pre + dbase[threadIdx.x] + hist[(size_t)threadIdx.x * nblk + blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 255) *nvalid_out = pre + dbase[255] + my_tot;
+    int run = pre + dbase[threadIdx.x] + my_hist;
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w) {
       const int c = off[w][threadIdx.x];
@@ -134,23 +175,12 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_radix_scatter(
     }
   }
   __syncthreads();
-  const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int it = 0; it < SORT_KPL; ++it) {      // in index order: the pass is stable
-    const int key = k[it];
-    const bool act = key != TLSAN_INVALID_KEY;
-    const int digit = act ? (key >> shift) & 255 : 256 + lane;  // inactive lanes match only themselves
-    const unsigned m = __match_any_sync(0xffffffffu, digit);
-    const int rank = __popc(m & lt);
-    int pos = 0;
-    if (act) pos = off[warp][digit] + rank;
-    __syncwarp();
-    if (act && rank == 0) off[warp][digit] += __popc(m);
-    __syncwarp();
-    if (act) {
-      const long long idx = wbase + it * 32 + lane;
-      const int val = vals_in ? vals_in[idx] : (int)idx;
-      keys_out[pos] = key;
+  for (int it = 0; it < SORT_KPL; ++it) {
+    if (k[it] != TLSAN_INVALID_KEY) {
+      const int pos = off[warp][(k[it] >> shift) & 255] + rk[it];
+      const int val = FROM_BATCH ? (int)(wbase + it * 32 + lane) : v[it];
+      keys_out[pos] = k[it];
       vals_out[pos] = val;
       if (inv_out) inv_out[val] = pos;
     }
