@@ -412,20 +412,30 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&h)[4], ui
   }
 }
 // acc += A(16x8) B(8x8), B fragment read from the hi/lo images at rows (k0+2t, k0+2t+1), column n0+g
-__device__ __forceinline__ void gemm_step(float (&acc)[4], const uint32_t (&h)[4], const uint32_t (&l)[4],
-                                          const SmemGemm& sb, int k0, int n0, int g, int t) {
+// the big term (hi x hi) and the two small ones run on separate accumulators -- two independent HMMA chains per output
+// tile instead of one three times as long; the caller adds `accs` to `acc` once, after the k loop
+__device__ __forceinline__ void gemm_step(float (&acc)[4], float (&accs)[4], const uint32_t (&h)[4],
+                                          const uint32_t (&l)[4], const SmemGemm& sb, int k0, int n0, int g, int t) {
   const int i0 = (k0 + 2 * t) * GEMM_LD + n0 + g, i1 = i0 + GEMM_LD;
   const uint32_t bh0 = __float_as_uint(sb.hi[i0]), bh1 = __float_as_uint(sb.hi[i1]);
   const uint32_t bl0 = __float_as_uint(sb.lo[i0]), bl1 = __float_as_uint(sb.lo[i1]);
-  mma_tf32(acc, l[0], l[2], l[1], l[3], bh0, bh1);
-  mma_tf32(acc, h[0], h[2], h[1], h[3], bl0, bl1);
+  mma_tf32(accs, l[0], l[2], l[1], l[3], bh0, bh1);
   mma_tf32(acc, h[0], h[2], h[1], h[3], bh0, bh1);
+  mma_tf32(accs, h[0], h[2], h[1], h[3], bl0, bl1);
 }
 
+// 64-row tiles of o_long travel global -> shared with cp.async, double-buffered: the next tile is in flight while this
+// one is multiplied (the first version loaded each warp's A fragment into registers right before its 96 HMMAs:
+// long_scoreboard 56 % of the stall samples, 10 % of the DRAM bandwidth).  Warp w: rows 16 (w / 2) .. +15 of the
+// tile, output columns 32 (w % 2) .. +31.
+#define TILE_LD 72
+#define DF_ROWS 64
 __global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
                                                        int B) {
-  __shared__ SmemGemm sb;
-  __shared__ float sbd[64];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  SmemGemm& sb = *reinterpret_cast<SmemGemm*>(dyn_smem);
+  float* sbd = reinterpret_cast<float*>(dyn_smem + sizeof(SmemGemm));
+  float (*sa)[DF_ROWS * TILE_LD] = reinterpret_cast<float (*)[DF_ROWS * TILE_LD]>(dyn_smem + sizeof(SmemGemm) + 256);
   for (int e4 = threadIdx.x; e4 < 64 * 16; e4 += 256) {       // float4 loads: 4 independent per thread
     const float4 w4 = *reinterpret_cast<const float4*>(dense + TLSAN_OFF_WD + 4 * e4);
     const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -440,45 +450,58 @@ __global__ void __launch_bounds__(256, 2) k_dense_fwd_mma(const float* __restric
   if (threadIdx.x < 64) sbd[threadIdx.x] = dense[TLSAN_OFF_BD + threadIdx.x];
   pdl_wait();                                      // o_long of the long-term forward
   pdl_trigger();
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int half = warp & 1;                       // output columns 32*half .. +31
-  const int ntiles = (B + 15) / 16;
-  for (int tile = blockIdx.x * 4 + (warp >> 1); tile < ntiles; tile += gridDim.x * 4) {
-    const int rA = tile * 16 + g, rB = rA + 8;
-    const bool vA = rA < B, vB = rB < B;
-    const float* pA = scratch + (size_t)rA * (TLSAN_SCR * 64) + 64 + 2 * t;
-    const float* pB = scratch + (size_t)rB * (TLSAN_SCR * 64) + 64 + 2 * t;
-    float2 xa[8], xb[8];                            // the whole A fragment up front: 16 loads in flight
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      xa[ks] = vA ? *reinterpret_cast<const float2*>(pA + ks * 8) : make_float2(0.f, 0.f);
-      xb[ks] = vB ? *reinterpret_cast<const float2*>(pB + ks * 8) : make_float2(0.f, 0.f);
+  const int half = warp & 1, r0 = (warp >> 1) * 16;
+  const int ntiles = (B + DF_ROWS - 1) / DF_ROWS;
+  // rows of a tile: 4 x 16-byte cp.async per thread, rows past B zero-filled
+  auto issue = [&](int tile, int buf) {
+    for (int e = threadIdx.x; e < DF_ROWS * 16; e += 256) {
+      const int r = e >> 4, q = e & 15, row = tile * DF_ROWS + r;
+      float* dst = sa[buf] + r * TILE_LD + 4 * q;
+      if (row < B) cp16_async(dst, scratch + (size_t)row * (TLSAN_SCR * 64) + 64 + 4 * q);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float acc[4][4];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) issue(tile, 0);
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    cp_async_wait_all();
+    __syncthreads();                                // this tile has landed (and sb is written); the previous one is consumed
+    if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1);
+    const float* a = sa[buf] + (r0 + g) * TILE_LD + 2 * t;
+    float acc[4][4], accs[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       acc[nt][0] = acc[nt][2] = sbd[half * 32 + nt * 8 + 2 * t];
       acc[nt][1] = acc[nt][3] = sbd[half * 32 + nt * 8 + 2 * t + 1];
+      accs[nt][0] = accs[nt][1] = accs[nt][2] = accs[nt][3] = 0.f;
     }
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      const float x[4] = {xa[ks].x, xa[ks].y, xb[ks].x, xb[ks].y};
+      const float2 xa = *reinterpret_cast<const float2*>(a + ks * 8);
+      const float2 xb = *reinterpret_cast<const float2*>(a + 8 * TILE_LD + ks * 8);
+      const float x[4] = {xa.x, xa.y, xb.x, xb.y};
       uint32_t h[4], l[4];
       split4(x, h, l);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, half * 32 + nt * 8, g, t);
+      for (int nt = 0; nt < 4; ++nt) gemm_step(acc[nt], accs[nt], h, l, sb, ks * 8, half * 32 + nt * 8, g, t);
     }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] += accs[nt][i];
+    const int rA = tile * DF_ROWS + r0 + g, rB = rA + 8;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int col = 320 + half * 32 + nt * 8 + 2 * t;
-      if (vA) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + col, acc[nt][0], acc[nt][1]);
-      if (vB) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + col, acc[nt][2], acc[nt][3]);
+      if (rA < B) st2(scratch + (size_t)rA * (TLSAN_SCR * 64) + col, acc[nt][0], acc[nt][1]);
+      if (rB < B) st2(scratch + (size_t)rB * (TLSAN_SCR * 64) + col, acc[nt][2], acc[nt][3]);
     }
   }
 }
 
-#define TILE_LD 72
 __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__ dense, float* __restrict__ scratch,
                                                        int B, float* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];   // 55 KB: over the static limit, opted in by the launcher
@@ -533,9 +556,12 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
     const float* sz = sz2[buf];
     // (a) d o_long = dZ Wd^T : this warp computes output columns 16*warp .. +15 for the 16 rows
     {
-      float acc[2][4];
+      float acc[2][4], accs[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      for (int nt = 0; nt < 2; ++nt) {
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        accs[nt][0] = accs[nt][1] = accs[nt][2] = accs[nt][3] = 0.f;
+      }
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         const float2 a = *reinterpret_cast<const float2*>(sz + g * TILE_LD + ks * 8 + 2 * t);
@@ -544,8 +570,12 @@ __global__ void __launch_bounds__(128) k_dense_bwd_mma(const float* __restrict__
         uint32_t h[4], l[4];
         split4(x, h, l);
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) gemm_step(acc[nt], h, l, sb, ks * 8, warp * 16 + nt * 8, g, t);
+        for (int nt = 0; nt < 2; ++nt) gemm_step(acc[nt], accs[nt], h, l, sb, ks * 8, warp * 16 + nt * 8, g, t);
       }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] += accs[nt][i];
       const int rA = tile * 16 + g, rB = rA + 8;
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -603,10 +633,15 @@ static int mma_grid(int B, int ctas_per_sm) {
 }
 
 int tlsan_launch_dense_fwd(const float* dense, float* scratch, int B, cudaStream_t st) {
-  const int ntile16 = (B + 15) / 16;
-  int gg = (ntile16 + 3) / 4;
-  if (gg > tlsan_num_sms() * 2) gg = tlsan_num_sms() * 2;   // one resident wave: the B image is built once per CTA
-  tlsan_launch_k(k_dense_fwd_mma, dim3(gg), dim3(256), 0, st, dense, scratch, B);
+  const int ntile = (B + DF_ROWS - 1) / DF_ROWS;
+  const int gg = ntile < tlsan_num_sms() * 2 ? ntile : tlsan_num_sms() * 2;   // one resident wave: the B image is built once per CTA
+  const size_t smem = sizeof(SmemGemm) + 256 + 2 * DF_ROWS * TILE_LD * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_dense_fwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tlsan_launch_k(k_dense_fwd_mma, dim3(gg), dim3(256), smem, st, dense, scratch, B);
   TLSAN_CHECK_LAUNCH("k_dense_fwd_mma");
   return TLSAN_OK;
 }

@@ -546,7 +546,9 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
       const unsigned char* mr = ring(n);                        // this round's metadata: {id, crow, P*hist_t, hist_t}, rank
       const int* pos = reinterpret_cast<const int*>(mr + 256);
       float* ru = a.rows_u + (size_t)it0.b * a.PU + 32;
-      float dtau_l = 0.f;                                       // lane j collects d tau of token r0 + j
+      // d tau of the round's tokens: lane q < 16 collects token 2q (first of tile q), lane 16 + q token 2q + 1
+      float dtau_l = 0.f;
+      const bool upper = L.lane >= 16;
       for (int j = 0; j < cnt; j += 2) {
         const bool okB = j + 1 < cnt;
         const float tA = tau[j], tB = okB ? tau[j + 1] : 0.f;
@@ -559,22 +561,29 @@ __global__ void __launch_bounds__(PF_THREADS, KIND == 1 ? 3 : 2) k_pf_long(const
         const float rA0 = dx[0] * tA, rA1 = dx[1] * tA;
         sq_acc = fmaf(rA0, rA0, sq_acc); sq_acc = fmaf(rA1, rA1, sq_acc);
         st2(a.rows_i + (size_t)pos[j] * 64 + L.f0, rA0, rA1);
-        const float dtA = warp_sum_f(fmaf(dx[0], eA.x, dx[1] * eA.y));
-        if (L.lane == j) dtau_l = dtA;
         if (okB) {
           const float rB0 = dx[2] * tB, rB1 = dx[3] * tB;
           sq_acc = fmaf(rB0, rB0, sq_acc); sq_acc = fmaf(rB1, rB1, sq_acc);
           st2(a.rows_i + (size_t)pos[j + 1] * 64 + L.f0, rB0, rB1);
-          const float dtB = warp_sum_f(fmaf(dx[2], eB.x, dx[3] * eB.y));
-          if (L.lane == j + 1) dtau_l = dtB;
         }
+        // both dot products in ONE butterfly: the halves of the warp swap the partial they do not keep, then the
+        // lower half sums token A's 32 partials and the upper half token B's (5 shuffles instead of 10; eB = 0 and
+        // dx[2..3] = 0 without a second token)
+        const float pA = fmaf(dx[0], eA.x, dx[1] * eA.y), pB = fmaf(dx[2], eB.x, dx[3] * eB.y);
+        float v = (upper ? pB : pA) + __shfl_xor_sync(0xffffffffu, upper ? pA : pB, 16);
+#pragma unroll
+        for (int o2 = 8; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if ((L.lane & 15) == (j >> 1)) dtau_l = v;
       }
-      if (L.lane < cnt) {
-        const int4 m = reinterpret_cast<const int4*>(mr)[L.lane];
-        ggamma = fmaf(dtau_l, __int_as_float(m.z), ggamma);    // d gamma += d tau * P[u,t] hist_t
-        const float dp = dtau_l * gamma * __int_as_float(m.w); // d usert_emb[u, t] = d tau * gamma * hist_t
-        sq_acc = fmaf(dp, dp, sq_acc);
-        ru[it0.r0 + L.lane] = dp;
+      {
+        const int tok = 2 * (L.lane & 15) + (upper ? 1 : 0);
+        if (tok < cnt) {
+          const int4 m = reinterpret_cast<const int4*>(mr)[tok];
+          ggamma = fmaf(dtau_l, __int_as_float(m.z), ggamma);  // d gamma += d tau * P[u,t] hist_t
+          const float dp = dtau_l * gamma * __int_as_float(m.w); // d usert_emb[u, t] = d tau * gamma * hist_t
+          sq_acc = fmaf(dp, dp, sq_acc);
+          ru[it0.r0 + tok] = dp;
+        }
       }
       if (it0.r0 + PF_R >= it0.ell)
         for (int tt = max(it0.ell, 0) + L.lane; tt < a.PU - 32; tt += 32) ru[tt] = 0.f;

@@ -19,19 +19,20 @@ struct KeySrc {
   int B, L, S, spsh, NI, NC, NR;
   const int *u, *cand, *c, *sl, *sl_new, *hist_i, *hist_i_new;
 };
-__device__ __forceinline__ int occ_key(const KeySrc& k, long long g) {
-  const int b = (int)(g >> k.spsh), j = (int)(g & ((1 << k.spsh) - 1));
-  const int LS = k.L + k.S;
-  int key = TLSAN_INVALID_KEY;                      // also the padding slots j >= L+S+3
-  if (j < LS) {                                     // a history slot: one length load (warp-uniform when SP >= 32), one id
-    const bool lng = j < k.L;
-    const int jj = lng ? j : j - k.L;
-    if (jj < __ldg((lng ? k.sl : k.sl_new) + b))
-      key = __ldg((lng ? k.hist_i + (size_t)b * k.L : k.hist_i_new + (size_t)b * k.S) + jj);
-  } else if (j <= LS + 2) {                         // candidate | u_cate | user
-    const int q = j - LS;
-    key = __ldg((q == 0 ? k.cand : q == 1 ? k.c : k.u) + b) + (q == 0 ? 0 : q == 1 ? k.NI : k.NI + k.NC);
-  }
+// Branch-free on purpose (selects + one or two loads): the divergent five-way version was ~100 instructions per key
+// and most of the instructions of both pass-0 kernels.  g < B * SP < 2^31 (check_dims).
+__device__ __forceinline__ int occ_key(const KeySrc& k, int g) {
+  const int b = g >> k.spsh, j = g & ((1 << k.spsh) - 1);
+  const int LS = k.L + k.S, q = j - LS;               // q = 0 candidate | 1 u_cate | 2 user ; padding slots beyond
+  const bool lng = j < k.L, hist = j < LS, scal = (unsigned)q <= 2u;
+  const int jj = lng ? j : j - k.L;
+  const int lim = hist ? __ldg((lng ? k.sl : k.sl_new) + b) : 0;
+  const bool hv = hist && jj < lim;                   // a real history / session entry
+  const int* hp = (lng ? k.hist_i : k.hist_i_new) + (size_t)b * (lng ? k.L : k.S) + jj;
+  const int* sp = (q == 0 ? k.cand : q == 1 ? k.c : k.u) + b;
+  const int add = hv || q == 0 ? 0 : q == 1 ? k.NI : k.NI + k.NC;
+  int key = TLSAN_INVALID_KEY;
+  if (hv || scal) key = __ldg(hv ? hp : sp) + add;
   // ids are range-checked when a batch is staged; a batch buffer that was freed and reused while a presort
   // announced for it was still queued must not turn into out-of-range segment writes either
   if ((unsigned)key >= (unsigned)k.NR) key = TLSAN_INVALID_KEY;
@@ -51,7 +52,7 @@ __device__ __forceinline__ void load_keys(const int* __restrict__ keys, const Ke
 #pragma unroll
   for (int it = 0; it < SORT_KPL; ++it) {
     const long long idx = wbase + it * 32 + lane;
-    k[it] = idx < n ? (FROM_BATCH ? occ_key(src, idx) : keys[idx]) : TLSAN_INVALID_KEY;
+    k[it] = idx < n ? (FROM_BATCH ? occ_key(src, (int)idx) : keys[idx]) : TLSAN_INVALID_KEY;
   }
 }
 
