@@ -15,7 +15,7 @@
 #define TLSAN_PART_SUMSQ (TLSAN_DENSE_PAD + 1)
 #define TLSAN_PART 4456
 #define TLSAN_SCR 6            // 64-float slots per sample in scratch: do_long | o_long | max | 1/den | dz | z
-#define TLSAN_SORT_CTA_KEYS 4096  // keys per CTA in one radix pass (16 warps x 256)
+#define TLSAN_SORT_CTA_KEYS 5120  // keys per CTA in one radix pass (16 warps x 320)
 
 void tlsan_set_error(const char* fmt, ...);
 

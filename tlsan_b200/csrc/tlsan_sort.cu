@@ -39,12 +39,13 @@ __device__ __forceinline__ int occ_key(const KeySrc& k, int g) {
   return key;
 }
 
-// Radix pass geometry: a CTA of 16 warps owns TLSAN_SORT_CTA_KEYS = 4096 consecutive keys; a warp
-// owns 256 of them, loaded up front as 8 coalesced loads per lane (so the serial ranking loop
+// Radix pass geometry: a CTA of 16 warps owns TLSAN_SORT_CTA_KEYS = 5120 consecutive keys; a warp
+// owns 320 of them, loaded up front as 10 coalesced loads per lane (so the serial ranking loop
 // below runs from registers).  Histograms are kept per CTA: hist[digit][cta].
 #define SORT_WARPS 16
-#define SORT_KPL 8     // keys per lane
+#define SORT_KPL 10    // keys per lane: 2 M occurrence slots (B 65 536 x 32) = 410 CTAs, one resident wave at 3 CTAs per SM
 #define SORT_KPW (32 * SORT_KPL)
+static_assert(SORT_WARPS * SORT_KPW == TLSAN_SORT_CTA_KEYS, "workspace layout and radix pass disagree on the CTA tile");
 
 template <bool FROM_BATCH>
 __device__ __forceinline__ void load_keys(const int* __restrict__ keys, const KeySrc& src, long long n,
@@ -98,20 +99,25 @@ __global__ void __launch_bounds__(256) k_radix_scan_rows(int* __restrict__ hist,
 
 // One pass = count + rank in ONE sweep over the warp's keys: in index order a key's rank among the warp's keys of the
 // same digit is (matching keys seen in earlier iterations) + (matching lower lanes of this iteration); the running
-// count per digit lives in the warp's shared-memory row and ends up as the warp's digit histogram.  The CTA then
-// turns the 16 histograms into start offsets (digit base + this CTA's base inside the digit + lower warps) and every
-// lane scatters its 8 keys from registers with nothing but one shared-memory read in between -- all stores of a lane
-// are in flight together.  (The first version counted with shared-memory atomics, ranked in a second sweep with a
-// dependent read-modify-write per iteration and loaded the values inside that loop: 34 / 24 us per pass.)
+// count per digit lives in the warp's shared-memory row and ends up as the warp's digit histogram.  The CTA turns the
+// 16 histograms into offsets, the keys are re-ordered by digit INSIDE the CTA through shared memory, and thread i then
+// writes the i-th key of that order: keys of one digit go to consecutive output positions, so the global stores are
+// runs of ~6 (pass 0) / ~17 (pass 1) keys instead of single 4-byte writes to as many sectors (the scattered writes,
+// 2.2 M sectors per pass, bounded the first versions: 34 / 24 us per pass).
 template <bool FROM_BATCH>
 __global__ void __launch_bounds__(32 * SORT_WARPS, FROM_BATCH ? 3 : 2) k_radix_scatter(
     const int* __restrict__ keys_in, const KeySrc src, const int* __restrict__ vals_in, long long ncap,
     const int* __restrict__ nvalid, int* __restrict__ nvalid_out, int shift, int nblk, const int* __restrict__ hist,
     const int* __restrict__ tot, int* __restrict__ keys_out, int* __restrict__ vals_out,
     int* __restrict__ inv_out /* last pass only: occurrence id -> sorted rank */) {
-  __shared__ int off[SORT_WARPS][256];
-  __shared__ int dbase[256];
-  __shared__ int wtot[8];
+  constexpr int TILE = SORT_WARPS * SORT_KPW;
+  __shared__ int offkey[TILE > SORT_WARPS * 256 ? TILE : SORT_WARPS * 256];
+  int (*off)[256] = reinterpret_cast<int (*)[256]>(offkey);   // per-warp digit counts -> offsets; then the staged keys
+  __shared__ int sval[TILE];
+  __shared__ int gstart[256];                 // output position of the CTA's first key of digit d
+  __shared__ int cstart[257];                 // position of that key in the CTA's digit-ordered tile; [256] = #keys
+  __shared__ int wtot[8], wtot2[8];
+  int* skey = offkey;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n = nvalid ? (long long)*nvalid : ncap;
   // a CTA past the valid keys (later passes run on the compacted list) has nothing to rank or write
@@ -152,39 +158,58 @@ __global__ void __launch_bounds__(32 * SORT_WARPS, FROM_BATCH ? 3 : 2) k_radix_s
     if (act && below == 0) off[warp][digit] = seen + __popc(m);
     __syncwarp();
   }
-  if (threadIdx.x < 256) {  // exclusive scan of the 256 digit totals (8 warps x 32)
-    int x = my_tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) wtot[warp] = x;
-    dbase[threadIdx.x] = x - my_tot;
-  }
   __syncthreads();
-  if (threadIdx.x < 256) {  // counts -> start offsets: digit base + CTA base in the digit + lower warps
-    int pre = 0;
-    for (int w = 0; w < warp; ++w) pre += wtot[w];
-    if (blockIdx.x == 0 && threadIdx.x == 255) *nvalid_out = pre + dbase[255] + my_tot;
-    int run = pre + dbase[threadIdx.x] + my_hist;
+  int ctot = 0;
+  if (threadIdx.x < 256) {  // thread d: the warps' counts of digit d -> offsets inside the CTA's run of d
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w) {
       const int c = off[w][threadIdx.x];
-      off[w][threadIdx.x] = run;
-      run += c;
+      off[w][threadIdx.x] = ctot;
+      ctot += c;
     }
+    // two exclusive scans over the 256 digits (8 warps x 32): the global digit totals and this CTA's
+    int x = my_tot, y = ctot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int xs = __shfl_up_sync(0xffffffffu, x, o), ys = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) { x += xs; y += ys; }
+    }
+    if (lane == 31) { wtot[warp] = x; wtot2[warp] = y; }
+    gstart[threadIdx.x] = x - my_tot;
+    cstart[threadIdx.x] = y - ctot;
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    int pre = 0, pre2 = 0;
+    for (int w = 0; w < warp; ++w) { pre += wtot[w]; pre2 += wtot2[w]; }
+    if (blockIdx.x == 0 && threadIdx.x == 255) *nvalid_out = pre + gstart[255] + my_tot;
+    gstart[threadIdx.x] += pre + my_hist;      // digit base + this CTA's base inside the digit
+    cstart[threadIdx.x] += pre2;
+    if (threadIdx.x == 255) cstart[256] = cstart[255] + ctot;
   }
   __syncthreads();
 #pragma unroll
+  for (int it = 0; it < SORT_KPL; ++it) {      // position inside the CTA's digit-ordered tile
+    const int digit = (k[it] >> shift) & 255;
+    if (k[it] != TLSAN_INVALID_KEY) rk[it] += cstart[digit] + off[warp][digit];
+  }
+  __syncthreads();                             // the offsets are consumed: their storage becomes the key stage
+#pragma unroll
   for (int it = 0; it < SORT_KPL; ++it) {
     if (k[it] != TLSAN_INVALID_KEY) {
-      const int pos = off[warp][(k[it] >> shift) & 255] + rk[it];
-      const int val = FROM_BATCH ? (int)(wbase + it * 32 + lane) : v[it];
-      keys_out[pos] = k[it];
-      vals_out[pos] = val;
-      if (inv_out) inv_out[val] = pos;
+      skey[rk[it]] = k[it];
+      sval[rk[it]] = FROM_BATCH ? (int)(wbase + it * 32 + lane) : v[it];
     }
+  }
+  __syncthreads();
+  const int total = cstart[256];
+  for (int i = threadIdx.x; i < total; i += 32 * SORT_WARPS) {
+    const int key = skey[i], val = sval[i];
+    const int digit = (key >> shift) & 255;
+    const int pos = gstart[digit] + (i - cstart[digit]);
+    keys_out[pos] = key;
+    vals_out[pos] = val;
+    if (inv_out) inv_out[val] = pos;
   }
 }
 
