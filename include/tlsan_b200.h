@@ -14,9 +14,11 @@
  *   - return 0 on success, a negative TLSAN_E_* code otherwise; `tlsan_last_error()` returns
  *     a thread-local description; no C++ exception crosses the ABI;
  *   - indices are int32, values fp32; embedding rows are 128 B and must be 16-B aligned.
- * The small attention weights are mirrored into one __constant__ bank per process (CUDA-core variant only) and the
- * internal streams / presort registry are per process: concurrent train steps from two host threads on one device
- * must be serialised by the caller.
+ * The internal streams / presort registry are per process and guarded by one lock: train-step entry points called from
+ * several host threads enqueue one at a time (their kernels still overlap on the callers' streams).  The small
+ * attention weights of the CUDA-core variant (TLSAN_FUSED_IMPL=ffma, not the default) are mirrored into one
+ * __constant__ bank per process: two models using THAT variant concurrently on one device must be serialised by
+ * the caller.
  */
 #ifndef TLSAN_B200_H
 #define TLSAN_B200_H

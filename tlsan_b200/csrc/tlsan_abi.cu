@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "tlsan_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -80,6 +81,7 @@ static SideStream* side_stream() {
   return &s;
 }
 static bool g_prof_overlap = false;   // the recorded steps ran the sort on the side stream
+static std::recursive_mutex g_api_mutex;   // guards the process-global state of the stateful entry points
 
 // Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
 // one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
@@ -244,6 +246,9 @@ static char* ws_base(void* workspace) {
 
 static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_batch_t* b, void* workspace,
                            size_t workspace_bytes, float* flat, bool with_tsq, const tlsan_next_t* next, void* stream) {
+  // the side streams, the presort registry and the phase recorder are per-process: host threads driving different
+  // models enqueue their steps one at a time (the kernels themselves still overlap on their streams)
+  std::lock_guard<std::recursive_mutex> guard(g_api_mutex);
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
@@ -368,6 +373,7 @@ static int step_grads_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, co
 static int apply_flat_impl(const tlsan_dims_t* dims, const tlsan_params_t* p, const float* flat, float lr, float reg,
                            float clip_norm, void* workspace, size_t workspace_bytes, float* stats, bool have_tsq,
                            void* stream, const tlsan_opt_t* opt = nullptr) {
+  std::lock_guard<std::recursive_mutex> guard(g_api_mutex);
   int rc;
   if ((rc = check_dims(dims))) return rc;
   if ((rc = check_params(p, true))) return rc;
