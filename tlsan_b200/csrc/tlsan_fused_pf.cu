@@ -298,11 +298,11 @@ struct SoftL2 {
 
 // backward of one tile: tile_bwd of tlsan_mma_common.cuh with the softmax exponent in the log2 domain
 // (w.W2 / w.b2 carry log2(e); wt holds the UNscaled transposed maps for d pre / d x)
-__device__ __forceinline__ void tile_bwd_l2(const float (&x)[4], bool okB, const float (&o)[2], const float (&kf)[2],
-                                            const float (&nmx)[2], const FwaW& w, const FwaWT& wt, int lane,
-                                            float (&dx)[4], FwaGrad& G) {
-  float m1[4], m2[4];
-  tile_maps(x, w, m1, m2);
+// core: the maps m1 / m2 of the tile are given (recomputed by tile_bwd_l2, or kept from the forward when the whole
+// sequence was one tile)
+__device__ __forceinline__ void tile_bwd_core(const float (&x)[4], const float (&m1)[4], const float (&m2)[4], bool okB,
+                                              const float (&o)[2], const float (&kf)[2], const float (&nmx)[2],
+                                              const FwaWT& wt, int lane, float (&dx)[4], FwaGrad& G) {
   float ado[4], dm2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -338,6 +338,14 @@ __device__ __forceinline__ void tile_bwd_l2(const float (&x)[4], bool okB, const
       }
     }
   }
+}
+
+__device__ __forceinline__ void tile_bwd_l2(const float (&x)[4], bool okB, const float (&o)[2], const float (&kf)[2],
+                                            const float (&nmx)[2], const FwaW& w, const FwaWT& wt, int lane,
+                                            float (&dx)[4], FwaGrad& G) {
+  float m1[4], m2[4];
+  tile_maps(x, w, m1, m2);
+  tile_bwd_core(x, m1, m2, okB, o, kf, nmx, wt, lane, dx, G);
 }
 
 // fixed-order reduction of a warp's weight-gradient accumulators into red[0..143]
@@ -715,10 +723,21 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
     };
     // ================= short-term FWA forward over [z ; e(hist_i_new)] (model.py:350-364)
     SoftL2 ss; ss.init();
-    for (int k = 0; k < ntok; k += 2) {
+    // the first tile ([z ; first session item]: the WHOLE sequence of 87 % of the samples) keeps its inputs and maps
+    // in registers for the backward pass below; later tiles are recomputed there
+    float x0[4], m10[4], m20[4];
+    {
+      const bool okB = 1 < ntok;
+      x0[0] = z[0]; x0[1] = z[1];
+      if (okB) { const float2 e = item_x(0); x0[2] = e.x; x0[3] = e.y; } else { x0[2] = 0.f; x0[3] = 0.f; }
+      tile_maps(x0, w, m10, m20);
+      if (!okB) { m20[2] = -INFINITY; m20[3] = -INFINITY; }
+      ss.push2(m20, x0);
+    }
+    for (int k = 2; k < ntok; k += 2) {
       const bool okB = k + 1 < ntok;
       float x[4];
-      if (k == 0) { x[0] = z[0]; x[1] = z[1]; } else { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
+      { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
       if (okB) { const float2 e = item_x(k); x[2] = e.x; x[3] = e.y; } else { x[2] = 0.f; x[3] = 0.f; }
       float m1[4], m2[4];
       tile_maps(x, w, m1, m2);
@@ -754,18 +773,25 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
     // ---- short-term FWA backward, d v = du
     const float kf[2] = {inv_s[0] * du[0], inv_s[1] * du[1]};
     const float nmx[2] = {-ss.mx[0], -ss.mx[1]};
-    float dz[2] = {0.f, 0.f};
-    for (int k = 0; k < ntok; k += 2) {
+    float dz[2];
+    {
+      const bool okB = 1 < ntok;
+      float dx[4];
+      tile_bwd_core(x0, m10, m20, okB, v, kf, nmx, wt, L.lane, dx, G);
+      dz[0] = dx[0]; dz[1] = dx[1];
+      if (okB) {
+        sq_acc = fmaf(dx[2], dx[2], sq_acc); sq_acc = fmaf(dx[3], dx[3], sq_acc);
+        st2(slot_row(2), dx[2], dx[3]);
+      }
+    }
+    for (int k = 2; k < ntok; k += 2) {
       const bool okB = k + 1 < ntok;
       float x[4], dx[4];
-      if (k == 0) { x[0] = z[0]; x[1] = z[1]; } else { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
+      { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
       if (okB) { const float2 e = item_x(k); x[2] = e.x; x[3] = e.y; } else { x[2] = 0.f; x[3] = 0.f; }
       tile_bwd_l2(x, okB, v, kf, nmx, w, wt, L.lane, dx, G);
-      if (k == 0) { dz[0] = dx[0]; dz[1] = dx[1]; }
-      else {
-        sq_acc = fmaf(dx[0], dx[0], sq_acc); sq_acc = fmaf(dx[1], dx[1], sq_acc);
-        st2(slot_row(2 + k - 1), dx[0], dx[1]);
-      }
+      sq_acc = fmaf(dx[0], dx[0], sq_acc); sq_acc = fmaf(dx[1], dx[1], sq_acc);
+      st2(slot_row(2 + k - 1), dx[0], dx[1]);
       if (okB) {
         sq_acc = fmaf(dx[2], dx[2], sq_acc); sq_acc = fmaf(dx[3], dx[3], sq_acc);
         st2(slot_row(2 + k), dx[2], dx[3]);
