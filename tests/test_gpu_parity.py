@@ -100,7 +100,9 @@ def test_train_step_matches_committed_golden(dm):
 @pytest.mark.parametrize("B,L,S,full,dup", [
     (1, 10, 1, False, False), (33, 10, 3, False, False), (64, 10, 18, True, False),
     (50, 1, 1, True, False), (40, 90, 5, False, False), (32, 90, 2, True, False),
-    (257, 10, 4, False, True), (100, 37, 7, False, True)])
+    (257, 10, 4, False, True), (100, 37, 7, False, True),
+    # occurrence-slot counts around the radix tile (5 120 slots = 160 samples of 32 slots) and the forward's claim size
+    (159, 10, 18, False, False), (160, 10, 18, True, False), (161, 10, 18, False, True), (321, 10, 18, False, False)])
 def test_train_step_edge_shapes(B, L, S, full, dup):
     rng = np.random.default_rng(B * 1000 + L)
     NU, NI, NC = 50, 301, 7
