@@ -53,7 +53,7 @@ static bool use_mma() { return fused_impl() >= 1; }
 // The radix sort of the occurrence keys only feeds the kernels that WRITE gradient rows (short-term kernel
 // onwards), so it runs on a side stream beside the long-term forward and the dense GEMM (fork / join with
 // events; works under stream capture too).  TLSAN_SORT_OVERLAP=0 keeps everything on the caller's stream.
-struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr; };
+struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, part = nullptr, dpx = nullptr; };
 static SideStream* side_stream() {
   static SideStream per_dev[64];
   static int enabled = -1;
@@ -72,6 +72,7 @@ static SideStream* side_stream() {
         cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, lo) != cudaSuccess ||   // presort: fills gaps
         cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.part, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.dpx, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
       s.st = nullptr;
@@ -487,8 +488,13 @@ int tlsan_dp_exchange(const tlsan_dims_t* dims, const tlsan_params_t* p, void* c
           "tlsan_dp_exchange needs emb | usert | item_b in one buffer (see header)");
   const TlsanWs w = tlsan_ws_layout(*dims);
   REQUIRE(workspace_bytes >= w.total + 256, TLSAN_E_WORKSPACE, "workspace too small");
+  std::lock_guard<std::recursive_mutex> guard(g_api_mutex);
+  // the small exchange (dense gradients, norm partials -> clip scale) runs on the side stream, behind k_finalize1 of
+  // the step and beside its segmented row reduce
+  SideStream* side = use_mma() ? side_stream() : nullptr;
   rc = tlsan_launch_dp_exchange(*dims, *p, w, ws_base(workspace), reinterpret_cast<float* const*>(arenas), rank, world,
-                                epoch, lr, reg, clip_norm, stats, (cudaStream_t)stream);
+                                epoch, lr, reg, clip_norm, stats, side ? side->st : nullptr, side ? side->dpx : nullptr,
+                                (cudaStream_t)stream);
   tlsan_profile_mark(TLSAN_PHASE_APPLY, (cudaStream_t)stream);
   return rc;
 }

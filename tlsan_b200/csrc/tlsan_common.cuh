@@ -176,7 +176,7 @@ int tlsan_launch_apply_replicated(const tlsan_dims_t& d, const tlsan_params_t& p
 size_t tlsan_dp_arena_bytes_impl(const tlsan_dims_t& d, int world);
 int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                              float* const* arenas, int rank, int world, int epoch, float lr, float reg, float clip,
-                             float* stats, cudaStream_t st);
+                             float* stats, cudaStream_t side, cudaEvent_t side_done, cudaStream_t st);
 int tlsan_launch_label_rank(const tlsan_dims_t& d, const tlsan_params_t& p, const float* ut, const int32_t* label,
                             int32_t* rank, cudaStream_t st);
 size_t tlsan_rank_ws_bytes(const tlsan_dims_t& d);

@@ -660,26 +660,34 @@ __global__ void __launch_bounds__(256) k_dp_reduce_cate(int NI, float* __restric
   dp_signal_when_grid_done(flags + 16, flags + 0, epoch);
 }
 
-// dense gradients + loss / norm partials summed over ranks (fixed order) into the partial-row layout k_finalize2 reads
-__global__ void __launch_bounds__(1024) k_dp_dense_sum(DpPeers peers, DpLayout y, long long f_dgrad, int world, int epoch,
-                                                       float* __restrict__ dtot, int* __restrict__ err,
+// dense gradients + loss / norm partials summed over ranks (fixed order) into the partial-row layout k_finalize2 reads.
+// Runs EARLY, on the library's side stream right behind k_finalize1 (which produced this rank's partials) and beside the
+// segmented row reduce: block 0 publishes "partials ready" (flag 2), every block waits for the peers' flag 2, then one
+// element per thread with every peer's word in flight together (small CTAs: they must find room beside the row reduce).  The clip scale is therefore known before the
+// gradient rows are complete, and the two single-CTA kernels (this + k_finalize2) leave the critical path.
+__global__ void __launch_bounds__(256) k_dp_dense_sum(DpPeers peers, DpLayout y, long long f_dgrad, int rank, int world,
+                                                       int epoch, float* __restrict__ dtot, int* __restrict__ err,
                                                        long long timeout_ns, float* __restrict__ stats) {
-  if (!dp_wait(peers, y.flat_count + y.chunk, 0, world, epoch, err, timeout_ns)) {
-    if (threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int* mine = reinterpret_cast<int*>(peers.arena[rank] + y.flat_count + y.chunk) + 2;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(mine), "r"(epoch) : "memory");
+  }
+  if (!dp_wait(peers, y.flat_count + y.chunk, 2, world, epoch, err, timeout_ns)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
     return;
   }
-  for (int e = threadIdx.x; e < TLSAN_PART; e += 1024) {
-    if (e < TLSAN_DENSE_COUNT || e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ) {
-      float v[16];                       // every peer's word in flight together, then the fixed-order sum
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < TLSAN_PART && (e < TLSAN_DENSE_COUNT || e == TLSAN_PART_LOSS || e == TLSAN_PART_SUMSQ)) {
+    float v[16];
 #pragma unroll
-      for (int p = 0; p < 16; ++p)
-        if (p < world) v[p] = ld_peer1(peers.arena[p] + f_dgrad + e);
-      float s = 0.f;
+    for (int p = 0; p < 16; ++p)
+      if (p < world) v[p] = ld_peer1(peers.arena[p] + f_dgrad + e);
+    float s = 0.f;
 #pragma unroll
-      for (int p = 0; p < 16; ++p)
-        if (p < world) s += v[p];
-      dtot[e] = s;
-    }
+    for (int p = 0; p < 16; ++p)
+      if (p < world) s += v[p];
+    dtot[e] = s;
   }
 }
 
@@ -704,33 +712,54 @@ __device__ __forceinline__ float4 dp_grad4(const float* __restrict__ flat, long 
   return ld_peer4(flat + f_gb + (e - y.off_itemb));                                            // item_b
 }
 
-// slice `rank` of the table part of wflat: sum over ranks, update, publish; then flag 2
+// slice `rank` of the table part of wflat: sum over ranks, update, publish; then flag 2.
+// W = compiled rank count (2, 4, 8, 16 >= world): U = 8 / W elements per thread and sweep, i.e. always ~8 peer reads
+// (float4) in flight per thread before the first use -- a peer read is a 1-2 us round trip, and the volatile loads are
+// not pipelined across loop iterations by the compiler (one element per sweep: 35 us for the whole table on one GPU).
+template <int W>
 __global__ void __launch_bounds__(256) k_dp_apply_slice(DpPeers peers, DpLayout y, int rank, int world, int NIC, int NU,
                                                         int L, int PU, long long f_gb, long long f_gu,
                                                         float* __restrict__ wflat, float lr, float reg,
-                                                        const float* __restrict__ stats, int epoch,
-                                                        const int* __restrict__ err) {
-  if (*reinterpret_cast<const volatile int*>(err)) return;      // a wait timed out: leave the weights untouched
+                                                        float* __restrict__ stats, int epoch,
+                                                        int* __restrict__ err, long long timeout_ns) {
+  constexpr int U = W >= 8 ? 1 : 8 / W;
+  // every peer's gradient rows complete (flag 1 of k_dp_reduce_cate)?  A timed-out wait leaves the weights untouched.
+  if (!dp_wait(peers, y.flat_count + y.chunk, 0, world, epoch, err, timeout_ns)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
+    return;
+  }
   const float scale = stats[TLSAN_STAT_SCALE];
   const long long lo = (long long)rank * y.chunk, hi = min(lo + y.chunk, y.n_tab);
   float* wnew = peers.arena[rank] + y.flat_count;
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += stride) {
-    // all ranks' words in flight together (a peer read is ~1-2 us: never one after the other), then a fixed-order sum
-    float4 v[16];
+  const long long nthr4 = (long long)gridDim.x * blockDim.x * 4;
+  for (long long e0 = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e0 < hi; e0 += U * nthr4) {
+    float4 v[U][W], w[U];
 #pragma unroll
-    for (int p = 0; p < 16; ++p)
-      if (p < world) v[p] = dp_grad4(peers.arena[p], e, NIC, NU, L, PU, f_gb, f_gu, y);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * nthr4;
+      if (e < hi) {
 #pragma unroll
-    for (int p = 0; p < 16; ++p)
-      if (p < world) { g.x += v[p].x; g.y += v[p].y; g.z += v[p].z; g.w += v[p].w; }
-    const float r = e < y.off_itemb ? reg : 0.f;               // item_b carries no L2 term (model.py:164-169)
-    float4 w = *reinterpret_cast<float4*>(wflat + e);
-    w.x -= lr * ((g.x + r * w.x) * scale); w.y -= lr * ((g.y + r * w.y) * scale);
-    w.z -= lr * ((g.z + r * w.z) * scale); w.w -= lr * ((g.w + r * w.w) * scale);
-    *reinterpret_cast<float4*>(wflat + e) = w;
-    *reinterpret_cast<float4*>(wnew + (e - lo)) = w;
+        for (int p = 0; p < W; ++p)
+          if (p < world) v[u][p] = dp_grad4(peers.arena[p], e, NIC, NU, L, PU, f_gb, f_gu, y);
+        w[u] = *reinterpret_cast<const float4*>(wflat + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * nthr4;
+      if (e < hi) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);         // fixed rank order: identical on every rank
+#pragma unroll
+        for (int p = 0; p < W; ++p)
+          if (p < world) { g.x += v[u][p].x; g.y += v[u][p].y; g.z += v[u][p].z; g.w += v[u][p].w; }
+        const float r = e < y.off_itemb ? reg : 0.f;         // item_b carries no L2 term (model.py:164-169)
+        float4 x = w[u];
+        x.x -= lr * ((g.x + r * x.x) * scale); x.y -= lr * ((g.y + r * x.y) * scale);
+        x.z -= lr * ((g.z + r * x.z) * scale); x.w -= lr * ((g.w + r * x.w) * scale);
+        *reinterpret_cast<float4*>(wflat + e) = x;
+        *reinterpret_cast<float4*>(wnew + (e - lo)) = x;
+      }
+    }
   }
   int* flags = reinterpret_cast<int*>(peers.arena[rank] + y.flat_count + y.chunk);
   dp_signal_when_grid_done(flags + 17, flags + 1, epoch);
@@ -744,45 +773,63 @@ __global__ void __launch_bounds__(256) k_dp_gather(DpPeers peers, DpLayout y, in
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[TLSAN_STAT_DP_ERR] = 1.f;
     return;
   }
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (int p = 0; p < world; ++p) {
-    if (p == rank) continue;
-    const long long lo = (long long)p * y.chunk, hi = min(lo + y.chunk, y.n_tab);
-    const float* src = peers.arena[p] + y.flat_count;
-    for (long long e = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < hi; e += 4 * stride) {
-      float4 v[4];
+  // one pass over the (world - 1) foreign slices, 4 float4 loads in flight per thread
+  const long long c4 = y.chunk / 4, total = c4 * (world - 1);
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * nthr) {
+    float4 v[4];
+    long long dst[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (e + i * stride < hi) v[i] = ld_peer4(src + (e + i * stride - lo));
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (e + i * stride < hi) *reinterpret_cast<float4*>(wflat + e + i * stride) = v[i];
+    for (int q = 0; q < 4; ++q) {
+      const long long j = i + q * nthr;
+      dst[q] = -1;
+      if (j < total) {
+        const int pi = (int)(j / c4);
+        const int p = pi < rank ? pi : pi + 1;
+        const long long off = (j - (long long)pi * c4) * 4, e = (long long)p * y.chunk + off;
+        if (e < y.n_tab) { v[q] = ld_peer4(peers.arena[p] + y.flat_count + off); dst[q] = e; }
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (dst[q] >= 0) *reinterpret_cast<float4*>(wflat + dst[q]) = v[q];
   }
 }
 
 // `arenas[rank]` must be the buffer tlsan_step_grads wrote its flat gradients to
+// `side` / `side_done` (optional): the library's side stream -- ordered behind k_finalize1 of this step, NOT behind the
+// segmented row reduce -- and an event to record on it
 int tlsan_launch_dp_exchange(const tlsan_dims_t& d, const tlsan_params_t& p, const TlsanWs& w, char* ws,
                              float* const* arenas, int rank, int world, int epoch, float lr, float reg, float clip,
-                             float* stats, cudaStream_t st) {
+                             float* stats, cudaStream_t side, cudaEvent_t side_done, cudaStream_t st) {
   const DpLayout y = dp_layout(d, world);
   DpPeers peers;
   for (int i = 0; i < 16; ++i) peers.arena[i] = i < world ? arenas[i] : nullptr;
   float* flat = arenas[rank];
   int* flags = reinterpret_cast<int*>(flat + y.flat_count + y.chunk);
   int* err = flags + 8;
-  k_dp_reduce_cate<<<d.NC, 256, 0, st>>>(d.NI, flat + w.f_gi, p.cate_off, p.cate_items, flags, epoch);
-  TLSAN_CHECK_LAUNCH("k_dp_reduce_cate");
+  // (1) small exchange: dense gradients, loss and norm partials -> clip scale, dense parameters updated
+  cudaStream_t s1 = side ? side : st;
   float* dtot = reinterpret_cast<float*>(ws + w.part_a);          // the per-CTA partials are consumed by now
-  k_dp_dense_sum<<<1, 1024, 0, st>>>(peers, y, (long long)w.f_dgrad, world, epoch, dtot, err, dp_timeout_ns(), stats);
+  k_dp_dense_sum<<<(TLSAN_PART + 255) / 256, 256, 0, s1>>>(peers, y, (long long)w.f_dgrad, rank, world, epoch, dtot,
+                                                             err, dp_timeout_ns(), stats);
   TLSAN_CHECK_LAUNCH("k_dp_dense_sum");
   const float invB = 1.0f / (float)(d.B_global > 0 ? d.B_global : d.B);
-  k_finalize2<<<1, 1024, 0, st>>>(dtot, reinterpret_cast<float*>(ws + w.tsq), tsq_grid(), nullptr, 0, invB, lr, reg,
+  k_finalize2<<<1, 1024, 0, s1>>>(dtot, reinterpret_cast<float*>(ws + w.tsq), tsq_grid(), nullptr, 0, invB, lr, reg,
                                   clip, p.dense, stats, opt_args(nullptr, p.emb));
   TLSAN_CHECK_LAUNCH("k_finalize2");
-  k_dp_apply_slice<<<tlsan_num_sms() * 4, 256, 0, st>>>(peers, y, rank, world, d.NI + d.NC, d.NU, d.L, w.PU,
-                                                        (long long)w.f_gb, (long long)w.f_gu, p.emb, lr, reg, stats,
-                                                        epoch, err);
+  if (side) TLSAN_CHECK_CUDA(cudaEventRecord(side_done, side));
+  // (2) gradient rows: fold the category halves, publish (flag 1)
+  k_dp_reduce_cate<<<d.NC, 256, 0, st>>>(d.NI, flat + w.f_gi, p.cate_off, p.cate_items, flags, epoch);
+  TLSAN_CHECK_LAUNCH("k_dp_reduce_cate");
+  if (side) TLSAN_CHECK_CUDA(cudaStreamWaitEvent(st, side_done, 0));
+  // (3) reduce-scatter + update of this rank's slice (waits for every peer's flag 1), publish (flag 2); (4) all-gather
+#define DP_APPLY(Wc)                                                                                                   \
+  k_dp_apply_slice<Wc><<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, d.NI + d.NC, d.NU, d.L, w.PU,       \
+                                                            (long long)w.f_gb, (long long)w.f_gu, p.emb, lr, reg,      \
+                                                            stats, epoch, err, dp_timeout_ns())
+  if (world <= 2) DP_APPLY(2); else if (world <= 4) DP_APPLY(4); else if (world <= 8) DP_APPLY(8); else DP_APPLY(16);
+#undef DP_APPLY
   TLSAN_CHECK_LAUNCH("k_dp_apply_slice");
   k_dp_gather<<<tlsan_num_sms() * 2, 256, 0, st>>>(peers, y, rank, world, epoch, p.emb, err, dp_timeout_ns(), stats);
   TLSAN_CHECK_LAUNCH("k_dp_gather");
