@@ -87,7 +87,7 @@ static std::recursive_mutex g_api_mutex;   // guards the process-global state of
 // Pipelined steps: the occurrence sort of the NEXT batch is enqueued behind the backward kernels of the current
 // one, into the next step's workspace; that step (dims->reserved bit 1) waits for the event instead of sorting.
 // ev: ranks (inv) ready -- what the gradient-row writers wait for; ev_seg: segment bounds ready too (row reduce; the
-// last kernel of the presort); ev_part: balanced partition ready (long-term forward)
+// last kernel of the sort); ev_part: balanced partition of the short-term / backward kernels ready (end of the chain)
 struct Presort { char* ws = nullptr; cudaEvent_t ev = nullptr, ev_seg = nullptr, ev_part = nullptr; bool valid = false; };
 static Presort g_presort[32];
 // `avoid`: the entry the calling step is consuming -- its events are still to be waited on by kernels that step

@@ -13,8 +13,9 @@
 //     while round n is computed from buffer n % 2, the rows of round n+1 are in flight (16 lanes x 16 B per token,
 //     addresses from metadata that landed a round ago) and the metadata of round n+2 is being copied.  No load a
 //     tile depends on is issued less than one round of compute earlier.
-// Work is assigned statically (sample b -> warp b mod #warps): every per-warp partial sum is accumulated in a fixed
-// order, results are bit-identical from run to run.
+// Work assignment: the backward and short-term kernels take a balanced STATIC partition of the samples (k_part_*:
+// contiguous ranges of equal cost per warp), so every per-warp partial sum is accumulated in a fixed order and results
+// are bit-identical from run to run; the forward, whose outputs are all per sample, claims samples dynamically.
 //
 // Tile-level changes against tlsan_mma_common.cuh:
 //   * log2(e) is folded into W2 / b2 once per kernel: the softmax works in the log2 domain (no multiply per exp);
@@ -915,8 +916,9 @@ static int launch_pf_long(const FArgs& a, const void* meta, const void* part, in
   return TLSAN_OK;
 }
 
-// ctas_per_sm (forward): 3 fills the SM; 2 leaves room for the radix-sort kernels running beside it on the side stream
-// (the same ctas_per_sm must have been given to tlsan_launch_partition)
+// ctas_per_sm (forward): 3 fills the SM.  The samples are claimed dynamically, so CTAs that become resident late
+// (the sort kernels share the SMs) cost nothing; tlsan_launch_long_meta must have been given the same value (it
+// seeds the work counter with grid x warps x chunk).
 int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st) {
   return launch_pf_long<1>(a, meta, part, ctas_per_sm, nullptr, st);
 }
