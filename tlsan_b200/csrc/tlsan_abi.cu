@@ -199,7 +199,8 @@ int tlsan_score(const tlsan_dims_t* dims, const tlsan_params_t* p, const tlsan_b
 // scratch [B][TLSAN_SCR][64] + per-token metadata [B][L] x 16 B + the balanced partition, each 256-B aligned
 static size_t score_ws_bytes(const tlsan_dims_t* d) {
   return tlsan_align_up((size_t)d->B * TLSAN_SCR * 64 * sizeof(float), 256) +
-         tlsan_align_up((size_t)d->B * d->L * 16, 256) + tlsan_partition_bytes() + 512;
+         tlsan_align_up((size_t)d->B * d->L * 16, 256) + tlsan_align_up(tlsan_partition_bytes(), 256) +
+         tlsan_score_meta_bytes(d->B, d->S) + 512;
 }
 
 int tlsan_score_workspace_bytes(const tlsan_dims_t* dims, size_t* bytes) {

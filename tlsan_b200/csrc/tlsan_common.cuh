@@ -89,6 +89,7 @@ struct TlsanWs {
 };
 
 size_t tlsan_partition_bytes();
+size_t tlsan_score_meta_bytes(int B, int S);   // scoring-layout short-term metadata of tlsan_score_ws (tlsan_fused_pf.cu)
 
 static inline TlsanWs tlsan_ws_layout(const tlsan_dims_t& d) {
   TlsanWs w;

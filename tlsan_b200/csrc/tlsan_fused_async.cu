@@ -391,7 +391,7 @@ int tlsan_launch_long_fwd_mma(const FArgs& a, int ctas_per_sm, cudaStream_t st);
 int tlsan_overlap_ctas();
 int tlsan_launch_bwd_long_mma(const FArgs& a, int* grid_b, cudaStream_t st);
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
-                           cudaStream_t st);                                                     // tlsan_fused_pf.cu
+                           int score_ncand, cudaStream_t st);                                                     // tlsan_fused_pf.cu
 int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int* grid_a,
                           cudaStream_t st);
 int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
@@ -425,7 +425,7 @@ int tlsan_launch_fwd_bwd_async(const tlsan_dims_t& d, const tlsan_params_t& p, c
   // depends on the batch only: the caller computed it behind the sort (part_ready), or asks for it here (no side stream)
   (void)part_early;
   if (variant == 2 && !part_ready && (rc = tlsan_launch_partition(a, long_ctas, true, part, st))) return rc;
-  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, part, long_ctas, st))) return rc;
+  if (variant == 2 && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, part, long_ctas, 0, st))) return rc;
   if ((rc = variant == 2 ? tlsan_launch_long_fwd_pf(a, meta, part, long_ctas, st)
                          : hybrid ? tlsan_launch_long_fwd_mma(a, long_ctas, st) : launch_async<1>(a, nullptr, st)))
     return rc;

@@ -711,7 +711,10 @@ int tlsan_launch_score_mma(const tlsan_dims_t& d, const tlsan_params_t& p, const
 }
 
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
-                           cudaStream_t st);                                                     // tlsan_fused_pf.cu
+                           int score_ncand, cudaStream_t st);
+size_t tlsan_score_meta_bytes(int B, int S);
+int tlsan_launch_score_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int ncand,
+                          cudaStream_t st);                                                     // tlsan_fused_pf.cu
 int tlsan_launch_long_fwd_pf(const FArgs& a, const void* meta, const void* part, int ctas_per_sm, cudaStream_t st);
 int tlsan_launch_partition(const FArgs& a, int fwd_ctas, bool train, void* part, cudaStream_t st);
 size_t tlsan_partition_bytes();
@@ -726,9 +729,13 @@ int tlsan_launch_score_ws(const tlsan_dims_t& d, const tlsan_params_t& p, const 
   if (use_ws < 0) { const char* e = getenv("TLSAN_FUSED_IMPL"); use_ws = (e && *e && strcmp(e, "pf") != 0) ? 0 : 1; }
   void* meta = reinterpret_cast<char*>(scratch) + tlsan_align_up((size_t)d.B * TLSAN_SCR * 64 * sizeof(float), 256);
   void* part = reinterpret_cast<char*>(meta) + tlsan_align_up((size_t)d.B * d.L * 16, 256);
-  if (use_ws && (rc = tlsan_launch_long_meta(a, meta, nullptr, nullptr, part, 3, st))) return rc;
+  // short-term metadata (scoring layout) behind the partition block: [B][S + 3] row pairs, [B] scalars
+  void* smeta = reinterpret_cast<char*>(part) + tlsan_align_up(tlsan_partition_bytes(), 256);
+  void* sscal = reinterpret_cast<char*>(smeta) + tlsan_align_up((size_t)d.B * (d.S + 3) * 8, 256);
+  if (use_ws && (rc = tlsan_launch_long_meta(a, meta, smeta, sscal, part, 3, ncand, st))) return rc;
   if ((rc = use_ws ? tlsan_launch_long_fwd_pf(a, meta, part, 3, st) : tlsan_launch_long_fwd_mma(a, 3, st))) return rc;
   if ((rc = tlsan_launch_dense_fwd(p.dense, scratch, d.B, st))) return rc;
+  if (use_ws) return tlsan_launch_score_pf(a, smeta, sscal, part, ncand, st);
   k_fwd_mma<3><<<mma_grid(d.B, 3), MMA_THREADS, 0, st>>>(a, ncand);
   TLSAN_CHECK_LAUNCH("k_fwd_mma<short score>");
   return TLSAN_OK;

@@ -104,13 +104,17 @@ __device__ __forceinline__ FwaW load_fwa_log2(const float* __restrict__ dense, i
 // rows (one sample each; smeta == NULL: scoring, long-term part only).  smeta[b][0] = candidate, [1] = user vector,
 // [2 + j] = session item j, each {row of the item / user half, row of the category half};
 // sscal[b] = {sl_new, candidate, y, item_b[candidate]}
+// score_ncand > 0: SCORING layout of the short-term metadata (k_pf_score): smeta[b][0] = candidate 1, [1] = user vector,
+// [2] = candidate 2 (= candidate 1 when there is only one), [3 + j] = session item j; sscal[b] = {sl_new, 0,
+// item_b[candidate 1], item_b[candidate 2]}
 __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta, int2* __restrict__ smeta,
-                                                   int4* __restrict__ sscal, int* __restrict__ counter, int counter0) {
+                                                   int4* __restrict__ sscal, int* __restrict__ counter, int counter0,
+                                                   int score_ncand) {
   const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nlong = (long long)a.B * a.L;
   pdl_wait();                                                   // usert / item_b: the previous step's update
   pdl_trigger();
-  if (gidx == 0 && counter) *counter = counter0;                // work counter of the long-term forward (k_pf_long<1>)
+  if (gidx == 0 && counter) { counter[0] = counter0; counter[1] = counter0; }   // work counters of k_pf_long<1> / k_pf_score
   if (gidx < nlong) {
     const int b = (int)(gidx / a.L), t = (int)(gidx - (long long)b * a.L);
     int4 m = make_int4(0, 0, 0, 0);
@@ -127,6 +131,25 @@ __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restri
   if (!smeta || bb >= a.B) return;
   const int b = (int)bb;
   const int cand = __ldg(a.i + b), u = __ldg(a.u + b), uc = __ldg(a.c + b), s = min(__ldg(a.sl_new + b), a.S);
+  if (score_ncand > 0) {
+    int2* out = smeta + (size_t)b * (a.S + 3);
+    const int* hn = a.hist_i_new + (size_t)b * a.S;
+    const int cand2 = score_ncand > 1 ? __ldg(a.i2 + b) : cand;
+    const int id0 = s > 0 ? __ldg(hn) : 0, id1 = s > 1 ? __ldg(hn + 1) : 0;
+    const int c1 = __ldg(a.icl + cand), c2 = __ldg(a.icl + cand2), c0i = __ldg(a.icl + id0), c1i = __ldg(a.icl + id1);
+    const float ib1 = __ldg(a.item_b + cand), ib2 = __ldg(a.item_b + cand2);
+    out[0] = make_int2(cand, a.NI + c1);
+    out[1] = make_int2(a.NI + a.NC + u, a.NI + uc);
+    out[2] = make_int2(cand2, a.NI + c2);
+    if (s > 0) out[3] = make_int2(id0, a.NI + c0i);
+    if (s > 1) out[4] = make_int2(id1, a.NI + c1i);
+    for (int j = 2; j < s; ++j) {
+      const int id = __ldg(hn + j);
+      out[3 + j] = make_int2(id, a.NI + __ldg(a.icl + id));
+    }
+    sscal[b] = make_int4(s, 0, __float_as_int(ib1), __float_as_int(ib2));
+    return;
+  }
   const float y = __ldg(a.y + b);
   int2* out = smeta + (size_t)b * (a.S + 2);
   const int* hn = a.hist_i_new + (size_t)b * a.S;
@@ -822,6 +845,145 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_short(const PsArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// short-term part of SCORING (tlsan_score_ws, Model.eval_auc): short FWA forward over [z ; e(hist_i_new)], u_t and the
+// logits of one or two candidates from the same u_t (model.py:135-137,251-261,350-364).  Same pipeline as k_pf_short
+// (metadata two samples ahead, rows one ahead), samples claimed dynamically like the long-term forward -- nothing is
+// accumulated across samples.  Replaces the round-robin k_fwd_mma<3>, whose per-sample chain
+// (u, sl_new, candidates -> icl -> rows) was exposed: 61 -> ~35 us at B 65 536.
+struct PscArgs {
+  FArgs a;
+  const int2* smeta;        // [B][S + 3]  (scoring layout of k_long_meta)
+  const int4* sscal;        // [B]
+  int* counter;             // next unclaimed sample (k_long_meta resets it to #warps * chunk)
+  int chunk, ncand;
+};
+#define PSC_ROWS (PS_RS + 3)                     // staged rows: PS_RS session items, candidate 1, user vector, candidate 2
+#define PSC_BUF (PSC_ROWS * 256 + 256)           // + z
+#define PSC_RING (16 + 35 * 8 + 8)               // int4 scalars ; int2 rows[3 + 32]
+#define PSC_PER_WARP ((2 * PSC_BUF + 3 * PSC_RING + 127) / 128 * 128)
+
+__global__ void __launch_bounds__(PF_THREADS, 3) k_pf_score(const PscArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FArgs& a = A.a;
+  LaneGeo L; L.init();
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * PF_WARPS + warp;
+  const int h = L.lane >> 4, c16 = L.lane & 15;
+  unsigned char* mine = smem + (size_t)warp * PSC_PER_WARP;
+  const FwaW w = load_fwa_log2(a.dense, TLSAN_OFF_W1S, L.g, L.t);
+  const int SW = a.S + 3;
+  auto ring = [&](int n) { return mine + 2 * PSC_BUF + (n % 3) * PSC_RING; };
+  int curEnd, nxt = a.B;
+  auto claim = [&]() -> int {
+    int v = 0;
+    if (L.lane == 0) v = atomicAdd(A.counter, A.chunk);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  auto succ = [&](int b) -> int {                 // the sample after b in this warp's sequence (a.B: none); once per sample
+    if (b >= a.B) return a.B;
+    if (b + 1 < curEnd) return b + 1;
+    const int nb = nxt;
+    if (nb >= a.B) return a.B;
+    curEnd = min(nb + A.chunk, a.B);
+    nxt = claim();
+    return nb;
+  };
+  auto issue_meta = [&](int b, unsigned char* dst) {
+    if (b >= a.B) return;
+    if (L.lane == 0) cp16_s(smem_addr(dst), A.sscal + b);
+    const uint32_t rp = smem_addr(dst) + 16;
+    for (int k = L.lane; k < min(SW, 35); k += 32) cp8_s(rp + k * 8, A.smeta + (size_t)b * SW + k);
+  };
+  auto issue_rows = [&](int b, const unsigned char* src, unsigned char* buf) {
+    if (b >= a.B) return;
+    const int s = reinterpret_cast<const int*>(src)[0];
+    const int2* rp = reinterpret_cast<const int2*>(src + 16);
+    const int n = min(s, PS_RS);
+    const uint32_t dst = smem_addr(buf) + c16 * 16;
+    const int col = (c16 & 7) * 4;
+    for (int r = h; r < n; r += 2) {
+      const int2 p = rp[3 + r];
+      cp16_s(dst + r * 256, a.emb + (size_t)(c16 < 8 ? p.x : p.y) * 32 + col);
+    }
+    {
+      const int2 p = rp[h];                                     // half 0: candidate 1, half 1: user vector
+      cp16_s(dst + (PS_RS + h) * 256, a.emb + (size_t)(c16 < 8 ? p.x : p.y) * 32 + col);
+    }
+    if (h == 0) {
+      const int2 p = rp[2];                                     // candidate 2
+      cp16_s(dst + (PS_RS + 2) * 256, a.emb + (size_t)(c16 < 8 ? p.x : p.y) * 32 + col);
+    } else {
+      cp16_s(dst + (PS_RS + 3) * 256, a.scratch + (size_t)b * (TLSAN_SCR * 64) + 320 + c16 * 4);   // z
+    }
+  };
+
+  pdl_wait();                                                   // z (k_dense_fwd_mma), smeta / sscal, the work counter
+  pdl_trigger();
+  int b0 = min(gw * A.chunk, a.B);
+  curEnd = min(b0 + A.chunk, a.B);
+  if (b0 < a.B) nxt = claim();
+  int b1 = succ(b0), b2 = succ(b1);
+  issue_meta(b0, ring(0));
+  issue_meta(b1, ring(1));
+  cp_commit();
+  cp_wait_group<0>();
+  __syncwarp();
+  issue_rows(b0, ring(0), mine);
+  cp_commit();
+
+  for (int n = 0; b0 < a.B; ++n) {
+    const int b = b0;
+    unsigned char* buf = mine + (size_t)(n & 1) * PSC_BUF;
+    cp_wait_group<0>();
+    __syncwarp();
+    issue_rows(b1, ring(n + 1), mine + (size_t)((n + 1) & 1) * PSC_BUF);
+    issue_meta(b2, ring(n + 2));
+    cp_commit();
+
+    const unsigned char* mr = ring(n);
+    const int4 sc4 = *reinterpret_cast<const int4*>(mr);
+    const int s = sc4.x;
+    const int2* rp = reinterpret_cast<const int2*>(mr + 16);
+    const float (*rows)[64] = reinterpret_cast<const float (*)[64]>(buf);
+    const int ntok = s + 1;
+    const float2 zz = *reinterpret_cast<const float2*>(&rows[PS_RS + 3][L.f0]);
+    auto item_x = [&](int it) -> float2 {        // session item `it`: staged row, else direct gather
+      if (it < PS_RS) return *reinterpret_cast<const float2*>(&rows[it][L.f0]);
+      int id, cr;
+      if (it < 32) { const int2 p = rp[3 + it]; id = p.x; cr = p.y; }
+      else { id = __ldg(a.hist_i_new + (size_t)b * a.S + it); cr = a.NI + __ldg(a.icl + id); }
+      return ldg2(a.emb + (size_t)(L.half ? cr : id) * 32 + L.col);
+    };
+    SoftL2 ss; ss.init();
+    for (int k = 0; k < ntok; k += 2) {
+      const bool okB = k + 1 < ntok;
+      float x[4];
+      if (k == 0) { x[0] = zz.x; x[1] = zz.y; } else { const float2 e = item_x(k - 1); x[0] = e.x; x[1] = e.y; }
+      if (okB) { const float2 e = item_x(k); x[2] = e.x; x[3] = e.y; } else { x[2] = 0.f; x[3] = 0.f; }
+      float m1[4], m2[4];
+      tile_maps(x, w, m1, m2);
+      if (!okB) { m2[2] = -INFINITY; m2[3] = -INFINITY; }
+      ss.push2(m2, x);
+    }
+    const float v[2] = {ss.acc[0] / ss.den[0], ss.acc[1] / ss.den[1]};
+    const float2 q1 = *reinterpret_cast<const float2*>(&rows[PS_RS][L.f0]);
+    const float2 p = *reinterpret_cast<const float2*>(&rows[PS_RS + 1][L.f0]);
+    const float ut[2] = {v[0] + p.x, v[1] + p.y};
+    const float l1 = warp_sum_f(fmaf(ut[0], q1.x, ut[1] * q1.y)) + __int_as_float(sc4.z);
+    if (L.lane == 0) a.logits[(size_t)b * A.ncand] = l1;
+    if (a.ut) st2(a.ut + (size_t)b * 64 + L.f0, ut[0], ut[1]);
+    if (A.ncand > 1) {                            // Model.eval_auc second run (model.py:251-261): same u_t, other item
+      const float2 q2 = *reinterpret_cast<const float2*>(&rows[PS_RS + 2][L.f0]);
+      const float l2 = warp_sum_f(fmaf(ut[0], q2.x, ut[1] * q2.y)) + __int_as_float(sc4.w);
+      if (L.lane == 0) a.logits[(size_t)b * A.ncand + 1] = l2;
+    }
+    __syncwarp();
+    b0 = b1; b1 = b2; b2 = succ(b2);
+  }
+  cp_wait_group<0>();
+}
+
 // ------------------------------------------------------------------ launchers
 size_t tlsan_long_meta_bytes(int B, int L) { return (size_t)B * L * sizeof(int4); }
 
@@ -832,11 +994,11 @@ static int* pf_counter(const void* part);
 static int pf_chunk();
 static int pf_grid(int B, int ctas_per_sm);
 int tlsan_launch_long_meta(const FArgs& a, void* meta, void* smeta, void* sscal, void* part, int fwd_ctas,
-                           cudaStream_t st) {
+                           int score_ncand, cudaStream_t st) {
   const long long n = (long long)a.B * a.L + (smeta ? a.B : 0);
   tlsan_launch_k(k_long_meta, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, reinterpret_cast<int4*>(meta),
                  reinterpret_cast<int2*>(smeta), reinterpret_cast<int4*>(sscal), pf_counter(part),
-                 pf_grid(a.B, fwd_ctas) * PF_WARPS * pf_chunk());
+                 pf_grid(a.B, fwd_ctas) * PF_WARPS * pf_chunk(), score_ncand);
   TLSAN_CHECK_LAUNCH("k_long_meta");
   return TLSAN_OK;
 }
@@ -941,5 +1103,24 @@ int tlsan_launch_short_pf(const FArgs& a, const void* smeta, const void* sscal, 
   if (grid_a) *grid_a = gr;
   tlsan_launch_k(k_pf_short, dim3(gr), dim3(PF_THREADS), (size_t)smem, st, A);
   TLSAN_CHECK_LAUNCH("k_pf_short");
+  return TLSAN_OK;
+}
+
+size_t tlsan_score_meta_bytes(int B, int S) {
+  return tlsan_align_up((size_t)B * (S + 3) * sizeof(int2), 256) + tlsan_align_up((size_t)B * sizeof(int4), 256);
+}
+int tlsan_launch_score_pf(const FArgs& a, const void* smeta, const void* sscal, const void* part, int ncand,
+                          cudaStream_t st) {
+  PscArgs A;
+  A.a = a; A.smeta = reinterpret_cast<const int2*>(smeta); A.sscal = reinterpret_cast<const int4*>(sscal);
+  A.counter = pf_counter(part) + 1; A.chunk = pf_chunk(); A.ncand = ncand;
+  const int smem = PSC_PER_WARP * PF_WARPS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLSAN_CHECK_CUDA(cudaFuncSetAttribute(k_pf_score, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  tlsan_launch_k(k_pf_score, dim3(pf_grid(a.B, 3)), dim3(PF_THREADS), (size_t)smem, st, A);
+  TLSAN_CHECK_LAUNCH("k_pf_score");
   return TLSAN_OK;
 }
