@@ -102,7 +102,9 @@ def test_train_step_matches_committed_golden(dm):
     (50, 1, 1, True, False), (40, 90, 5, False, False), (32, 90, 2, True, False),
     (257, 10, 4, False, True), (100, 37, 7, False, True),
     # occurrence-slot counts around the radix tile (5 120 slots = 160 samples of 32 slots) and the forward's claim size
-    (159, 10, 18, False, False), (160, 10, 18, True, False), (161, 10, 18, False, True), (321, 10, 18, False, False)])
+    (159, 10, 18, False, False), (160, 10, 18, True, False), (161, 10, 18, False, True), (321, 10, 18, False, False),
+    # a session longer than the ring slot of the short-term kernel (32 items): the tail is gathered directly
+    (48, 10, 40, False, False)])
 def test_train_step_edge_shapes(B, L, S, full, dup):
     rng = np.random.default_rng(B * 1000 + L)
     NU, NI, NC = 50, 301, 7
@@ -306,15 +308,23 @@ def test_save_restore_roundtrip(dm, dm_model, tmp_path):
         assert torch.equal(v, m2.state_dict()[k])
 
 
-def test_score_workspace_path_matches_fused_path_and_oracle():
+@pytest.mark.parametrize("S", [5, 18, 40])
+def test_score_workspace_path_matches_fused_path_and_oracle(S):
     """tlsan_score_ws (batched dense GEMM between the kernels, B >= 2048) vs tlsan_score vs oracle."""
-    rng = np.random.default_rng(17)
-    NU, NI, NC, L, S, B = 300, 2000, 13, 10, 5, 3001
+    rng = np.random.default_rng(17 + S)
+    NU, NI, NC, L, B = 300, 2000, 13, 10, 3001
     cfg = _cfg(NU, NI, NC, L)
     params = _params(cfg)
     icl = rng.integers(0, NC, NI).astype(np.int32)
     model = model_from_params(params, icl, cfg)
     batch = synth_batch(rng, B, L, S, NI, NU, NC, is_test=True)
+    if S > 6:       # long sessions: rows beyond the staged ones (6) and beyond the ring slot (32) are gathered directly
+        batch = list(batch)
+        long_rows = rng.choice(B, 200, replace=False)
+        batch[7][long_rows] = rng.integers(max(1, S - 10), S + 1, 200)
+        batch[4][long_rows] = rng.integers(0, NI, (200, S))
+        batch[4][np.arange(S)[None, :] >= batch[7][:, None]] = 0
+        batch = tuple(batch)
     db = model.stage_batch(batch, is_test=True)
     lg_ws, ut_ws = model.score_staged(db, 2, want_ut=True)            # B >= 2048 -> workspace path
     dims = model._dims(db.B, db.S)
@@ -324,7 +334,7 @@ def test_score_workspace_path_matches_fused_path_and_oracle():
                                       ut.data_ptr(), model._stream()))
     assert rel_err(lg_ws.cpu().numpy(), lg.cpu().numpy()) < 5e-5     # two summation orders of the same fp32 math
     assert rel_err(ut_ws.cpu().numpy(), ut.cpu().numpy()) < 5e-5
-    rows = rng.choice(B, 300, replace=False)
+    rows = np.concatenate([rng.choice(B, 300, replace=False), np.argsort(-np.asarray(batch[7]))[:40]])   # + the longest sessions
     sub = tuple(np.asarray(f)[rows] for f in batch)
     r1, _ = O.forward_logits(params, icl, sub, 1, config=cfg)
     r2, _ = O.forward_logits(params, icl, sub, 2, config=cfg)
