@@ -196,8 +196,10 @@ int tlsan_apply_flat_opt(const tlsan_dims_t* dims, const tlsan_params_t* p, cons
  * fused reduce-scatter + optimiser step + all-gather.  Every rank owns an ARENA that its peers map through CUDA
  * IPC and passes it to tlsan_step_grads as the `flat` gradient buffer; rank r then sums slice r of the weight index
  * space out of all arenas (peer memory, fixed rank order: deterministic, identical on every rank), applies
- * L2 + clip + SGD to that slice, publishes it, and every rank pulls the other slices; ranks meet at two
- * release / acquire flags in the arenas.  The tables must be ONE device buffer: emb [(NI+NC+NU)*32] |
+ * L2 + clip + SGD to that slice, publishes it, and every rank pulls the other slices; ranks meet at three
+ * release / acquire flags in the arenas (dense-gradient / norm partials ready -- that small exchange runs early, on
+ * the library's side stream beside the segmented row reduce --, gradient rows ready, updated slice published).
+ * The tables must be ONE device buffer: emb [(NI+NC+NU)*32] |
  * usert [NU*L, padded to 4] | item_b [NI, padded to 4], with params->usert / item_b pointing into it.
  *   tlsan_dp_arena_bytes / _create / _open / _release : arena size for (dims, world); cudaMalloc + IPC handle
  *       (64 bytes, to be exchanged by the host, e.g. torch.distributed.all_gather_object); map a peer's arena.
