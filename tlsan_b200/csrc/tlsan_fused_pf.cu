@@ -110,11 +110,17 @@ __device__ __forceinline__ FwaW load_fwa_log2(const float* __restrict__ dense, i
 __global__ void __launch_bounds__(256) k_long_meta(const FArgs a, int4* __restrict__ meta, int2* __restrict__ smeta,
                                                    int4* __restrict__ sscal, int* __restrict__ counter, int counter0,
                                                    int score_ncand) {
-  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // the per-sample threads of the short-term part have the longest dependent chain (candidate -> icl / item_b, session
+  // ids -> icl, a loop for long sessions): they get the FIRST blocks so that the per-token threads run beside them
+  // instead of the kernel ending on them
+  const long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nshort = smeta ? a.B : 0;
   const long long nlong = (long long)a.B * a.L;
+  const long long gidx = g0 < nshort ? nlong + g0 : g0 - nshort;   // index in the original (tokens, then samples) order
   pdl_wait();                                                   // usert / item_b: the previous step's update
   pdl_trigger();
-  if (gidx == 0 && counter) { counter[0] = counter0; counter[1] = counter0; }   // work counters of k_pf_long<1> / k_pf_score
+  if (g0 == 0 && counter) { counter[0] = counter0; counter[1] = counter0; }   // work counters of k_pf_long<1> / k_pf_score
+  if (g0 >= nlong + nshort) return;
   if (gidx < nlong) {
     const int b = (int)(gidx / a.L), t = (int)(gidx - (long long)b * a.L);
     int4 m = make_int4(0, 0, 0, 0);
