@@ -270,13 +270,25 @@ def test_prec_recall_match_oracle(dm, dm_model):
     cfg, params, model = dm_model
     model.reset_metrics()
     st_p, st_r = O.StreamingTopK(), O.StreamingTopK()
+    seen = near = 0
     for lo in range(0, 512, 128):
         batch = O.collate_test(dm.test_set[lo:lo + 128], 10)
         scores = O.eval_logits_all(params, dm.icl, batch, dtype=torch.float64, config=cfg)
         p_ref, _ = st_p.update(scores, batch[1])
         _, r_ref = st_r.update(scores, batch[1])
         p = model.eval_prec(None, batch); r = model.eval_recall(None, batch)
-        assert np.allclose(p, p_ref, atol=2e-3) and np.allclose(r, r_ref, atol=1e-2)
+        # exact, except for rows whose label score has a competitor within fp32 reach (2e-5 relative): only those can
+        # change rank between the fp64 oracle and the fp32 kernels; each moves a cumulative metric by at most 1 / rows
+        sc = np.asarray(scores, np.float64)
+        lab = np.asarray(batch[1], np.int64)
+        sl = sc[np.arange(len(lab)), lab]
+        d = np.abs(sc - sl[:, None]); d[np.arange(len(lab)), lab] = np.inf
+        near += int(np.sum(d.min(axis=1) <= 2e-5 * np.maximum(1.0, np.abs(sl))))
+        seen += len(lab)
+        ks = np.array([1, 10, 20, 30, 40, 50], np.float64)                      # model.py:144-156
+        assert np.all(np.abs(np.asarray(r) - np.asarray(r_ref)) <= near / seen + 1e-9), (r, r_ref, near)
+        assert np.all(np.abs(np.asarray(p) - np.asarray(p_ref)) <= near / (seen * ks) + 1e-9), (p, p_ref, near)
+    assert near <= 8, near                                                    # the test must stay (almost) exact
     assert np.isclose(model.prec_10.eval(), p[1]) and np.isclose(model.recall_50.eval(), r[5])
 
 
