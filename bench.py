@@ -437,6 +437,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of back-to-back steps in the sustained leg")
     ap.add_argument("--skip-extras", action="store_true", help="profiling runs: only the device-resident leg")
+    ap.add_argument("--dp-parity", action="store_true", help="with --skip-extras at N > 1: still run the dp_parity check")
     ap.add_argument("--no-pipeline", action="store_true", help="do not presort the next batch behind the current step")
     ap.add_argument("--workload", default="electronics", choices=sorted(WORKLOADS))
     ap.add_argument("--strong", action="store_true", help="fixed GLOBAL batch: every rank gets batch / N rows")
@@ -492,9 +493,16 @@ def main():
     phases_ms = {n: float(v) for n, v in zip(_lib.PHASES, ph)}
 
     if args.skip_extras:
+        short = {"ms_per_step": ms / args.steps, "phases_ms": phases_ms,
+                 "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps}
+        if args.dp_parity and world > 1:          # profiling-style run that still checks multi-GPU correctness
+            try:
+                short["dp_parity"] = dp_parity(ctx)
+            except Exception as e:
+                short["dp_parity"] = {"error": repr(e)[:300]}
+            ctx.barrier()
         if rank == 0:
-            _emit({"ms_per_step": ms / args.steps, "phases_ms": phases_ms,
-                   "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps})
+            _emit(short)
         if clocks:
             clocks.stop()
         if world > 1:
