@@ -18,7 +18,8 @@ L2 + clip + SGD over every table row).  ONE JSON line on stdout:
   roofline         SURVEY 8d byte model: the whole step (headline) and the dominant kernel, against MEASURED_PEAKS.json
   cpu_baseline     the oracle port on the host cores, bounded sample (rank 0, N = 1)
   dp_parity        N > 1: a fixed global batch trained data-parallel (nccl / p2p exchange) and row-sharded must give
-                   bit-identical weights on every rank and the weights of a 1-rank step
+                   bit-identical weights on every rank and the weights of a 1-rank step (also with
+                   --skip-extras --dp-parity)
   dataset_resident, eval, eval_rank, movies (configs[2], weak + strong), scoring_sweep (configs[3]),
   sharded_10M (configs[4]): the other BASELINE configurations, compact.
 """
