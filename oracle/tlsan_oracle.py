@@ -12,9 +12,17 @@ image (python 3.12, no network); its published op semantics are restated here an
 function cites the reference call site it follows.
 
 PARITY STATUS
-  * model arithmetic: **parity unpinned** -- the reference has no tests, golden vectors
-    or fixtures for this path and TF cannot execute here.  The
-    only external anchor is README.md:35 (Digital-Music AUC 0.9753).
+  * model arithmetic: the reference has no tests, golden vectors or fixtures for this path
+     and TF cannot execute here.  **Pinned to the reference's own graph
+    code**: ``oracle/make_model_golden.py`` imports the UNMODIFIED ``TLSAN/model.py`` with
+    ``tensorflow`` bound to ``oracle/tf1_shim.py`` (an eager torch restatement of the ~50 public
+    TF-1.8 API entries the file calls) and executes build_model / attention_net / init_optimizer
+    on fixed Digital-Music batches; this oracle reproduces the recorded loss, logits, every
+    gradient and the updated weights to 1e-10 in float64
+    (``tests/golden/model_ref_graph.npz``, ``tests/test_reference_graph.py``).  **Still
+    unpinned**: TF's own kernels and TF-internal gradient plumbing (items 1-3 below) -- no
+    TensorFlow output exists to compare with; external anchor README.md:35 (Digital-Music
+    AUC 0.9753).
   * data path (batch layout, time buckets): **pinned** -- ``tests/golden/`` holds
     outputs of the *unmodified* reference ``TLSAN/input.py`` and ``TLSAN/build_dataset.py``
     executed in the build container by ``oracle/make_golden.py``.

@@ -54,6 +54,35 @@ def test_score_matches_committed_golden(dm, dm_model):
     assert round(float(model.eval_auc(None, batch)), 4) == round(float(g["test_f64_auc"]), 4)
 
 
+def test_cuda_matches_the_reference_graph_vectors(dm):
+    """The CUDA path against vectors produced by EXECUTING the reference's own graph code (TLSAN/model.py, unmodified,
+    on the TF-1.8 API shim -- oracle/make_model_golden.py): both eval_auc logits, the train loss and the weights after
+    one sgd step.  tests/test_reference_graph.py checks the oracle against the same vectors at 1e-10."""
+    import os
+    from tests.util import GOLD
+    g = np.load(os.path.join(GOLD, "model_ref_graph.npz"))
+    assert int(g["param_seed"]) == 7
+    cfg = _cfg(*dm.counts)
+    params = _params(cfg)
+    model = model_from_params(params, dm.icl, cfg)
+    lo, hi = (int(x) for x in g["test_rows"])
+    tb = O.collate_test(dm.test_set[lo:hi], 10)
+    assert rel_err(model.logits(tb, 1), g["test/logits_pos"]) < TOL
+    assert rel_err(model.logits(tb, 2), g["test/logits_neg"]) < TOL
+    lo, hi = (int(x) for x in g["train_rows"])
+    lr = float(g["lr"])
+    loss = model.train(None, O.collate_train(dm.train_set[lo:hi], 10), lr)
+    assert abs(loss - float(g["train/loss"])) / float(g["train/loss"]) < TOL
+    sd = model.state_dict()
+    for k in params:
+        v = g["train/new/" + k]
+        got = sd[k].numpy()
+        step = np.asarray(params[k], np.float64) - v         # lr * grad
+        err = np.max(np.abs(got - v))
+        bound = TOL * (np.max(np.abs(step)) + 1e-7) + 2e-7 * np.max(np.abs(v))
+        assert err <= bound, (k, err, bound)
+
+
 def _check_step(params, icl, cfg, batch, lr=1.0, **kw):
     ref = O.train_step(params, icl, batch, lr, cfg, dtype=torch.float64)
     model = model_from_params(params, icl, cfg, **kw)
