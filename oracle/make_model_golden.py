@@ -10,7 +10,9 @@ fixed Digital-Music batches, so constructing ``Model(config, item_cate_list)`` e
 ``attention_net`` / ``feature_wise_attention`` and helpers (:316-483) and ``init_optimizer`` (:185-205) exactly as the
 reference wrote them.  Recorded, in float64:
 
-  train/   loss, logits, every variable's gradient (tf.gradients), global norm, the weights after apply_gradients (sgd)
+  train/   loss, logits, every variable's gradient (tf.gradients), global norm (dense-gradient reading and the TF-1.8
+           un-aggregated IndexedSlices reading over the lookups the graph really makes), the weights after
+           apply_gradients (sgd)
   test/    logits of the positive and the negative candidate (Model.eval_auc's two runs), eval_logits of 8 rows
 
 What this pins: the graph the reference builds (which ops, in which order, on which shapes, with which masks and
@@ -71,7 +73,8 @@ def main():
     m, st = run_reference_graph(cfg, dm.icl, params, feeds_of(batch, LR, 1, np.asarray(batch[2], np.float32)))
     out["train/loss"] = np.float64(m.loss.detach())
     out["train/logits"] = m.logits.detach().numpy()
-    out["train/norm"] = np.float64(st.last_norm)
+    out["train/norm"] = np.float64(st.last_norm)                    # norm of the dense (summed) gradient
+    out["train/norm_tf"] = np.float64(st.last_norm_tf)              # TF-1.8 reading: un-aggregated IndexedSlices values
     assert set(st.last_grads) == set(params), sorted(set(st.last_grads) ^ set(params))
     for k, v in st.last_grads.items():
         out["train/grad/" + k] = v

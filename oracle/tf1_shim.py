@@ -14,9 +14,11 @@ How it works: ``install(feeds, variables, dtype)`` puts this module into ``sys.m
   (``t * clip / max(norm, clip)``), ``GradientDescentOptimizer.apply_gradients`` to ``w - lr * g``.
 
 Every op below restates the documented TF-1.8 semantics of ONE public API entry; nothing here knows about TLSAN.
+``gradients`` additionally evaluates the global norm the way TF 1.8 does on the output of tf.gradients (one
+IndexedSlices per lookup into a variable, concatenated un-aggregated, ``global_norm`` squares ``.values``) over the
+lookups the executed graph really made -- a restatement of TF internals from its sources, applied generically.
 What this does NOT reproduce: TF's kernels' floating-point summation order (the run is done in float64 to take
-rounding out of the comparison) and TF-internal gradient plumbing (IndexedSlices, un-aggregated global norm) -- see
-DESIGN.md section 2.
+rounding out of the comparison) -- see DESIGN.md section 2.
 """
 import contextlib
 import sys
@@ -26,7 +28,7 @@ import numpy as np
 import torch
 
 _S = types.SimpleNamespace(feeds=None, feed_i=0, variables=None, dtype=torch.float64, scope=[], trainable=[],
-                           created={}, last_grads=None, last_norm=None, applied=None)
+                           created={}, last_grads=None, last_norm=None, last_norm_tf=None, applied=None, slices=[])
 
 float32 = "float32"
 int32 = "int32"
@@ -51,8 +53,8 @@ def install(feeds, variables, dtype=torch.float64):
     """feeds: list of values in placeholder creation order; variables: {tf variable name: numpy array}."""
     _S.feeds, _S.feed_i, _S.dtype = list(feeds), 0, dtype
     _S.variables = {k: np.asarray(v) for k, v in variables.items()}
-    _S.scope, _S.trainable, _S.created = [], [], {}
-    _S.last_grads = _S.last_norm = _S.applied = None
+    _S.scope, _S.trainable, _S.created, _S.slices = [], [], {}, []
+    _S.last_grads = _S.last_norm = _S.last_norm_tf = _S.applied = None
     sys.modules["tensorflow"] = sys.modules[__name__]
     return sys.modules[__name__]
 
@@ -185,10 +187,19 @@ def tile(x, multiples):
     return x.repeat(*[int(m) for m in multiples])
 
 
+def _lookup(params, ids):
+    """params[ids] along axis 0.  A lookup into a trainable variable is remembered: its gradient is ONE IndexedSlices
+    of tf.gradients (values = the gradient of this output, indices = ids), see gradients() below."""
+    out = params[ids]
+    if isinstance(params, torch.Tensor) and hasattr(params, "tf_name"):
+        _S.slices.append((params.tf_name, ids, out))
+    return out
+
+
 def gather(params, indices):
     """tf.gather along axis 0; params may be a python list (item_cate_list)."""
     p = params if isinstance(params, torch.Tensor) else torch.as_tensor(np.asarray(params), dtype=torch.int64)
-    return p[indices]
+    return _lookup(p, indices)
 
 
 def multiply(a, b):
@@ -230,7 +241,7 @@ def cond(pred, true_fn, false_fn):
 class _NN:
     @staticmethod
     def embedding_lookup(params, ids):
-        return params[ids]
+        return _lookup(params, ids)
 
     @staticmethod
     def l2_loss(t):
@@ -287,9 +298,28 @@ contrib = _Contrib()
 
 # ----------------------------------------------------------------------------------------------- gradients / optimizer
 def gradients(ys, xs):
-    g = torch.autograd.grad(ys, xs, allow_unused=True)
-    g = [torch.zeros_like(x) if gi is None else gi for gi, x in zip(g, xs)]
+    """Dense gradients (what apply_gradients ends up applying), plus the global norm AS TF 1.8 COMPUTES IT on the
+    output of tf.gradients: every lookup into a variable contributes one IndexedSlices whose `.values` are the
+    gradient of that lookup's output; gradients_impl._AggregatedGrads CONCATENATES the slices of a variable
+    (a dense contribution, e.g. d l2_loss, becomes one more slice over all rows) without summing duplicate rows, and
+    clip_ops.global_norm squares `.values` -- so norm_tf^2 = sum over variables of
+    (sum over its lookups |d out|^2  +  |dense remainder|^2).  Restated from the TF-1.8 sources; the lookups are the
+    ones the reference graph really makes."""
+    outs = [o for (_, _, o) in _S.slices]
+    both = torch.autograd.grad(ys, list(xs) + outs, allow_unused=True)
+    g = [torch.zeros_like(x) if gi is None else gi for gi, x in zip(both[:len(xs)], xs)]
     _S.last_grads = {x.tf_name: gi.detach().numpy().copy() for gi, x in zip(g, xs)}
+    sq = 0.0
+    for x, gi in zip(xs, g):
+        rest = gi.detach().clone()
+        for (name, ids, o), go in zip(_S.slices, both[len(xs):]):
+            if name != x.tf_name or go is None:
+                continue
+            sq += float((go * go).sum())
+            idx = torch.as_tensor(np.asarray(ids)).reshape(-1) if not isinstance(ids, torch.Tensor) else ids.reshape(-1)
+            rest.index_add_(0, idx, -go.detach().reshape((idx.numel(),) + tuple(rest.shape[1:])))
+        sq += float((rest * rest).sum())
+    _S.last_norm_tf = sq ** 0.5
     return list(g)
 
 

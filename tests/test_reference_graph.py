@@ -35,7 +35,11 @@ def test_train_step_equals_the_reference_graph(ctx):
     ref = O.train_step(params, dm.icl, batch, float(g["lr"]), cfg, dtype=torch.float64, clip_mode="agg")
     _close(ref["loss"], g["train/loss"])
     _close(ref["norm_agg"], g["train/norm"])
-    assert ref["scale"] == 1.0                      # clip inactive: the un-aggregated (TF-internal) reading agrees
+    # the TF-1.8 reading of the global norm (un-aggregated IndexedSlices values), evaluated by the shim over the
+    # lookups the reference graph really makes, equals the oracle's own bookkeeping of those slices
+    _close(ref["norm_tf"], g["train/norm_tf"])
+    assert abs(ref["norm_tf"] - ref["norm_agg"]) > 1e-2 * ref["norm_agg"]          # the two readings really differ
+    assert ref["scale"] == 1.0                      # clip inactive on this batch
     for k in params:
         _close(ref["grads"][k], g["train/grad/" + k])
         _close(ref["new_params"][k], g["train/new/" + k])
