@@ -14,6 +14,8 @@ reference wrote them.  Recorded, in float64:
            un-aggregated IndexedSlices reading over the lookups the graph really makes), the weights after
            apply_gradients (sgd)
   test/    logits of the positive and the negative candidate (Model.eval_auc's two runs), eval_logits of 8 rows
+  <shape>/ the same train quantities as digests (logits, loss, norms, sum |gradient| per variable) on synthetic batches of
+           the BASELINE shapes: Electronics (B 512), Movies-TV (B 512), Electronics with Ls 90 (B 64)
 
 What this pins: the graph the reference builds (which ops, in which order, on which shapes, with which masks and
 variable scopes).  What it cannot pin: TF's own kernels (summation order; irrelevant in float64) and TF-internal
@@ -36,6 +38,9 @@ TRAIN_ROWS = (0, 64)          # dm.train_set[0:64]
 TEST_ROWS = (0, 64)           # dm.test_set[0:64]
 LR = 1.0
 PARAM_SEED = 7
+SHAPE_SEED = 1234
+# (tag, workload of tlsan_b200/synth.py, batch, Ls)
+SHAPES = (("electronics", "electronics", 512, 10), ("movies", "movies", 512, 10), ("electronics_L90", "electronics", 64, 90))
 
 
 def run_reference_graph(config, icl, params, feeds):
@@ -87,6 +92,24 @@ def main():
     out["test/eval_logits"] = m1.eval_logits.detach().numpy()[:8]              # model.py:140  (eval_prec / eval_recall)
     m2, _ = run_reference_graph(cfg, dm.icl, params, feeds_of(tb, 0.0, 2))      # second run: self.i = batch[2]  (:251-261)
     out["test/logits_neg"] = m2.logits.detach().numpy()
+
+    # ---- digests on the BASELINE shapes (synthetic generators of tlsan_b200/synth.py): logits in full, loss, both norms
+    # and sum |gradient| per variable -- enough to pin the graph on 18-wide sessions, Ls = 90, 15 huge categories
+    from tlsan_b200 import synth
+    for tag, workload, B, L in SHAPES:
+        _, NU, NI, NC = synth.WORKLOADS[workload]
+        rng = np.random.default_rng(SHAPE_SEED)
+        scfg = O.default_config(NU, NI, NC, Ls=L)
+        sicl = rng.integers(0, NC, NI).astype(np.int32)
+        sb = synth.synth_batches(rng, 1, B, L, NU, NI, NC)[0]
+        sp = O.randomize_params(O.init_params(scfg), seed=PARAM_SEED, scale=0.2)
+        ms, sts = run_reference_graph(scfg, sicl, sp, feeds_of(sb, LR, 1, np.asarray(sb[2], np.float32)))
+        out[tag + "/loss"] = np.float64(ms.loss.detach())
+        out[tag + "/logits"] = ms.logits.detach().numpy()
+        out[tag + "/norm"] = np.float64(sts.last_norm)
+        out[tag + "/norm_tf"] = np.float64(sts.last_norm_tf)
+        for k, v in sts.last_grads.items():
+            out[tag + "/gradabs/" + k] = np.float64(np.abs(v).sum())
 
     os.makedirs(GOLD, exist_ok=True)
     path = os.path.join(GOLD, "model_ref_graph.npz")

@@ -58,6 +58,30 @@ def test_scoring_equals_the_reference_graph(ctx):
     _close(np.asarray(sc)[:8], g["test/eval_logits"])
 
 
+@pytest.mark.parametrize("tag,workload,B,L", [("electronics", "electronics", 512, 10), ("movies", "movies", 512, 10),
+                                              ("electronics_L90", "electronics", 64, 90)])
+def test_baseline_shapes_equal_the_reference_graph(ctx, tag, workload, B, L):
+    """synthetic batches of the BASELINE shapes (18-wide sessions, Ls = 90, 15 huge categories) through the reference
+    graph: logits in full, loss, both readings of the global norm, sum |gradient| per variable"""
+    from oracle import make_model_golden as G
+    from tlsan_b200 import synth
+    g = ctx[0]
+    _, NU, NI, NC = synth.WORKLOADS[workload]
+    rng = np.random.default_rng(G.SHAPE_SEED)
+    cfg = O.default_config(NU, NI, NC, Ls=L)
+    icl = rng.integers(0, NC, NI).astype(np.int32)
+    batch = synth.synth_batches(rng, 1, B, L, NU, NI, NC)[0]
+    params = O.randomize_params(O.init_params(cfg), seed=G.PARAM_SEED, scale=0.2)
+    ref = O.train_step(params, icl, batch, G.LR, cfg, dtype=torch.float64)
+    _close(ref["loss"], g[tag + "/loss"])
+    _close(ref["norm_agg"], g[tag + "/norm"])
+    _close(ref["norm_tf"], g[tag + "/norm_tf"])
+    r1, _ = O.forward_logits(params, icl, batch, 1, dtype=torch.float64, config=cfg)
+    _close(r1, g[tag + "/logits"])
+    for k in params:
+        _close(np.abs(np.asarray(ref["grads"][k], np.float64)).sum(), g[tag + "/gradabs/" + k], tol=1e-9)
+
+
 def test_fp32_oracle_is_within_the_product_tolerance_of_the_reference_graph(ctx):
     """the float32 evaluation (what the CUDA kernels are compared with at 1e-4) against the float64 reference graph"""
     g, dm, cfg, params = ctx
