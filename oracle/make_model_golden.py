@@ -54,7 +54,11 @@ def run_reference_graph(config, icl, params, feeds):
     assert os.path.realpath(ref_model.__file__).startswith("/root/reference/"), ref_model.__file__
     cfg = dict(config)
     cfg["model_dir"] = "/tmp/tlsan_ref_graph"
-    m = ref_model.Model(cfg, [int(c) for c in icl])
+    try:
+        m = ref_model.Model(cfg, [int(c) for c in icl])
+    finally:                                                 # leave no fake `tensorflow` / reference `model` module behind
+        sys.modules.pop("tensorflow", None)
+        sys.modules.pop("model", None)
     return m, tf1_shim.state()
 
 
